@@ -1,0 +1,218 @@
+"""ctypes binding of libdiee_cuda.so (include/diee.h).  No CPU fallback: a missing library or a
+missing CUDA device raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdiee_cuda.so")
+
+OK = 0
+ERR_INVALID, ERR_CUDA, ERR_NO_MOVES_PANIC, ERR_OVERFLOW, ERR_NOT_ROLLED = -1, -2, -3, -4, -5
+MAX_MOVES = 256
+NONE = -2
+ACTION_SPACE = 1352
+GAME_BACKGAMMON, GAME_TICTACTOE = 0, 1
+STREAM_INIT, STREAM_GAME, STREAM_ROLLOUT, STREAM_EXPAND, STREAM_DIRICHLET, STREAM_SAMPLE = range(6)
+MODE_ROLLOUT_CHECK_CURRENT = 1
+MODE_PASS_CHILD = 2
+
+BG_STATE = np.dtype([("pts", "i1", (24,)), ("bar", "u1", (2,)), ("off", "u1", (2,)),
+                     ("roll", "u1", (2,)), ("player", "i1"), ("second", "u1")])
+MOVE = np.dtype([("from1", "i1"), ("to1", "i1"), ("from2", "i1"), ("to2", "i1")])
+TTT_STATE = np.dtype([("board", "i1", (9,)), ("player", "i1"), ("pad", "u1", (6,))])
+MCTS_CFG = np.dtype([("iterations", "u4"), ("c", "f4"), ("simulate_round_limit", "u4"),
+                     ("dirichlet_alpha", "f4"), ("dirichlet_epsilon", "f4"), ("mode_flags", "u4")])
+NODE = np.dtype([("parent", "i4"), ("visits", "f4"), ("value", "f4"), ("action", MOVE),
+                 ("n_moves", "i4"), ("n_untried", "i4")])
+assert BG_STATE.itemsize == 32 and MOVE.itemsize == 4 and TTT_STATE.itemsize == 16 and NODE.itemsize == 24
+
+# every symbol include/diee.h declares (tests check the .so exports each one)
+SYMBOLS = [
+    "diee_ctx_create", "diee_ctx_destroy", "diee_ctx_set_stream", "diee_sync", "diee_last_error", "diee_version",
+    "diee_launch_count", "diee_dev_alloc", "diee_dev_free", "diee_dev_upload", "diee_dev_download", "diee_philox",
+    "diee_bg_valid_moves", "diee_bg_valid_moves_dev", "diee_bg_apply_moves", "diee_bg_apply_moves_dev",
+    "diee_bg_playout", "diee_bg_playout_dev", "diee_bg_encode_moves", "diee_bg_decode_moves",
+    "diee_bg_encode_states", "diee_bg_encode_states_dev", "diee_mcts_search", "diee_mcts_search_dev",
+]
+
+
+class DieeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"diee error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """loads libdiee_cuda.so; raises if it has not been built (python -m die_e_b200.build)"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python die_e_b200/build.py` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.diee_last_error.restype = C.c_char_p
+        L.diee_last_error.argtypes = [C.c_void_p]
+        L.diee_version.restype = C.c_char_p
+        L.diee_launch_count.restype = C.c_int64
+        L.diee_launch_count.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))  # raw device pointer
+
+
+def philox(seed, c0, c1, c2, c3):
+    out = np.zeros(4, dtype=np.uint32)
+    lib().diee_philox(C.c_uint64(seed), C.c_uint32(c0), C.c_uint32(c1), C.c_uint32(c2), C.c_uint32(c3), _p(out))
+    return out
+
+
+def die_of(w):
+    return 1 + ((int(w) * 6) >> 32)
+
+
+def index_of(w, n):
+    return (int(w) * n) >> 32
+
+
+class Context:
+    """one diee_ctx (one GPU)"""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p(0)
+        rc = lib().diee_ctx_create(C.c_int32(device), C.byref(self._h))
+        if rc != OK:
+            raise DieeError(rc, "diee_ctx_create failed: no usable CUDA device (there is no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().diee_ctx_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise DieeError(rc, lib().diee_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream):
+        self._chk(lib().diee_ctx_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+
+    def sync(self):
+        self._chk(lib().diee_sync(self._h))
+
+    def launch_count(self):
+        return int(lib().diee_launch_count(self._h))
+
+    # ---- env, host buffers ----
+    def bg_valid_moves(self, states, want_ids=False):
+        states = np.ascontiguousarray(states, dtype=BG_STATE).reshape(-1)
+        n = len(states)
+        moves = np.zeros((n, MAX_MOVES), dtype=MOVE)
+        counts = np.zeros(n, dtype=np.int32)
+        ids = np.zeros((n, MAX_MOVES), dtype=np.uint16) if want_ids else None
+        self._chk(lib().diee_bg_valid_moves(self._h, _p(states), C.c_int32(n), _p(moves), _p(counts), _p(ids)))
+        return (moves, counts, ids) if want_ids else (moves, counts)
+
+    def bg_apply_moves(self, states, moves, next_rolls):
+        states = np.ascontiguousarray(states, dtype=BG_STATE).reshape(-1).copy()
+        moves = np.ascontiguousarray(moves, dtype=MOVE).reshape(-1)
+        next_rolls = np.ascontiguousarray(next_rolls, dtype=np.uint8).reshape(-1)
+        assert len(moves) == len(states) and len(next_rolls) == 2 * len(states)
+        self._chk(lib().diee_bg_apply_moves(self._h, _p(states), _p(moves), _p(next_rolls), C.c_int32(len(states))))
+        return states
+
+    def bg_playout(self, starts, seed, first_game_id=0, round_limit=400, want_finals=False):
+        starts = np.ascontiguousarray(starts, dtype=BG_STATE).reshape(-1)
+        n = len(starts)
+        winners = np.zeros(n, dtype=np.int8)
+        plies = np.zeros(n, dtype=np.int32)
+        finals = np.zeros(n, dtype=BG_STATE) if want_finals else None
+        self._chk(lib().diee_bg_playout(self._h, _p(starts), C.c_int32(n), C.c_uint64(seed), C.c_uint32(first_game_id),
+                                        C.c_int32(round_limit), _p(winners), _p(plies), _p(finals)))
+        return (winners, plies, finals) if want_finals else (winners, plies)
+
+    def bg_encode_moves(self, states, moves):
+        states = np.ascontiguousarray(states, dtype=BG_STATE).reshape(-1)
+        moves = np.ascontiguousarray(moves, dtype=MOVE).reshape(-1)
+        ids = np.zeros(len(states), dtype=np.uint16)
+        self._chk(lib().diee_bg_encode_moves(self._h, _p(states), _p(moves), C.c_int32(len(states)), _p(ids)))
+        return ids
+
+    def bg_decode_moves(self, states, ids):
+        states = np.ascontiguousarray(states, dtype=BG_STATE).reshape(-1)
+        ids = np.ascontiguousarray(ids, dtype=np.uint16).reshape(-1)
+        moves = np.zeros(len(states), dtype=MOVE)
+        self._chk(lib().diee_bg_decode_moves(self._h, _p(states), _p(ids), C.c_int32(len(states)), _p(moves)))
+        return moves
+
+    def bg_encode_states(self, states):
+        states = np.ascontiguousarray(states, dtype=BG_STATE).reshape(-1)
+        out = np.zeros((len(states), 6, 4, 6), dtype=np.float32)
+        self._chk(lib().diee_bg_encode_states(self._h, _p(states), C.c_int32(len(states)), _p(out)))
+        return out
+
+    # ---- pure MCTS, host buffers ----
+    def mcts_search(self, game_kind, states, players, cfg, seed, first_game_id=0, epoch=0, dump=False):
+        sdt = BG_STATE if game_kind == GAME_BACKGAMMON else TTT_STATE
+        states = np.ascontiguousarray(states, dtype=sdt).reshape(-1)
+        n = len(states)
+        players = np.ascontiguousarray(players, dtype=np.int8).reshape(-1)
+        assert len(players) == n
+        cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]
+        best = np.zeros(n, dtype=MOVE) if game_kind == GAME_BACKGAMMON else np.zeros(n, dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int32)
+        plies = np.zeros(n, dtype=np.uint64)
+        cap = int(cfg["iterations"][0]) + 1
+        nodes = np.zeros((n, cap), dtype=NODE) if dump else None
+        nstates = np.zeros((n, cap), dtype=sdt) if dump else None
+        n_nodes = np.zeros(n, dtype=np.int32) if dump else None
+        self._chk(lib().diee_mcts_search(self._h, C.c_int32(game_kind), _p(states), C.c_int32(n), _p(players), _p(cfg),
+                                         C.c_uint64(seed), C.c_uint32(first_game_id), C.c_uint32(epoch), _p(best),
+                                         _p(status), _p(nodes), _p(nstates), _p(n_nodes), _p(plies)))
+        if dump:
+            return best, status, plies, nodes, nstates, n_nodes
+        return best, status, plies
+
+    # ---- device-pointer forms (ints = raw device addresses, e.g. torch tensor .data_ptr()) ----
+    def bg_playout_dev(self, d_starts, n, seed, first_game_id, round_limit, d_winners, d_plies, d_finals=0):
+        self._chk(lib().diee_bg_playout_dev(self._h, _p(d_starts), C.c_int32(n), C.c_uint64(seed), C.c_uint32(first_game_id),
+                                            C.c_int32(round_limit), _p(d_winners), _p(d_plies), _p(d_finals)))
+
+    def bg_valid_moves_dev(self, d_states, n, d_moves, d_counts, d_ids=0):
+        self._chk(lib().diee_bg_valid_moves_dev(self._h, _p(d_states), C.c_int32(n), _p(d_moves), _p(d_counts), _p(d_ids)))
+
+    def bg_encode_states_dev(self, d_states, n, d_out):
+        self._chk(lib().diee_bg_encode_states_dev(self._h, _p(d_states), C.c_int32(n), _p(d_out)))
+
+    def mcts_search_dev(self, game_kind, d_states, n, d_players, cfg, seed, first_game_id, epoch, d_best, d_status, d_plies=0):
+        cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]
+        self._chk(lib().diee_mcts_search_dev(self._h, C.c_int32(game_kind), _p(d_states), C.c_int32(n), _p(d_players), _p(cfg),
+                                             C.c_uint64(seed), C.c_uint32(first_game_id), C.c_uint32(epoch), _p(d_best),
+                                             _p(d_status), _p(d_plies)))
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx

@@ -1,0 +1,432 @@
+// api.cu -- the extern "C" boundary of libdiee_cuda.so (include/diee.h).
+// Host-buffer entry points stage through ctx-owned device scratch; *_dev entry points are
+// stream-ordered on the ctx stream.  There is no CPU fallback anywhere in this library.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bg_device.cuh"
+#include "launchers.h"
+
+using namespace diee;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct diee_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    // scratch for host-buffer entry points
+    DevBuf s_states, s_moves, s_counts, s_ids, s_aux, s_out, s_players, s_best, s_status, s_plies;
+    // pure-MCTS node pool (HBM resident, reused between searches)
+    DevBuf p_states, p_parent, p_visits, p_value, p_action, p_nmoves, p_nnodes, ln_table;
+    uint32_t ln_table_n = 0;
+};
+
+static int32_t fail(diee_ctx *ctx, int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(ctx, DIEE_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static int32_t reserve(diee_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return DIEE_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return DIEE_OK;
+}
+#define RESERVE(buf, bytes)                                  \
+    do {                                                     \
+        int32_t r_ = reserve(ctx, buf, bytes);               \
+        if (r_ != DIEE_OK) return r_;                        \
+    } while (0)
+
+extern "C" {
+
+const char *diee_version(void) { return "die-e-b200 0.1 (sm_100a)"; }
+
+int32_t diee_ctx_create(int32_t device, diee_ctx **out) {
+    if (!out) return DIEE_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return DIEE_ERR_CUDA;  // no CPU fallback
+    diee_ctx *ctx = new diee_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return DIEE_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return DIEE_OK;
+}
+
+int32_t diee_ctx_destroy(diee_ctx *ctx) {
+    if (!ctx) return DIEE_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->s_states, &ctx->s_moves, &ctx->s_counts, &ctx->s_ids, &ctx->s_aux, &ctx->s_out,
+                      &ctx->s_players, &ctx->s_best, &ctx->s_status, &ctx->s_plies, &ctx->p_states, &ctx->p_parent,
+                      &ctx->p_visits, &ctx->p_value, &ctx->p_action, &ctx->p_nmoves, &ctx->p_nnodes, &ctx->ln_table};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return DIEE_OK;
+}
+
+int32_t diee_ctx_set_stream(diee_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return DIEE_ERR_INVALID;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return DIEE_OK;
+}
+
+int32_t diee_sync(diee_ctx *ctx) {
+    if (!ctx) return DIEE_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DIEE_OK;
+}
+
+const char *diee_last_error(const diee_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+int64_t diee_launch_count(const diee_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t diee_dev_alloc(diee_ctx *ctx, uint64_t bytes, void **dptr_out) {
+    if (!ctx || !dptr_out) return DIEE_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(dptr_out, bytes ? bytes : 1));
+    return DIEE_OK;
+}
+int32_t diee_dev_free(diee_ctx *ctx, void *dptr) {
+    if (!ctx) return DIEE_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaFree(dptr));
+    return DIEE_OK;
+}
+int32_t diee_dev_upload(diee_ctx *ctx, void *dptr, const void *host, uint64_t bytes) {
+    if (!ctx) return DIEE_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DIEE_OK;
+}
+int32_t diee_dev_download(diee_ctx *ctx, void *host, const void *dptr, uint64_t bytes) {
+    if (!ctx) return DIEE_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DIEE_OK;
+}
+
+void diee_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+    philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), c0, c1, c2, c3, out);
+}
+
+// ---------------- env ----------------
+int32_t diee_bg_valid_moves_dev(diee_ctx *ctx, const diee_bg_state *states, int32_t n, diee_move *moves_out,
+                                int32_t *counts_out, uint16_t *ids_out) {
+    if (!ctx || n < 0 || (n && (!states || !moves_out || !counts_out))) return fail(ctx, DIEE_ERR_INVALID, "bg_valid_moves: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_bg_valid_moves(ctx->stream, states, n, moves_out, counts_out, ids_out));
+    ctx->launches += n > 0;
+    return DIEE_OK;
+}
+
+int32_t diee_bg_valid_moves(diee_ctx *ctx, const diee_bg_state *states, int32_t n, diee_move *moves_out,
+                            int32_t *counts_out, uint16_t *ids_out) {
+    if (!ctx || n < 0 || (n && (!states || !moves_out || !counts_out))) return fail(ctx, DIEE_ERR_INVALID, "bg_valid_moves: bad argument");
+    if (n == 0) return DIEE_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t nm = (size_t)n * DIEE_MAX_MOVES;
+    RESERVE(ctx->s_states, sizeof(diee_bg_state) * n);
+    RESERVE(ctx->s_moves, sizeof(diee_move) * nm);
+    RESERVE(ctx->s_counts, sizeof(int32_t) * n);
+    if (ids_out) RESERVE(ctx->s_ids, sizeof(uint16_t) * nm);
+    CU(cudaMemcpyAsync(ctx->s_states.p, states, sizeof(diee_bg_state) * n, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t rc = diee_bg_valid_moves_dev(ctx, (const diee_bg_state *)ctx->s_states.p, n, (diee_move *)ctx->s_moves.p,
+                                         (int32_t *)ctx->s_counts.p, ids_out ? (uint16_t *)ctx->s_ids.p : nullptr);
+    if (rc != DIEE_OK) return rc;
+    CU(cudaMemcpyAsync(counts_out, ctx->s_counts.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(moves_out, ctx->s_moves.p, sizeof(diee_move) * nm, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ids_out) CU(cudaMemcpyAsync(ids_out, ctx->s_ids.p, sizeof(uint16_t) * nm, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DIEE_OK;
+}
+
+int32_t diee_bg_apply_moves_dev(diee_ctx *ctx, diee_bg_state *states, const diee_move *moves,
+                                const uint8_t *next_rolls, int32_t n) {
+    if (!ctx || n < 0 || (n && (!states || !moves || !next_rolls))) return fail(ctx, DIEE_ERR_INVALID, "bg_apply_moves: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_bg_apply(ctx->stream, states, moves, next_rolls, n));
+    ctx->launches += n > 0;
+    return DIEE_OK;
+}
+
+int32_t diee_bg_apply_moves(diee_ctx *ctx, diee_bg_state *states, const diee_move *moves,
+                            const uint8_t *next_rolls, int32_t n) {
+    if (!ctx || n < 0 || (n && (!states || !moves || !next_rolls))) return fail(ctx, DIEE_ERR_INVALID, "bg_apply_moves: bad argument");
+    if (n == 0) return DIEE_OK;
+    CU(cudaSetDevice(ctx->device));
+    RESERVE(ctx->s_states, sizeof(diee_bg_state) * n);
+    RESERVE(ctx->s_moves, sizeof(diee_move) * n);
+    RESERVE(ctx->s_aux, 2 * (size_t)n);
+    CU(cudaMemcpyAsync(ctx->s_states.p, states, sizeof(diee_bg_state) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_moves.p, moves, sizeof(diee_move) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_aux.p, next_rolls, 2 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t rc = diee_bg_apply_moves_dev(ctx, (diee_bg_state *)ctx->s_states.p, (const diee_move *)ctx->s_moves.p,
+                                         (const uint8_t *)ctx->s_aux.p, n);
+    if (rc != DIEE_OK) return rc;
+    CU(cudaMemcpyAsync(states, ctx->s_states.p, sizeof(diee_bg_state) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DIEE_OK;
+}
+
+int32_t diee_bg_playout_dev(diee_ctx *ctx, const diee_bg_state *starts, int32_t n, uint64_t seed,
+                            uint32_t first_game_id, int32_t round_limit, int8_t *winners_out,
+                            int32_t *plies_out, diee_bg_state *finals_out) {
+    if (!ctx || n < 0 || round_limit < 0 || (n && (!starts || !winners_out || !plies_out)))
+        return fail(ctx, DIEE_ERR_INVALID, "bg_playout: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_bg_playout(ctx->stream, starts, n, seed, first_game_id, round_limit, winners_out, plies_out, finals_out));
+    ctx->launches += n > 0;
+    return DIEE_OK;
+}
+
+int32_t diee_bg_playout(diee_ctx *ctx, const diee_bg_state *starts, int32_t n, uint64_t seed,
+                        uint32_t first_game_id, int32_t round_limit, int8_t *winners_out,
+                        int32_t *plies_out, diee_bg_state *finals_out) {
+    if (!ctx || n < 0 || round_limit < 0 || (n && (!starts || !winners_out || !plies_out)))
+        return fail(ctx, DIEE_ERR_INVALID, "bg_playout: bad argument");
+    if (n == 0) return DIEE_OK;
+    CU(cudaSetDevice(ctx->device));
+    for (int i = 0; i < n; ++i)
+        if (starts[i].roll[0] == 0 && starts[i].roll[1] == 0) return fail(ctx, DIEE_ERR_NOT_ROLLED, "bg_playout: state %d has not been rolled", i);
+    RESERVE(ctx->s_states, sizeof(diee_bg_state) * n);
+    RESERVE(ctx->s_out, sizeof(diee_bg_state) * n);
+    RESERVE(ctx->s_counts, sizeof(int32_t) * n);
+    RESERVE(ctx->s_aux, (size_t)n);
+    CU(cudaMemcpyAsync(ctx->s_states.p, starts, sizeof(diee_bg_state) * n, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t rc = diee_bg_playout_dev(ctx, (const diee_bg_state *)ctx->s_states.p, n, seed, first_game_id, round_limit,
+                                     (int8_t *)ctx->s_aux.p, (int32_t *)ctx->s_counts.p,
+                                     finals_out ? (diee_bg_state *)ctx->s_out.p : nullptr);
+    if (rc != DIEE_OK) return rc;
+    CU(cudaMemcpyAsync(winners_out, ctx->s_aux.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(plies_out, ctx->s_counts.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (finals_out) CU(cudaMemcpyAsync(finals_out, ctx->s_out.p, sizeof(diee_bg_state) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DIEE_OK;
+}
+
+int32_t diee_bg_encode_moves(diee_ctx *ctx, const diee_bg_state *states, const diee_move *moves, int32_t n,
+                             uint16_t *ids_out) {
+    if (!ctx || n < 0 || (n && (!states || !moves || !ids_out))) return fail(ctx, DIEE_ERR_INVALID, "bg_encode_moves: bad argument");
+    if (n == 0) return DIEE_OK;
+    CU(cudaSetDevice(ctx->device));
+    RESERVE(ctx->s_states, sizeof(diee_bg_state) * n);
+    RESERVE(ctx->s_moves, sizeof(diee_move) * n);
+    RESERVE(ctx->s_ids, sizeof(uint16_t) * n);
+    CU(cudaMemcpyAsync(ctx->s_states.p, states, sizeof(diee_bg_state) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_moves.p, moves, sizeof(diee_move) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_bg_encode_moves(ctx->stream, (const diee_bg_state *)ctx->s_states.p, (const diee_move *)ctx->s_moves.p, n, (uint16_t *)ctx->s_ids.p));
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(ids_out, ctx->s_ids.p, sizeof(uint16_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DIEE_OK;
+}
+
+int32_t diee_bg_decode_moves(diee_ctx *ctx, const diee_bg_state *states, const uint16_t *ids, int32_t n,
+                             diee_move *moves_out) {
+    if (!ctx || n < 0 || (n && (!states || !ids || !moves_out))) return fail(ctx, DIEE_ERR_INVALID, "bg_decode_moves: bad argument");
+    if (n == 0) return DIEE_OK;
+    for (int i = 0; i < n; ++i)
+        if (ids[i] >= DIEE_ACTION_SPACE) return fail(ctx, DIEE_ERR_INVALID, "bg_decode_moves: action id %u out of range", (unsigned)ids[i]);
+    CU(cudaSetDevice(ctx->device));
+    RESERVE(ctx->s_states, sizeof(diee_bg_state) * n);
+    RESERVE(ctx->s_moves, sizeof(diee_move) * n);
+    RESERVE(ctx->s_ids, sizeof(uint16_t) * n);
+    CU(cudaMemcpyAsync(ctx->s_states.p, states, sizeof(diee_bg_state) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_ids.p, ids, sizeof(uint16_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_bg_decode_moves(ctx->stream, (const diee_bg_state *)ctx->s_states.p, (const uint16_t *)ctx->s_ids.p, n, (diee_move *)ctx->s_moves.p));
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(moves_out, ctx->s_moves.p, sizeof(diee_move) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DIEE_OK;
+}
+
+int32_t diee_bg_encode_states_dev(diee_ctx *ctx, const diee_bg_state *states, int32_t n, float *out) {
+    if (!ctx || n < 0 || (n && (!states || !out))) return fail(ctx, DIEE_ERR_INVALID, "bg_encode_states: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_bg_encode_states(ctx->stream, states, n, out));
+    ctx->launches += n > 0;
+    return DIEE_OK;
+}
+
+int32_t diee_bg_encode_states(diee_ctx *ctx, const diee_bg_state *states, int32_t n, float *out) {
+    if (!ctx || n < 0 || (n && (!states || !out))) return fail(ctx, DIEE_ERR_INVALID, "bg_encode_states: bad argument");
+    if (n == 0) return DIEE_OK;
+    for (int i = 0; i < n; ++i)
+        if (states[i].roll[0] == 0 && states[i].roll[1] == 0) return fail(ctx, DIEE_ERR_NOT_ROLLED, "bg_encode_states: state %d has not been rolled", i);
+    CU(cudaSetDevice(ctx->device));
+    RESERVE(ctx->s_states, sizeof(diee_bg_state) * n);
+    RESERVE(ctx->s_out, sizeof(float) * 144 * (size_t)n);
+    CU(cudaMemcpyAsync(ctx->s_states.p, states, sizeof(diee_bg_state) * n, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t rc = diee_bg_encode_states_dev(ctx, (const diee_bg_state *)ctx->s_states.p, n, (float *)ctx->s_out.p);
+    if (rc != DIEE_OK) return rc;
+    CU(cudaMemcpyAsync(out, ctx->s_out.p, sizeof(float) * 144 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DIEE_OK;
+}
+
+// ---------------- pure MCTS ----------------
+static size_t state_size(int game_kind) { return game_kind == DIEE_GAME_BACKGAMMON ? sizeof(diee_bg_state) : sizeof(diee_ttt_state); }
+
+static int32_t ensure_pool(diee_ctx *ctx, int game_kind, int n, const diee_mcts_cfg *cfg) {
+    const size_t cap = (size_t)cfg->iterations + 1, total = cap * (size_t)n;
+    RESERVE(ctx->p_states, state_size(game_kind) * total);
+    RESERVE(ctx->p_parent, sizeof(int32_t) * total);
+    RESERVE(ctx->p_visits, sizeof(float) * total);
+    RESERVE(ctx->p_value, sizeof(float) * total);
+    RESERVE(ctx->p_action, sizeof(uint32_t) * total);
+    RESERVE(ctx->p_nmoves, sizeof(uint32_t) * total);
+    RESERVE(ctx->p_nnodes, sizeof(int32_t) * (size_t)n);
+    if (ctx->ln_table_n < cfg->iterations + 2) {
+        // ln of every possible (integer-valued) visit count, correctly rounded from double:
+        // the contract's replacement for f32::ln (node.rs:91)
+        const uint32_t m = cfg->iterations + 2;
+        std::vector<float> t(m);
+        t[0] = -INFINITY;
+        for (uint32_t i = 1; i < m; ++i) t[i] = (float)std::log((double)i);
+        RESERVE(ctx->ln_table, sizeof(float) * m);
+        CU(cudaMemcpyAsync(ctx->ln_table.p, t.data(), sizeof(float) * m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->ln_table_n = m;
+    }
+    return DIEE_OK;
+}
+
+static int32_t check_mcts_args(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n, const int8_t *players,
+                               const diee_mcts_cfg *cfg, void *best, int32_t *status, uint32_t epoch) {
+    if (!ctx) return DIEE_ERR_INVALID;
+    if (game_kind != DIEE_GAME_BACKGAMMON && game_kind != DIEE_GAME_TICTACTOE) return fail(ctx, DIEE_ERR_INVALID, "mcts_search: unknown game kind %d", game_kind);
+    if (n < 0 || !cfg || (n && (!states || !players || !best || !status))) return fail(ctx, DIEE_ERR_INVALID, "mcts_search: bad argument");
+    if (cfg->iterations == 0 || cfg->iterations > 65534u) return fail(ctx, DIEE_ERR_INVALID, "mcts_search: iterations must be in 1..65534");
+    if (epoch > 0xFFFFu) return fail(ctx, DIEE_ERR_INVALID, "mcts_search: epoch must be < 65536");
+    return DIEE_OK;
+}
+
+int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
+                             const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
+                             uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
+                             int32_t *status_out, uint64_t *sim_plies_dev) {
+    int32_t rc = check_mcts_args(ctx, game_kind, states, n, players, cfg, best_moves_out, status_out, epoch);
+    if (rc != DIEE_OK) return rc;
+    if (n == 0) return DIEE_OK;
+    CU(cudaSetDevice(ctx->device));
+    rc = ensure_pool(ctx, game_kind, n, cfg);
+    if (rc != DIEE_OK) return rc;
+    PoolPtrs pp{ctx->p_states.p, (int32_t *)ctx->p_parent.p, (float *)ctx->p_visits.p, (float *)ctx->p_value.p,
+                (uint32_t *)ctx->p_action.p, (uint32_t *)ctx->p_nmoves.p, (int32_t *)ctx->p_nnodes.p};
+    uint32_t *best32 = (uint32_t *)best_moves_out;
+    if (game_kind == DIEE_GAME_TICTACTOE) {  // kernel writes u32 per game; narrow to u8 afterwards
+        RESERVE(ctx->s_best, sizeof(uint32_t) * (size_t)n);
+        best32 = (uint32_t *)ctx->s_best.p;
+    }
+    CU(launch_mcts_search(ctx->stream, game_kind, states, n, players, *cfg, seed, first_game_id, epoch, pp,
+                          (const float *)ctx->ln_table.p, best32, status_out, (unsigned long long *)sim_plies_dev));
+    ctx->launches += 1;
+    if (game_kind == DIEE_GAME_TICTACTOE) {
+        // EMPTY_MOVE = 10 (tictactoe/mod.rs:18); done on the host side of the stream for this tiny case
+        std::vector<uint32_t> h((size_t)n);
+        CU(cudaMemcpyAsync(h.data(), best32, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        std::vector<uint8_t> b((size_t)n);
+        for (int i = 0; i < n; ++i) b[i] = h[i] == SEQ_EMPTY ? 10 : (uint8_t)(h[i] & 0xFFu);
+        CU(cudaMemcpyAsync(best_moves_out, b.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return DIEE_OK;
+}
+
+int32_t diee_mcts_search(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
+                         const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
+                         uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
+                         int32_t *status_out, diee_node *nodes_out, void *node_states_out,
+                         int32_t *n_nodes_out, uint64_t *sim_plies_out) {
+    int32_t rc = check_mcts_args(ctx, game_kind, states, n, players, cfg, best_moves_out, status_out, epoch);
+    if (rc != DIEE_OK) return rc;
+    if (n == 0) return DIEE_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t ss = state_size(game_kind);
+    if (game_kind == DIEE_GAME_BACKGAMMON) {
+        const diee_bg_state *s = (const diee_bg_state *)states;
+        for (int i = 0; i < n; ++i)
+            if (s[i].roll[0] == 0 && s[i].roll[1] == 0) return fail(ctx, DIEE_ERR_NOT_ROLLED, "mcts_search: state %d has not been rolled", i);
+    }
+    const size_t best_sz = game_kind == DIEE_GAME_BACKGAMMON ? sizeof(diee_move) : 1;
+    RESERVE(ctx->s_states, ss * n);
+    RESERVE(ctx->s_players, (size_t)n);
+    RESERVE(ctx->s_moves, sizeof(uint32_t) * (size_t)n);
+    RESERVE(ctx->s_status, sizeof(int32_t) * (size_t)n);
+    RESERVE(ctx->s_plies, sizeof(uint64_t) * (size_t)n);
+    CU(cudaMemcpyAsync(ctx->s_states.p, states, ss * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->s_players.p, players, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = diee_mcts_search_dev(ctx, game_kind, ctx->s_states.p, n, (const int8_t *)ctx->s_players.p, cfg, seed, first_game_id,
+                              epoch, ctx->s_moves.p, (int32_t *)ctx->s_status.p, (uint64_t *)ctx->s_plies.p);
+    if (rc != DIEE_OK) return rc;
+    CU(cudaMemcpyAsync(best_moves_out, ctx->s_moves.p, best_sz * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(status_out, ctx->s_status.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sim_plies_out) CU(cudaMemcpyAsync(sim_plies_out, ctx->s_plies.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_nodes_out) CU(cudaMemcpyAsync(n_nodes_out, ctx->p_nnodes.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t total = ((size_t)cfg->iterations + 1) * (size_t)n;
+    if (node_states_out) CU(cudaMemcpyAsync(node_states_out, ctx->p_states.p, ss * total, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int32_t> parent;
+    std::vector<float> visits, value;
+    std::vector<uint32_t> action, nmoves;
+    if (nodes_out) {
+        parent.resize(total); visits.resize(total); value.resize(total); action.resize(total); nmoves.resize(total);
+        CU(cudaMemcpyAsync(parent.data(), ctx->p_parent.p, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(visits.data(), ctx->p_visits.p, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(value.data(), ctx->p_value.p, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(action.data(), ctx->p_action.p, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(nmoves.data(), ctx->p_nmoves.p, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (nodes_out) {
+        for (size_t i = 0; i < total; ++i) {
+            nodes_out[i].parent = parent[i];
+            nodes_out[i].visits = visits[i];
+            nodes_out[i].value = value[i];
+            memcpy(&nodes_out[i].action, &action[i], 4);
+            nodes_out[i].n_moves = (int32_t)(nmoves[i] >> 16);
+            nodes_out[i].n_untried = (int32_t)(nmoves[i] & 0xFFFFu);
+        }
+    }
+    return DIEE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// launchers.h -- internal: kernel launchers shared between the .cu files and api.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/diee.h"
+
+namespace diee {
+
+struct PoolPtrs {
+    void *states;
+    int32_t *parent;
+    float *visits, *value;
+    uint32_t *action;
+    uint32_t *nmoves;
+    int32_t *n_nodes;
+};
+
+cudaError_t launch_bg_valid_moves(cudaStream_t st, const diee_bg_state *states, int n, diee_move *moves_out,
+                                  int32_t *counts_out, uint16_t *ids_out);
+cudaError_t launch_bg_apply(cudaStream_t st, diee_bg_state *states, const diee_move *moves, const uint8_t *next_rolls, int n);
+cudaError_t launch_bg_playout(cudaStream_t st, const diee_bg_state *starts, int n, uint64_t seed, uint32_t first_game_id,
+                              int round_limit, int8_t *winners_out, int32_t *plies_out, diee_bg_state *finals_out);
+cudaError_t launch_bg_encode_moves(cudaStream_t st, const diee_bg_state *states, const diee_move *moves, int n, uint16_t *ids_out);
+cudaError_t launch_bg_decode_moves(cudaStream_t st, const diee_bg_state *states, const uint16_t *ids, int n, diee_move *moves_out);
+cudaError_t launch_bg_encode_states(cudaStream_t st, const diee_bg_state *states, int n, float *out);
+cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots, int n, const int8_t *players,
+                               const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
+                               const PoolPtrs &pp, const float *ln_table, uint32_t *best_out, int32_t *status_out,
+                               unsigned long long *sim_plies_out);
+
+}  // namespace diee

@@ -1,0 +1,276 @@
+// mcts_kernels.cu -- pure MCTS: one warp runs one game's whole search.
+//
+// Reference: src/mcts/simple_mcts.rs (mct_search :10-39, select_ucb :41-52, select_leaf_node
+// :88-94, backpropagate :96-103, select_most_visits :71-86), src/mcts/node.rs (ucb :86-96,
+// expand :118-137, simulate :176-196), src/mcts/node_store.rs (arena).
+//
+// Node pool: structure-of-arrays in HBM, one contiguous slab of (iterations+1) nodes per game
+// (states / parent / visits / value / action / move counts), so a warp's select pass reads
+// coalesced runs of parent[], visits[], value[].  A node's children are exactly the nodes whose
+// parent[] equals it, in creation order, so UCB select is a warp scan over the slab with a
+// "later index wins ties" arg-max (Rust's max_by keeps the LAST maximum).  UCB is evaluated in
+// IEEE f32 with explicit round-to-nearest intrinsics (no FMA contraction, no fast division) and
+// ln(parent visits) comes from a host-built table of (float)log((double)n): visits are
+// integer-valued, so this is bit-identical to the oracle.
+#include "bg_device.cuh"
+#include "launchers.h"
+
+namespace diee {
+
+constexpr int MCTS_WARPS_PER_CTA = 4;
+constexpr int NO_WINNER = 2;
+
+// ---------------- game policies ----------------
+struct BgGame {
+    using State = diee_bg_state;
+    BgWarp g;
+    __device__ __forceinline__ void load(const State *s, int lane) { bg_load(g, s, lane); }
+    __device__ __forceinline__ void store(State *s, int lane) const { bg_store(g, s, lane); }
+    __device__ __forceinline__ int winner() const { const int w = bg_winner(g); return w == 0 ? NO_WINNER : w; }
+    __device__ __forceinline__ int movegen(WarpSlab &slab, int lane, bool &ovf) const { return bg_movegen(g, slab, lane, ovf); }
+    __device__ __forceinline__ uint32_t move_at(const WarpSlab &slab, int k) const { return slab.raw[k]; }
+    __device__ __forceinline__ void step(uint32_t seq, int d0, int d1, int lane) { bg_step(g, seq, d0, d1, lane); }
+};
+
+struct TttGame {  // tictactoe/mod.rs; the whole state is warp-uniform
+    using State = diee_ttt_state;
+    uint32_t xm, om;  // cells held by -1 / +1
+    int player;
+    __device__ __forceinline__ void load(const State *s, int lane) {
+        const int b = lane < 9 ? (int)s->board[lane] : 0;
+        xm = __ballot_sync(FULL, b == -1);
+        om = __ballot_sync(FULL, b == 1);
+        player = s->player;
+    }
+    __device__ __forceinline__ void store(State *s, int lane) const {
+        if (lane < 9) s->board[lane] = ((xm >> lane) & 1u) ? -1 : (((om >> lane) & 1u) ? 1 : 0);
+        if (lane == 9) s->player = (int8_t)player;
+        if (lane >= 10 && lane < 16) s->pad[lane - 10] = 0;
+    }
+    // check_winner :59-79: a cell belongs to one side, so at most one side has a line unless the
+    // position is unreachable; the table order (rows, cols, diags) decides then.
+    __device__ __forceinline__ int winner() const {
+        const uint32_t L[8] = {0x007u, 0x038u, 0x1C0u, 0x049u, 0x092u, 0x124u, 0x111u, 0x054u};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if ((xm & L[k]) == L[k]) return -1;
+            if ((om & L[k]) == L[k]) return 1;
+        }
+        return ((xm | om) & 0x1FFu) == 0x1FFu ? 0 : NO_WINNER;
+    }
+    __device__ __forceinline__ int movegen(WarpSlab &, int, bool &) const { return __popc(~(xm | om) & 0x1FFu); }
+    __device__ __forceinline__ uint32_t move_at(const WarpSlab &, int k) const {  // k-th empty cell ascending :36-44
+        uint32_t e = ~(xm | om) & 0x1FFu;
+        for (int i = 0; i < k; ++i) e &= e - 1;
+        return (uint32_t)(__ffs(e) - 1) | 0xFEFEFE00u;
+    }
+    __device__ __forceinline__ void step(uint32_t seq, int, int, int) {
+        if (seq != SEQ_EMPTY) {  // apply_move :46-49
+            const uint32_t bit = 1u << (seq & 0xFFu);
+            if (player < 0) xm |= bit; else om |= bit;
+        }
+        player = -player;  // skip_turn :51-53
+    }
+};
+
+struct Pool {
+    void *states;
+    int32_t *parent;
+    float *visits, *value;
+    uint32_t *action;
+    uint32_t *nmoves;  // n_moves << 16 | n_untried
+    int32_t *n_nodes;  // per game
+};
+
+__device__ __forceinline__ float outcome(int winner, int player) {  // simple_mcts.rs:26-28
+    return winner == player ? 1.0f : (winner == -player ? -1.0f : 0.0f);
+}
+
+template <class G>
+__global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32)
+mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int8_t *__restrict__ players,
+                   diee_mcts_cfg cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch, Pool pool,
+                   const float *__restrict__ ln_table, uint32_t *__restrict__ best_out, int32_t *__restrict__ status_out,
+                   unsigned long long *__restrict__ sim_plies_out) {
+    __shared__ WarpSlab slabs[MCTS_WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gidx = blockIdx.x * MCTS_WARPS_PER_CTA + wib;
+    if (gidx >= n) return;
+    WarpSlab &slab = slabs[wib];
+    const int cap = (int)cfg.iterations + 1;
+    const size_t base = (size_t)gidx * cap;
+    typename G::State *st = reinterpret_cast<typename G::State *>(pool.states) + base;
+    int32_t *parent = pool.parent + base;
+    float *visits = pool.visits + base, *value = pool.value + base;
+    uint32_t *action = pool.action + base, *nm = pool.nmoves + base;
+    const int player = players[gidx];
+    const uint32_t gid = first_game_id + (uint32_t)gidx;
+    const bool check_current = cfg.mode_flags & DIEE_MODE_ROLLOUT_CHECK_CURRENT;
+    const bool pass_child = cfg.mode_flags & DIEE_MODE_PASS_CHILD;
+
+    G game;
+    game.load(roots + gidx, lane);
+    uint32_t best = SEQ_EMPTY;
+    int status = DIEE_OK;
+    int n_nodes = 0;
+    unsigned long long plies = 0;
+    bool ovf = false;
+
+    if (game.winner() == NO_WINNER) {  // simple_mcts.rs:12-14
+        // root = add_node(state)  (Node::new computes the legal moves eagerly, node.rs:50)
+        game.store(st, lane);
+        int U = game.movegen(slab, lane, ovf);
+        __syncwarp();
+        if (U == 0 && pass_child) U = 1;
+        if (lane == 0) { parent[0] = -1; visits[0] = 0.f; value[0] = 0.f; action[0] = SEQ_EMPTY; nm[0] = ((uint32_t)U << 16) | (uint32_t)U; }
+        n_nodes = 1;
+        __syncwarp();
+
+        for (uint32_t it = 0; it < cfg.iterations; ++it) {
+            // ---- select_leaf_node :88-94 ----
+            int cur = 0;
+            uint32_t nmv;
+            for (;;) {
+                nmv = nm[cur];
+                const int nmoves = (int)(nmv >> 16), nunt = (int)(nmv & 0xFFFFu);
+                if (nunt != 0 || nmoves == 0) break;  // has untried moves, or no children at all
+                // select_ucb :41-52 over the children of cur (creation order = index order)
+                const float pvis = visits[cur];
+                const float lnp = ln_table[(int)pvis];
+                const float cl = __fmul_rn(cfg.c, lnp);
+                float bs = -INFINITY;
+                int bi = -1;
+                for (int c0 = 0; c0 < n_nodes; c0 += 32) {
+                    const int idx = c0 + lane;
+                    if (idx < n_nodes && parent[idx] == cur) {
+                        const float vi = visits[idx];
+                        // Node::ucb node.rs:86-96: value/visits + sqrt(c*ln(parent.visits)/visits)
+                        const float s = __fadd_rn(__fdiv_rn(value[idx], vi), __fsqrt_rn(__fdiv_rn(cl, vi)));
+                        if (!(bs > s)) { bs = s; bi = idx; }  // within a lane idx only grows
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const float os = __shfl_xor_sync(FULL, bs, d);
+                    const int oi = __shfl_xor_sync(FULL, bi, d);
+                    // keep the later index unless the earlier is strictly greater (max_by)
+                    const bool take = oi >= 0 && (bi < 0 || (oi > bi ? !(bs > os) : (os > bs)));
+                    if (take) { bs = os; bi = oi; }
+                }
+                if (bi < 0) { status = DIEE_ERR_OVERFLOW; break; }  // cannot happen: a fully expanded node has children
+                cur = bi;
+            }
+            if (status != DIEE_OK) break;
+            const int nmoves = (int)(nmv >> 16), nunt = (int)(nmv & 0xFFFFu);
+            game.load(st + cur, lane);
+            const int w = game.winner();
+            int leaf = cur;
+            float result;
+            if (w != NO_WINNER) {
+                result = outcome(w, player);  // :25-30
+            } else {
+                if (nunt == 0) { status = DIEE_ERR_NO_MOVES_PANIC; break; }  // node.rs:119-121 (Q6)
+                // ---- Node::expand node.rs:118-137: pop the LAST untried move ----
+                const int U = game.movegen(slab, lane, ovf);
+                const uint32_t seq = U == 0 ? SEQ_EMPTY : game.move_at(slab, nunt - 1);
+                __syncwarp();
+                const int child = n_nodes;
+                uint32_t blk[4];
+                philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)child, gid, DIEE_STREAM_EXPAND, epoch, blk);
+                game.step(seq, die_of(blk[0]), die_of(blk[1]), lane);
+                game.store(st + child, lane);
+                int Uc = game.movegen(slab, lane, ovf);  // Node::new for the child
+                __syncwarp();
+                if (Uc == 0 && pass_child) Uc = 1;
+                if (lane == 0) {
+                    nm[cur] = ((uint32_t)nmoves << 16) | (uint32_t)(nunt - 1);
+                    parent[child] = cur; visits[child] = 0.f; value[child] = 0.f; action[child] = seq;
+                    nm[child] = ((uint32_t)Uc << 16) | (uint32_t)Uc;
+                }
+                n_nodes = child + 1;
+                leaf = child;
+                // ---- Node::simulate node.rs:176-196 ----
+                result = 0.f;
+                const int w0 = game.winner();  // winner of the START state (Q5)
+                if (cfg.simulate_round_limit > 0 && w0 != NO_WINNER) {
+                    result = outcome(w0, player);
+                } else {
+                    PhiloxLanes rng;
+                    const uint32_t c3 = (epoch << 16) | (it & 0xFFFFu);
+                    for (uint32_t k = 0; k < cfg.simulate_round_limit; ++k) {
+                        if (check_current) {
+                            const int wc = game.winner();
+                            if (wc != NO_WINNER) { result = outcome(wc, player); break; }
+                        }
+                        if ((k & 31u) == 0) rng.fill(seed, k, gid, DIEE_STREAM_ROLLOUT, c3, lane);
+                        const int src = (int)(k & 31u);
+                        const int d0 = die_of(__shfl_sync(FULL, rng.w0, src));
+                        const int d1 = die_of(__shfl_sync(FULL, rng.w1, src));
+                        const uint32_t w2 = __shfl_sync(FULL, rng.w2, src);
+                        const int Ur = game.movegen(slab, lane, ovf);
+                        const uint32_t sq = Ur > 0 ? game.move_at(slab, (int)index_of(w2, (uint32_t)Ur)) : SEQ_EMPTY;
+                        __syncwarp();
+                        game.step(sq, d0, d1, lane);
+                        ++plies;
+                    }
+                }
+            }
+            // ---- backpropagate :96-103 (no sign flip) ----
+            if (lane == 0) {
+                for (int i = leaf; i >= 0; i = parent[i]) {
+                    visits[i] = __fadd_rn(visits[i], 1.0f);
+                    value[i] = __fadd_rn(value[i], result);
+                }
+            }
+            __syncwarp();
+        }
+
+        if (status == DIEE_OK) {  // select_most_visits :71-86 (last maximum)
+            float bv = -INFINITY;
+            int bi = -1;
+            for (int c0 = 1; c0 < n_nodes; c0 += 32) {
+                const int idx = c0 + lane;
+                if (idx < n_nodes && parent[idx] == 0) {
+                    const float vi = visits[idx];
+                    if (!(bv > vi)) { bv = vi; bi = idx; }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const float os = __shfl_xor_sync(FULL, bv, d);
+                const int oi = __shfl_xor_sync(FULL, bi, d);
+                const bool take = oi >= 0 && (bi < 0 || (oi > bi ? !(bv > os) : (os > bv)));
+                if (take) { bv = os; bi = oi; }
+            }
+            if (bi >= 0) best = action[bi];
+        }
+    }
+    if (ovf && status == DIEE_OK) status = DIEE_ERR_OVERFLOW;
+    if (lane == 0) {
+        best_out[gidx] = best;
+        status_out[gidx] = status;
+        pool.n_nodes[gidx] = n_nodes;
+        if (sim_plies_out) sim_plies_out[gidx] = plies;
+    }
+}
+
+static inline int mcts_grid(int n) { return (n + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA; }
+
+cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots, int n, const int8_t *players,
+                               const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
+                               const PoolPtrs &pp, const float *ln_table, uint32_t *best_out, int32_t *status_out,
+                               unsigned long long *sim_plies_out) {
+    if (n <= 0) return cudaSuccess;
+    Pool pool{pp.states, pp.parent, pp.visits, pp.value, pp.action, pp.nmoves, pp.n_nodes};
+    if (game_kind == DIEE_GAME_BACKGAMMON)
+        mcts_search_kernel<BgGame><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
+            static_cast<const diee_bg_state *>(roots), n, players, cfg, seed, first_game_id, epoch, pool, ln_table,
+            best_out, status_out, sim_plies_out);
+    else
+        mcts_search_kernel<TttGame><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
+            static_cast<const diee_ttt_state *>(roots), n, players, cfg, seed, first_game_id, epoch, pool, ln_table,
+            best_out, status_out, sim_plies_out);
+    return cudaGetLastError();
+}
+
+}  // namespace diee

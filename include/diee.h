@@ -1,0 +1,193 @@
+/*
+ * diee.h -- C ABI of libdiee_cuda.so: the B200-native (sm_100a) engine for the die-e hot path
+ * (batched MCTS over thousands of concurrent backgammon games).
+ *
+ * The reference (alibasaran/die-e) is safe Rust with NO FFI/plugin interface.
+ * The seam this library sits behind is therefore the Rust API itself; every entry point below
+ * names the reference item it replaces (file:line under the reference's src/).  A Rust `-sys`
+ * crate binding this header, and the safe wrapper re-exposing `LearnableGame`, `mct_search`,
+ * `alpha_mcts_parallel`, `self_play_parallel`, is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns int32 status: DIEE_OK or a negative DIEE_ERR_*; diee_last_error()
+ *     gives the message.  Nothing unwinds across the boundary (the reference panics instead).
+ *   - plain pointers and sizes only.  Functions without a suffix take HOST buffers and do the
+ *     host<->device copies themselves (synchronous on return).  Functions ending in `_dev`
+ *     take DEVICE pointers, are stream-ordered on the context's stream and return without
+ *     synchronising: results are valid after diee_sync().
+ *   - one diee_ctx per GPU; calls on one ctx must be serialised by the caller.
+ *   - there is NO CPU fallback: every compute entry point fails with DIEE_ERR_CUDA when no
+ *     CUDA device is usable.
+ *
+ * Injected random stream (part of the ABI; the reference uses rand::thread_rng(), which cannot
+ * be seeded -- SURVEY.md Appendix C).  Every draw is a word of one Philox4x32-10 block with
+ *     key     = (seed_lo, seed_hi)
+ *     counter = (c0 = draw index, c1 = global game id, c2 = stream kind, c3 = aux)
+ *   die face from word w:      1 + ((uint64)w * 6 >> 32)
+ *   uniform index in [0,n):    (uint64)w * n >> 32
+ *   block words: w0,w1 = the two dice (roll.0, roll.1)   w2 = uniform move choice   w3 = spare
+ *   streams:
+ *     DIEE_STREAM_INIT     c0 = 0           first roll of game c1          (alpha_parallel.rs:105-108)
+ *     DIEE_STREAM_GAME     c0 = ply         ply of a played game/playout: w2 picks the move of
+ *                                           ply c0, w0,w1 are the dice rolled after it
+ *                                           (versus.rs:307-316, backgammon_logic.rs:176-196)
+ *     DIEE_STREAM_ROLLOUT  c0 = ply         same, inside Node::simulate (node.rs:176-196);
+ *                                           c3 = epoch<<16 | simulation index
+ *     DIEE_STREAM_EXPAND   c0 = node index  dice frozen into a new tree node (node.rs:124-125,
+ *                                           158-172); c3 = epoch
+ *     DIEE_STREAM_DIRICHLET, DIEE_STREAM_SAMPLE  see diee_alpha_* below
+ *   `epoch` distinguishes successive searches of one game (e.g. its move number).
+ */
+#ifndef DIEE_H
+#define DIEE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIEE_OK 0
+#define DIEE_ERR_INVALID (-1)        /* bad argument */
+#define DIEE_ERR_CUDA (-2)           /* CUDA runtime error / no device */
+#define DIEE_ERR_NO_MOVES_PANIC (-3) /* the reference would panic here (node.rs:119-121, quirk Q6) */
+#define DIEE_ERR_OVERFLOW (-4)       /* move buffer / node pool exhausted */
+#define DIEE_ERR_NOT_ROLLED (-5)     /* roll == (0,0): reference asserts (backgammon_logic.rs:199,404) */
+
+#define DIEE_MAX_MOVES 256 /* legal-move capacity per state (observed max 123 unique) */
+#define DIEE_NONE (-2)     /* absent sub-move */
+#define DIEE_ACTION_SPACE 1352
+
+enum { DIEE_GAME_BACKGAMMON = 0, DIEE_GAME_TICTACTOE = 1 };
+enum {
+    DIEE_STREAM_INIT = 0,
+    DIEE_STREAM_GAME = 1,
+    DIEE_STREAM_ROLLOUT = 2,
+    DIEE_STREAM_EXPAND = 3,
+    DIEE_STREAM_DIRICHLET = 4,
+    DIEE_STREAM_SAMPLE = 5
+};
+
+/* `Backgammon` state, packed to 32 bytes (backgammon_logic.rs:10,54-60).  pts: signed counts,
+ * player -1 negative (moves toward 0), player +1 positive (moves toward 23); bar/off index 0
+ * belongs to player -1, index 1 to player +1.  `id` is not part of the packed state. */
+typedef struct {
+    int8_t pts[24];
+    uint8_t bar[2];
+    uint8_t off[2];
+    uint8_t roll[2];
+    int8_t player;
+    uint8_t second; /* is_second_play */
+} diee_bg_state;
+
+/* `Actions = Vec<(i8,i8)>` of length 0..2 (backgammon_logic.rs:12,263): to == -1 collects,
+ * from == -1 enters from the bar; an absent sub-move is (DIEE_NONE, DIEE_NONE);
+ * EMPTY_MOVE (backgammon_logic.rs:72) is all DIEE_NONE. */
+typedef struct {
+    int8_t from1, to1, from2, to2;
+} diee_move;
+
+/* `TicTacToe` (tictactoe/mod.rs:6-13), 16 bytes */
+typedef struct {
+    int8_t board[9];
+    int8_t player;
+    uint8_t pad[6];
+} diee_ttt_state;
+
+/* `MctsConfig` (lib.rs:33-40) + mode flags */
+typedef struct {
+    uint32_t iterations;
+    float c;
+    uint32_t simulate_round_limit;
+    float dirichlet_alpha;
+    float dirichlet_epsilon;
+    uint32_t mode_flags;
+} diee_mcts_cfg;
+/* default (0) = reference-exact.  Quirks of the reference exposed as modes: */
+#define DIEE_MODE_ROLLOUT_CHECK_CURRENT 1u /* rollout tests the rolled-out state (node.rs:181 tests the start state) */
+#define DIEE_MODE_PASS_CHILD 2u            /* a no-move node gets one EMPTY_MOVE child instead of the panic */
+
+/* one node of the SoA pool as read back for inspection (mcts/node.rs:9-19) */
+typedef struct {
+    int32_t parent; /* -1 = root */
+    float visits, value;
+    diee_move action; /* tictactoe: from1 = cell */
+    int32_t n_moves;  /* legal moves of the node's state (expandable_moves at creation) */
+    int32_t n_untried;
+} diee_node;
+
+typedef struct diee_ctx diee_ctx;
+
+/* ---- context ---- */
+int32_t diee_ctx_create(int32_t device, diee_ctx **out);
+int32_t diee_ctx_destroy(diee_ctx *ctx);
+/* use an existing CUDA stream (cudaStream_t) for all launches of this ctx; NULL = ctx's own */
+int32_t diee_ctx_set_stream(diee_ctx *ctx, void *cuda_stream);
+int32_t diee_sync(diee_ctx *ctx);
+const char *diee_last_error(const diee_ctx *ctx);
+const char *diee_version(void);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+int64_t diee_launch_count(const diee_ctx *ctx);
+/* raw device memory owned by the library (so hosts without a CUDA allocator can use *_dev) */
+int32_t diee_dev_alloc(diee_ctx *ctx, uint64_t bytes, void **dptr_out);
+int32_t diee_dev_free(diee_ctx *ctx, void *dptr);
+int32_t diee_dev_upload(diee_ctx *ctx, void *dptr, const void *host, uint64_t bytes);
+int32_t diee_dev_download(diee_ctx *ctx, void *host, const void *dptr, uint64_t bytes);
+
+/* ---- the injected stream, host side (same function the kernels evaluate) ---- */
+void diee_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]);
+
+/* ---- backgammon env ----
+ * get_valid_moves (backgammon_logic.rs:403-414): ordered, de-duplicated legal plays of each
+ * state.  moves_out[i*DIEE_MAX_MOVES + k], counts_out[i]; ids_out (nullable) = encode() of each
+ * play (backgammon_logic.rs:262-359).  counts_out[i] = DIEE_ERR_NOT_ROLLED for an unrolled state. */
+int32_t diee_bg_valid_moves(diee_ctx *ctx, const diee_bg_state *states, int32_t n, diee_move *moves_out,
+                            int32_t *counts_out, uint16_t *ids_out);
+int32_t diee_bg_valid_moves_dev(diee_ctx *ctx, const diee_bg_state *states, int32_t n, diee_move *moves_out,
+                                int32_t *counts_out, uint16_t *ids_out);
+/* apply_move / skip_turn (backgammon_logic.rs:176-196) with the dice of the next roll injected:
+ * moves[i] == EMPTY_MOVE -> skip_turn.  next_rolls[2*i..] are used only when the turn passes. */
+int32_t diee_bg_apply_moves(diee_ctx *ctx, diee_bg_state *states, const diee_move *moves,
+                            const uint8_t *next_rolls, int32_t n);
+int32_t diee_bg_apply_moves_dev(diee_ctx *ctx, diee_bg_state *states, const diee_move *moves,
+                                const uint8_t *next_rolls, int32_t n);
+/* random-vs-random playout of whole games (Agent::Random both sides, versus.rs:160-268,307-316),
+ * fused in one launch: game i uses stream DIEE_STREAM_GAME of game id first_game_id+i; stops at a
+ * winner or after round_limit plies.  winners_out: -1/+1, 0 at the cap.  finals_out nullable. */
+int32_t diee_bg_playout(diee_ctx *ctx, const diee_bg_state *starts, int32_t n, uint64_t seed,
+                        uint32_t first_game_id, int32_t round_limit, int8_t *winners_out,
+                        int32_t *plies_out, diee_bg_state *finals_out);
+int32_t diee_bg_playout_dev(diee_ctx *ctx, const diee_bg_state *starts, int32_t n, uint64_t seed,
+                            uint32_t first_game_id, int32_t round_limit, int8_t *winners_out,
+                            int32_t *plies_out, diee_bg_state *finals_out);
+/* encode / decode one play per state (backgammon_logic.rs:262-401) */
+int32_t diee_bg_encode_moves(diee_ctx *ctx, const diee_bg_state *states, const diee_move *moves, int32_t n,
+                             uint16_t *ids_out);
+int32_t diee_bg_decode_moves(diee_ctx *ctx, const diee_bg_state *states, const uint16_t *ids, int32_t n,
+                             diee_move *moves_out);
+/* as_tensor (backgammon_logic.rs:198-252): out[i] = f32 [6,4,6] */
+int32_t diee_bg_encode_states(diee_ctx *ctx, const diee_bg_state *states, int32_t n, float *out);
+int32_t diee_bg_encode_states_dev(diee_ctx *ctx, const diee_bg_state *states, int32_t n, float *out);
+
+/* ---- pure MCTS: mct_search (mcts/simple_mcts.rs:10-39), one independent search per state ----
+ * states: diee_bg_state[n] or diee_ttt_state[n] by game_kind; players[i] = the player the value
+ * is counted for (versus.rs:305 passes game.get_player()).  Game i has global id first_game_id+i.
+ * best_moves_out: diee_move[n] (backgammon) or uint8[n] (tictactoe; 10 = EMPTY_MOVE).
+ * status_out[i]: DIEE_OK / DIEE_ERR_NO_MOVES_PANIC / DIEE_ERR_OVERFLOW per game.
+ * Optional pool read-back (all nullable): nodes_out[n*(iterations+1)], node_states_out (same
+ * count, state type by game_kind), n_nodes_out[n]; sim_plies_out[n] = rollout plies executed. */
+int32_t diee_mcts_search(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
+                         const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
+                         uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
+                         int32_t *status_out, diee_node *nodes_out, void *node_states_out,
+                         int32_t *n_nodes_out, uint64_t *sim_plies_out);
+/* device-resident form: states/players/best_moves/status are device pointers; the node pool
+ * lives in the ctx (HBM) and is reused between calls.  sim_plies_dev nullable (uint64[n]). */
+int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
+                             const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
+                             uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
+                             int32_t *status_out, uint64_t *sim_plies_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

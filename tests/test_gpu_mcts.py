@@ -1,0 +1,118 @@
+"""GPU parity tests for pure MCTS (mct_search) through the C ABI against the CPU oracle.
+Bar: bit-exact -- every node's parent/visits/value/action/move counts and state, the chosen
+move, the per-game status (incl. the reference's panic, Q6) in both rollout modes (Q5)."""
+import numpy as np
+import pytest
+
+import positions
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from die_e_b200 import _ffi
+    return _ffi.Context(0)
+
+
+def _cmp_trees(oracle, ffi, ctx, kind, states, players, cfg, seed, first, epoch):
+    best, status, plies, nodes, nstates, n_nodes = ctx.mcts_search(kind, states, players, cfg, seed, first, epoch, dump=True)
+    total_plies = 0
+    for i in range(len(states)):
+        if kind == ffi.GAME_BACKGAMMON:
+            rc, obest, onodes, ostates = oracle.mcts_search_bg(states[i:i + 1], int(players[i]), cfg, seed, first + i, epoch)
+        else:
+            rc, obest, onodes, ostates = oracle.mcts_search_ttt(states[i:i + 1], int(players[i]), cfg, seed, first + i, epoch)
+        assert status[i] == rc, (i, status[i], rc)
+        assert n_nodes[i] == len(onodes), i
+        k = len(onodes)
+        got = nodes[i, :k]
+        for f in ("parent", "n_moves", "n_untried"):
+            assert (got[f] == onodes[f]).all(), (i, f)
+        assert got["visits"].tobytes() == onodes["visits"].tobytes(), i       # bit-exact f32
+        assert got["value"].tobytes() == onodes["value"].tobytes(), i
+        assert got["action"].tobytes() == onodes["action"].tobytes(), i
+        assert nstates[i, :k].tobytes() == ostates.tobytes(), i
+        if kind == ffi.GAME_BACKGAMMON:
+            assert best[i:i + 1].tobytes() == obest.tobytes(), i
+        else:
+            assert best[i] == obest, i
+        total_plies += int(plies[i])
+    return status, total_plies
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_backgammon_mcts_bit_exact(ctx, oracle, mode):
+    from die_e_b200 import _ffi as ffi
+    states = positions.midgame_positions(seed=77, n=48, max_adv=120)
+    players = states["player"].copy()
+    cfg = oracle.mcts_cfg(iterations=60, c=2.0, limit=40, mode=mode)
+    status, plies = _cmp_trees(oracle, ffi, ctx, ffi.GAME_BACKGAMMON, states, players, cfg, 0xD1EE, 1000, 3)
+    assert plies > 0
+    if not (mode & 2):
+        # without PASS_CHILD some searches must hit the reference's panic (4.3 % of plies have no move)
+        pass
+
+
+def test_backgammon_mcts_reference_config(ctx, oracle):
+    """config 3 parameters (iterations=100, c=2, limit=400), reference-exact rollouts, PASS_CHILD"""
+    from die_e_b200 import _ffi as ffi
+    states = positions.midgame_positions(seed=5, n=12, max_adv=80)
+    cfg = oracle.mcts_cfg(iterations=100, c=2.0, limit=400, mode=2)
+    status, plies = _cmp_trees(oracle, ffi, ctx, ffi.GAME_BACKGAMMON, states, states["player"].copy(), cfg, 9, 0, 0)
+    assert (status == 0).all()
+    assert plies == 12 * 100 * 400  # Q5: every rollout runs the full limit in reference-exact mode
+
+
+def test_backgammon_mcts_panic_and_terminal(ctx, oracle):
+    from die_e_b200 import _ffi as ffi
+    pts = [0] * 24
+    pts[20] = -1
+    pts[19] = 2
+    pts[18] = 2
+    blocked = oracle.make_state(pts, off=(14, 11), roll=(1, 2), player=-1)      # no legal move at the root
+    won = oracle.make_state([0] * 24, off=(15, 3), roll=(1, 2), player=1)
+    pts2 = [0] * 24
+    pts2[0] = -1
+    pts2[23] = 1
+    near = oracle.make_state(pts2, off=(14, 14), roll=(3, 4), player=-1)        # children are terminal
+    states = np.concatenate([blocked, won, near])
+    players = np.array([-1, 1, -1], dtype=np.int8)
+    for mode in (0, 2):
+        cfg = oracle.mcts_cfg(iterations=30, c=2.0, limit=20, mode=mode)
+        status, _ = _cmp_trees(oracle, ffi, ctx, ffi.GAME_BACKGAMMON, states, players, cfg, 4, 0, 0)
+        assert status[0] == (ffi.ERR_NO_MOVES_PANIC if mode == 0 else 0)
+        assert status[1] == 0 and status[2] == 0
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tictactoe_mcts_bit_exact(ctx, oracle, mode):
+    from die_e_b200 import _ffi as ffi
+    rng = np.random.default_rng(2)
+    states = []
+    for g in range(64):
+        s = oracle.ttt_new()
+        for _ in range(int(rng.integers(0, 7))):
+            if oracle.ttt_check_winner(s) is not None:
+                break
+            mv = oracle.ttt_valid_moves(s)
+            oracle.ttt_apply_move(s, int(rng.choice(mv)))
+        states.append(s)
+    states = np.concatenate(states)
+    cfg = oracle.mcts_cfg(iterations=100, c=2.0, limit=400, mode=mode)
+    _cmp_trees(oracle, ffi, ctx, ffi.GAME_TICTACTOE, states, states["player"].copy(), cfg, 123, 0, 1)
+
+
+def test_mct_search_host_api(ctx, oracle):
+    from die_e_b200 import Backgammon, MctsConfig, TicTacToe, mct_search, _ffi as ffi
+    t = TicTacToe.new()
+    t.apply_move(4)
+    cfg = MctsConfig(iterations=50, simulate_round_limit=20)
+    mv = mct_search(t, t.get_player(), cfg, seed=3, game_id=7, ctx=ctx)
+    rc, obest, _, _ = oracle.mcts_search_ttt(t.s, t.get_player(), oracle.mcts_cfg(50, 2.0, 20), 3, 7, 0)
+    assert mv == obest and mv in t.get_valid_moves()
+    bg = Backgammon.new(ctx, seed=3, game_id=1)
+    bg.roll_die()
+    cfg = MctsConfig(iterations=30, simulate_round_limit=10, mode_flags=ffi.MODE_PASS_CHILD)
+    mv = mct_search(bg, bg.get_player(), cfg, seed=3, game_id=1, ctx=ctx)
+    assert mv in bg.get_valid_moves()

@@ -1,0 +1,410 @@
+#!/usr/bin/env python3
+"""bench.py -- the die-e hot path on B200: MCTS simulations/sec.
+
+Default workload = BASELINE.json configs[2]: backgammon pure MCTS (random rollouts),
+iterations=100, exploration_const=2, simulate_round_limit=400, 1,024 games batched per GPU.
+A "step" is one `mct_search` for every game of the batch (the call `versus.rs:303-306` makes each
+arena round) = games x iterations simulations.  `--workload playout` runs configs[1]
+(65,536 random-vs-random games per GPU, env step + legal-move generation only; unit plies/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload mcts|playout] [--games G] [--rollout ref_exact|check_current]
+
+N > 1: launched by torchrun, one rank per GPU; games are sharded (rank r owns global game ids
+[r*G, (r+1)*G)), no data-path collective (weak scaling); time = max over ranks.
+
+--impl reference: the reference's own CPU path for the same config -- the C oracle restating
+`mct_search` (the Rust reference cannot be built here: no cargo/rustc), one task per game over
+all host threads like rayon's par_iter, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0xD1EE
+OPENING = [2, 0, 0, 0, 0, -5, 0, -3, 0, 0, 0, 5, -5, 0, 0, 0, 3, 0, 5, 0, 0, 0, 0, -2]
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.samples, self._stop, self._t = gpu_index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 6 and s[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def initial_states(ffi, first_gid, n):
+    s = np.zeros(n, dtype=ffi.BG_STATE)
+    s["pts"][:] = OPENING
+    s["player"] = -1
+    for g in range(n):
+        w = ffi.philox(SEED, 0, first_gid + g, ffi.STREAM_INIT, 0)
+        s["roll"][g] = (ffi.die_of(w[0]), ffi.die_of(w[1]))
+    return s
+
+
+def midgame_states(ctx, ffi, first_gid, n):
+    """SURVEY 8(d) M-inputs: game g advanced k plies of random play, k = 10*(g % 9) in 0..80 (made with
+    the product's own playout kernel; never terminal this early -- the shortest game is ~40 plies)"""
+    s = initial_states(ffi, first_gid, n)
+    out = s.copy()
+    for grp in range(1, 9):
+        idx = np.arange(grp, n, 9)
+        if len(idx) == 0:
+            continue
+        # one launch over the whole batch keeps every game on its own id-keyed stream
+        _, _, fin_all = ctx.bg_playout(s, seed=SEED, first_game_id=first_gid, round_limit=10 * grp, want_finals=True)
+        out[idx] = fin_all[idx]
+    alive = (out["off"][:, 0] < 15) & (out["off"][:, 1] < 15)
+    out[~alive] = s[~alive]
+    return out
+
+
+def bsim_bytes(stats, n_sims):
+    """algorithmic HBM bytes per simulation for the SoA pool:
+    select: per level 8 B (move counts + visits of the node) + 12 B per child (parent, visits, value);
+    expand: 32 B parent state + 4 B count update + 32 B child state + 20 B child fields;
+    backprop: 20 B per node on the path (visits+value read-modify-write, parent link)."""
+    lv = float(stats["select_levels"].sum())
+    ch = float(stats["select_children"].sum())
+    ex = float(stats["expansions"].sum())
+    path_nodes = lv + n_sims  # a leaf at depth d has d+1 nodes on its path
+    total = 8.0 * lv + 12.0 * ch + 88.0 * ex + 20.0 * path_nodes
+    return total / max(1, n_sims)
+
+
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from die_e_b200 import _ffi as ffi
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = ffi.Context(local)
+    # an explicit (non-default) torch stream: the ctx launches on it, the timing events are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+    hbm_peak, peak_src = peaks()
+    G = args.games
+    first_gid = rank * G
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    if args.workload == "mcts":
+        mode = ffi.MODE_PASS_CHILD | (ffi.MODE_ROLLOUT_CHECK_CURRENT if args.rollout == "check_current" else 0)
+        cfg = np.zeros(1, dtype=ffi.MCTS_CFG)
+        cfg[0] = (args.iterations, 2.0, args.round_limit, 0.3, 0.25, mode)
+        h_states = midgame_states(ctx, ffi, first_gid, G)
+        h_players = h_states["player"].copy()
+        d_states = torch.from_numpy(h_states.view(np.uint8).reshape(G, 32)).to(dev)
+        d_players = torch.from_numpy(h_players).to(dev)
+        d_best = torch.zeros(G, dtype=torch.int32, device=dev)
+        d_status = torch.zeros(G, dtype=torch.int32, device=dev)
+        d_stats = torch.zeros(G, 24, dtype=torch.uint8, device=dev)
+        units_per_step = G * args.iterations
+
+        def step_dev(i):
+            ctx.mcts_search_dev(ffi.GAME_BACKGAMMON, d_states.data_ptr(), G, d_players.data_ptr(), cfg, SEED, first_gid,
+                                i & 0xFFFF, d_best.data_ptr(), d_status.data_ptr(), d_stats.data_ptr())
+
+        # e2e: the public host-buffer call (what versus.rs's Agent::Mcts arm maps to) from pinned memory
+        p_states = torch.from_numpy(h_states.view(np.uint8).reshape(G, 32).copy()).pin_memory()
+        p_players = torch.from_numpy(h_players.copy()).pin_memory()
+        np_states, np_players = p_states.numpy().view(ffi.BG_STATE).reshape(-1), p_players.numpy()
+        h2d, d2h = G * 32 + G, G * 4 + G * 4 + G * 24
+
+        def step_e2e(i):
+            best, status, stats = ctx.mcts_search(ffi.GAME_BACKGAMMON, np_states, np_players, cfg, SEED, first_gid, i & 0xFFFF)
+            return stats
+
+        metric, unit = "mcts_simulations_per_sec", "simulations/s"
+        wl = (f"backgammon pure MCTS (BASELINE configs[2]): {G} games/GPU, iterations={args.iterations}, c=2, "
+              f"simulate_round_limit={args.round_limit}, rollout={args.rollout}, no-move nodes=PASS_CHILD")
+    else:
+        h_states = initial_states(ffi, first_gid, G)
+        d_states = torch.from_numpy(h_states.view(np.uint8).reshape(G, 32)).to(dev)
+        d_winners = torch.zeros(G, dtype=torch.int8, device=dev)
+        d_plies = torch.zeros(G, dtype=torch.int32, device=dev)
+        d_finals = torch.zeros(G, 32, dtype=torch.uint8, device=dev)
+
+        def step_dev(i):
+            ctx.bg_playout_dev(d_states.data_ptr(), G, SEED + i, first_gid, args.round_limit, d_winners.data_ptr(),
+                               d_plies.data_ptr(), d_finals.data_ptr())
+
+        p_states = torch.from_numpy(h_states.view(np.uint8).reshape(G, 32).copy()).pin_memory()
+        np_states = p_states.numpy().view(ffi.BG_STATE).reshape(-1)
+        h2d, d2h = G * 32, G * (1 + 4 + 32)
+
+        def step_e2e(i):
+            return ctx.bg_playout(np_states, SEED + i, first_gid, args.round_limit, want_finals=True)
+
+        units_per_step = None  # plies: read back per step
+        metric, unit = "playout_plies_per_sec", "plies/s"
+        wl = (f"backgammon random-vs-random playouts (BASELINE configs[1]): {G} games/GPU, env step + "
+              f"legal-move generation, cap {args.round_limit} plies")
+
+    # ---- warm-up ----
+    for i in range(args.warmup):
+        step_dev(i)
+        torch.cuda.synchronize()
+
+    # ---- timed: device-resident (`value`) ----
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    units = 0.0
+    stats_acc = None
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the event bracket)
+        evs[i][0].record(stream)
+        step_dev(args.warmup + i)
+        evs[i][1].record(stream)
+        if args.workload == "playout":
+            evs[i][1].synchronize()
+            units += float(d_plies.sum().item())
+        else:
+            evs[i][1].synchronize()
+            st = d_stats.cpu().numpy().view(ffi.SEARCH_STATS).reshape(-1)
+            stats_acc = st if stats_acc is None else np.concatenate([stats_acc, st])
+            units += units_per_step
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    kern_ms = [a.elapsed_time(b) for a, b in evs]
+    dev_ms = float(sum(kern_ms))
+    assert int(d_status.abs().sum().item()) == 0 if args.workload == "mcts" else True
+
+    # ---- timed: end to end through the host-buffer C-ABI call ----
+    step_e2e(0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_units = 0.0
+    for i in range(args.steps):
+        r = step_e2e(args.warmup + i)
+        e2e_units += units_per_step if args.workload == "mcts" else float(r[1].sum())
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks: max time, summed units ----
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s, t_wall], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        u = torch.tensor([units, e2e_units, float(launches)], device=dev, dtype=torch.float64)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s, t_wall = [float(x) for x in t.tolist()]
+        units, e2e_units, launches = [float(x) for x in u.tolist()]
+
+    out = None
+    if rank == 0:
+        value = units / (dev_ms / 1e3)
+        if args.workload == "mcts":
+            n_sims_local = G * args.iterations * args.steps
+            b_sim = bsim_bytes(stats_acc, n_sims_local)
+            alg_bytes = b_sim * G * args.iterations  # per launch
+            plies_per_sim = float(stats_acc["rollout_plies"].sum()) / n_sims_local
+            extra = {"bytes_per_simulation": round(b_sim, 1), "rollout_plies_per_simulation": round(plies_per_sim, 2),
+                     "rollout_plies_per_sec": round(value * plies_per_sim, 1),
+                     "mean_select_depth": round(float(stats_acc["select_levels"].sum()) / n_sims_local, 3)}
+        else:
+            alg_bytes = 64.0 * units / args.steps / world  # 32 B read + 32 B write per ply
+            extra = {"bytes_per_ply": 64, "games_per_sec": round(G * world * args.steps / (dev_ms / 1e3), 1),
+                     "mean_plies_per_game": round(units / (G * world * args.steps), 2)}
+        avg_launch_ms = float(np.mean(kern_ms))
+        achieved = alg_bytes / (avg_launch_ms / 1e3) / 1e9
+        out = {
+            "metric": metric, "value": round(value, 1), "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int8 boards / f32 UCB", "data": "synthetic",
+            "config": {"workload": wl, "seed": hex(SEED), "timing": "CUDA events per step on the launch stream, "
+                       "max over ranks; L2 flushed (256 MiB fill) between timed steps", "wall_s": round(t_wall, 3),
+                       "parallelism": f"games sharded over {world} GPU(s), no collective", **extra},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 4), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": round(achieved / hbm_peak, 8), "traffic": None, "peak_source": peak_src,
+                         "kernel": "mcts_search_kernel<BgGame>" if args.workload == "mcts" else "bg_playout_kernel",
+                         "note": "the path is integer-issue/latency bound, not HBM bound: the whole rollout runs in "
+                                 "registers + shared memory (SURVEY 8d M-roofline (2)); see DESIGN.md and profiles/"},
+            "e2e": {"value": round(e2e_units / e2e_s, 1), "unit": unit, "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out, (h_states if args.workload == "mcts" else h_states)
+
+
+def cpu_leg(args, h_states, seconds_target, threads, ffi_cfg_mode):
+    """times the oracle (C restatement of the reference's CPU path) on a bounded sample"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    orc.build()
+    if args.workload == "mcts":
+        cfg = orc.mcts_cfg(args.iterations, 2.0, args.round_limit, 0.3, 0.25, ffi_cfg_mode)
+        # calibrate on a few games, then size the sample for ~seconds_target
+        n0 = min(len(h_states), 2 * threads)
+        t0 = time.perf_counter()
+        orc.mcts_search_bg_batch(h_states[:n0], h_states["player"][:n0].copy(), cfg, SEED, 0, 0, threads)
+        dt = time.perf_counter() - t0
+        n = int(max(threads, min(len(h_states), n0 * seconds_target / max(dt, 1e-3))))
+        t0 = time.perf_counter()
+        orc.mcts_search_bg_batch(h_states[:n], h_states["player"][:n].copy(), cfg, SEED, 0, 0, threads)
+        dt = time.perf_counter() - t0
+        return n * args.iterations / dt, f"{n} of the {len(h_states)} games x {args.iterations} iterations, {dt:.1f} s", dt
+    n0 = min(len(h_states), 64 * threads)
+    t0 = time.perf_counter()
+    _, plies = orc.bg_playout_batch(h_states[:n0], SEED, 0, args.round_limit, threads)
+    dt = time.perf_counter() - t0
+    n = int(max(threads, min(len(h_states), n0 * seconds_target / max(dt, 1e-3))))
+    t0 = time.perf_counter()
+    _, plies = orc.bg_playout_batch(h_states[:n], SEED, 0, args.round_limit, threads)
+    dt = time.perf_counter() - t0
+    return float(plies.sum()) / dt, f"{n} of the {len(h_states)} games, {dt:.1f} s", dt
+
+
+def host_states_for_reference(args):
+    """the same synthetic inputs as the GPU arm, generated with the oracle (no GPU needed)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    orc.build()
+    G = args.games
+    s = np.zeros(G, dtype=orc.BG_STATE)
+    s["pts"][:] = OPENING
+    s["player"] = -1
+    for g in range(G):
+        w = orc.philox(SEED, 0, g, orc.STREAM_INIT, 0)
+        s["roll"][g] = (orc.die(w[0]), orc.die(w[1]))
+    if args.workload == "mcts":
+        n = min(G, 512)  # the bounded sample never needs more
+        s = s[:n]
+        for g in range(n):
+            for ply in range(10 * (g % 9)):
+                if orc.bg_check_winner(s[g:g + 1]) is not None:
+                    break
+                orc.bg_random_ply(s[g:g + 1], orc.philox(SEED, ply, g, orc.STREAM_GAME, 0))
+    return s
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mcts", choices=["mcts", "playout"])
+    ap.add_argument("--games", type=int, default=None)
+    ap.add_argument("--iterations", type=int, default=100)
+    ap.add_argument("--round-limit", type=int, default=400)
+    ap.add_argument("--rollout", default="ref_exact", choices=["ref_exact", "check_current"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.games is None:
+        args.games = 1024 if args.workload == "mcts" else 65536
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    threads = os.cpu_count() or 1
+    mode = 2 | (1 if args.rollout == "check_current" else 0)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        h_states = host_states_for_reference(args)
+        per_step = max(2.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
+        vals, sample = [], ""
+        t_all0 = time.perf_counter()
+        for i in range(args.warmup + args.steps):
+            v, sample, dt = cpu_leg(args, h_states, per_step, threads, mode)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        tot_units = sum(v * dt for v, dt in vals)
+        tot_s = sum(dt for _, dt in vals)
+        value = tot_units / tot_s
+        unit = "simulations/s" if args.workload == "mcts" else "plies/s"
+        line = {
+            "impl": "reference", "metric": "mcts_simulations_per_sec" if args.workload == "mcts" else "playout_plies_per_sec",
+            "value": round(value, 1), "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1e3 * tot_s / max(1, args.steps), 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8 boards / f32 UCB", "data": "synthetic",
+            "config": {"workload": f"same config as the GPU arm ({args.workload}, iterations={args.iterations}, "
+                       f"simulate_round_limit={args.round_limit}, rollout={args.rollout}); each step = a bounded "
+                       "sample of the games on the host CPU", "wall_s": round(time.perf_counter() - t_all0, 1)},
+            "cpu_baseline": {"value": round(value, 1), "unit": unit, "cores": threads, "kind": "port", "sample": sample,
+                             "note": "C oracle restating the reference's mct_search, one task per game over a pthread pool "
+                                     "(= rayon par_iter, versus.rs:303-306); the Rust reference cannot be built here; the C "
+                                     "port omits its deep clones and per-candidate allocations, so it is a stronger baseline"},
+            "e2e": {"value": round(value, 1), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    out, h_states = run_ours(args, rank, world)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            v, sample, _ = cpu_leg(args, h_states, args.cpu_seconds, threads, mode)
+            out["cpu_baseline"] = {"value": round(v, 1), "unit": out["unit"], "cores": threads, "kind": "port", "sample": sample}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

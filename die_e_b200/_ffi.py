@@ -26,6 +26,9 @@ MCTS_CFG = np.dtype([("iterations", "u4"), ("c", "f4"), ("simulate_round_limit",
                      ("dirichlet_alpha", "f4"), ("dirichlet_epsilon", "f4"), ("mode_flags", "u4")])
 NODE = np.dtype([("parent", "i4"), ("visits", "f4"), ("value", "f4"), ("action", MOVE),
                  ("n_moves", "i4"), ("n_untried", "i4")])
+SEARCH_STATS = np.dtype([("rollout_plies", "u8"), ("select_levels", "u4"), ("select_children", "u4"),
+                         ("expansions", "u4"), ("terminal_leaves", "u4")])
+assert SEARCH_STATS.itemsize == 24
 assert BG_STATE.itemsize == 32 and MOVE.itemsize == 4 and TTT_STATE.itemsize == 16 and NODE.itemsize == 24
 
 # every symbol include/diee.h declares (tests check the .so exports each one)
@@ -178,17 +181,17 @@ class Context:
         cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]
         best = np.zeros(n, dtype=MOVE) if game_kind == GAME_BACKGAMMON else np.zeros(n, dtype=np.uint8)
         status = np.zeros(n, dtype=np.int32)
-        plies = np.zeros(n, dtype=np.uint64)
+        stats = np.zeros(n, dtype=SEARCH_STATS)
         cap = int(cfg["iterations"][0]) + 1
         nodes = np.zeros((n, cap), dtype=NODE) if dump else None
         nstates = np.zeros((n, cap), dtype=sdt) if dump else None
         n_nodes = np.zeros(n, dtype=np.int32) if dump else None
         self._chk(lib().diee_mcts_search(self._h, C.c_int32(game_kind), _p(states), C.c_int32(n), _p(players), _p(cfg),
                                          C.c_uint64(seed), C.c_uint32(first_game_id), C.c_uint32(epoch), _p(best),
-                                         _p(status), _p(nodes), _p(nstates), _p(n_nodes), _p(plies)))
+                                         _p(status), _p(nodes), _p(nstates), _p(n_nodes), _p(stats)))
         if dump:
-            return best, status, plies, nodes, nstates, n_nodes
-        return best, status, plies
+            return best, status, stats, nodes, nstates, n_nodes
+        return best, status, stats
 
     # ---- device-pointer forms (ints = raw device addresses, e.g. torch tensor .data_ptr()) ----
     def bg_playout_dev(self, d_starts, n, seed, first_game_id, round_limit, d_winners, d_plies, d_finals=0):
@@ -201,11 +204,11 @@ class Context:
     def bg_encode_states_dev(self, d_states, n, d_out):
         self._chk(lib().diee_bg_encode_states_dev(self._h, _p(d_states), C.c_int32(n), _p(d_out)))
 
-    def mcts_search_dev(self, game_kind, d_states, n, d_players, cfg, seed, first_game_id, epoch, d_best, d_status, d_plies=0):
+    def mcts_search_dev(self, game_kind, d_states, n, d_players, cfg, seed, first_game_id, epoch, d_best, d_status, d_stats=0):
         cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]
         self._chk(lib().diee_mcts_search_dev(self._h, C.c_int32(game_kind), _p(d_states), C.c_int32(n), _p(d_players), _p(cfg),
                                              C.c_uint64(seed), C.c_uint32(first_game_id), C.c_uint32(epoch), _p(d_best),
-                                             _p(d_status), _p(d_plies)))
+                                             _p(d_status), _p(d_stats)))
 
 
 _default_ctx = None

@@ -342,7 +342,7 @@ static int32_t check_mcts_args(diee_ctx *ctx, int32_t game_kind, const void *sta
 int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
                              const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
                              uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
-                             int32_t *status_out, uint64_t *sim_plies_dev) {
+                             int32_t *status_out, diee_search_stats *stats_dev) {
     int32_t rc = check_mcts_args(ctx, game_kind, states, n, players, cfg, best_moves_out, status_out, epoch);
     if (rc != DIEE_OK) return rc;
     if (n == 0) return DIEE_OK;
@@ -357,7 +357,7 @@ int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *state
         best32 = (uint32_t *)ctx->s_best.p;
     }
     CU(launch_mcts_search(ctx->stream, game_kind, states, n, players, *cfg, seed, first_game_id, epoch, pp,
-                          (const float *)ctx->ln_table.p, best32, status_out, (unsigned long long *)sim_plies_dev));
+                          (const float *)ctx->ln_table.p, best32, status_out, stats_dev));
     ctx->launches += 1;
     if (game_kind == DIEE_GAME_TICTACTOE) {
         // EMPTY_MOVE = 10 (tictactoe/mod.rs:18); done on the host side of the stream for this tiny case
@@ -376,7 +376,7 @@ int32_t diee_mcts_search(diee_ctx *ctx, int32_t game_kind, const void *states, i
                          const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
                          uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
                          int32_t *status_out, diee_node *nodes_out, void *node_states_out,
-                         int32_t *n_nodes_out, uint64_t *sim_plies_out) {
+                         int32_t *n_nodes_out, diee_search_stats *stats_out) {
     int32_t rc = check_mcts_args(ctx, game_kind, states, n, players, cfg, best_moves_out, status_out, epoch);
     if (rc != DIEE_OK) return rc;
     if (n == 0) return DIEE_OK;
@@ -392,15 +392,15 @@ int32_t diee_mcts_search(diee_ctx *ctx, int32_t game_kind, const void *states, i
     RESERVE(ctx->s_players, (size_t)n);
     RESERVE(ctx->s_moves, sizeof(uint32_t) * (size_t)n);
     RESERVE(ctx->s_status, sizeof(int32_t) * (size_t)n);
-    RESERVE(ctx->s_plies, sizeof(uint64_t) * (size_t)n);
+    RESERVE(ctx->s_plies, sizeof(diee_search_stats) * (size_t)n);
     CU(cudaMemcpyAsync(ctx->s_states.p, states, ss * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->s_players.p, players, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     rc = diee_mcts_search_dev(ctx, game_kind, ctx->s_states.p, n, (const int8_t *)ctx->s_players.p, cfg, seed, first_game_id,
-                              epoch, ctx->s_moves.p, (int32_t *)ctx->s_status.p, (uint64_t *)ctx->s_plies.p);
+                              epoch, ctx->s_moves.p, (int32_t *)ctx->s_status.p, (diee_search_stats *)ctx->s_plies.p);
     if (rc != DIEE_OK) return rc;
     CU(cudaMemcpyAsync(best_moves_out, ctx->s_moves.p, best_sz * n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(status_out, ctx->s_status.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (sim_plies_out) CU(cudaMemcpyAsync(sim_plies_out, ctx->s_plies.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (stats_out) CU(cudaMemcpyAsync(stats_out, ctx->s_plies.p, sizeof(diee_search_stats) * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (n_nodes_out) CU(cudaMemcpyAsync(n_nodes_out, ctx->p_nnodes.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     const size_t total = ((size_t)cfg->iterations + 1) * (size_t)n;
     if (node_states_out) CU(cudaMemcpyAsync(node_states_out, ctx->p_states.p, ss * total, cudaMemcpyDeviceToHost, ctx->stream));

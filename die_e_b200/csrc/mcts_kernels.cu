@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32)
 mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int8_t *__restrict__ players,
                    diee_mcts_cfg cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch, Pool pool,
                    const float *__restrict__ ln_table, uint32_t *__restrict__ best_out, int32_t *__restrict__ status_out,
-                   unsigned long long *__restrict__ sim_plies_out) {
+                   diee_search_stats *__restrict__ stats_out) {
     __shared__ WarpSlab slabs[MCTS_WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gidx = blockIdx.x * MCTS_WARPS_PER_CTA + wib;
@@ -114,6 +114,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     int status = DIEE_OK;
     int n_nodes = 0;
     unsigned long long plies = 0;
+    uint32_t sel_levels = 0, sel_children = 0, terminal_leaves = 0;
     bool ovf = false;
 
     if (game.winner() == NO_WINNER) {  // simple_mcts.rs:12-14
@@ -134,6 +135,8 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                 nmv = nm[cur];
                 const int nmoves = (int)(nmv >> 16), nunt = (int)(nmv & 0xFFFFu);
                 if (nunt != 0 || nmoves == 0) break;  // has untried moves, or no children at all
+                ++sel_levels;
+                sel_children += (uint32_t)nmoves;
                 // select_ucb :41-52 over the children of cur (creation order = index order)
                 const float pvis = visits[cur];
                 const float lnp = ln_table[(int)pvis];
@@ -168,6 +171,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
             float result;
             if (w != NO_WINNER) {
                 result = outcome(w, player);  // :25-30
+                ++terminal_leaves;
             } else {
                 if (nunt == 0) { status = DIEE_ERR_NO_MOVES_PANIC; break; }  // node.rs:119-121 (Q6)
                 // ---- Node::expand node.rs:118-137: pop the LAST untried move ----
@@ -250,7 +254,12 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
         best_out[gidx] = best;
         status_out[gidx] = status;
         pool.n_nodes[gidx] = n_nodes;
-        if (sim_plies_out) sim_plies_out[gidx] = plies;
+        if (stats_out) {
+            diee_search_stats ss;
+            ss.rollout_plies = plies; ss.select_levels = sel_levels; ss.select_children = sel_children;
+            ss.expansions = n_nodes > 0 ? (uint32_t)(n_nodes - 1) : 0u; ss.terminal_leaves = terminal_leaves;
+            stats_out[gidx] = ss;
+        }
     }
 }
 
@@ -259,17 +268,17 @@ static inline int mcts_grid(int n) { return (n + MCTS_WARPS_PER_CTA - 1) / MCTS_
 cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots, int n, const int8_t *players,
                                const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
                                const PoolPtrs &pp, const float *ln_table, uint32_t *best_out, int32_t *status_out,
-                               unsigned long long *sim_plies_out) {
+                               diee_search_stats *stats_out) {
     if (n <= 0) return cudaSuccess;
     Pool pool{pp.states, pp.parent, pp.visits, pp.value, pp.action, pp.nmoves, pp.n_nodes};
     if (game_kind == DIEE_GAME_BACKGAMMON)
         mcts_search_kernel<BgGame><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
             static_cast<const diee_bg_state *>(roots), n, players, cfg, seed, first_game_id, epoch, pool, ln_table,
-            best_out, status_out, sim_plies_out);
+            best_out, status_out, stats_out);
     else
         mcts_search_kernel<TttGame><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
             static_cast<const diee_ttt_state *>(roots), n, players, cfg, seed, first_game_id, epoch, pool, ln_table,
-            best_out, status_out, sim_plies_out);
+            best_out, status_out, stats_out);
     return cudaGetLastError();
 }
 

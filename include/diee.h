@@ -115,6 +115,15 @@ typedef struct {
     int32_t n_untried;
 } diee_node;
 
+/* per-game work counters of one search (feed the roofline arithmetic in bench.py) */
+typedef struct {
+    uint64_t rollout_plies;   /* plies executed inside Node::simulate */
+    uint32_t select_levels;   /* select_ucb calls (tree levels descended) */
+    uint32_t select_children; /* children scored over all select_ucb calls */
+    uint32_t expansions;      /* nodes created */
+    uint32_t terminal_leaves; /* iterations that ended on a terminal leaf */
+} diee_search_stats;
+
 typedef struct diee_ctx diee_ctx;
 
 /* ---- context ---- */
@@ -174,18 +183,18 @@ int32_t diee_bg_encode_states_dev(diee_ctx *ctx, const diee_bg_state *states, in
  * best_moves_out: diee_move[n] (backgammon) or uint8[n] (tictactoe; 10 = EMPTY_MOVE).
  * status_out[i]: DIEE_OK / DIEE_ERR_NO_MOVES_PANIC / DIEE_ERR_OVERFLOW per game.
  * Optional pool read-back (all nullable): nodes_out[n*(iterations+1)], node_states_out (same
- * count, state type by game_kind), n_nodes_out[n]; sim_plies_out[n] = rollout plies executed. */
+ * count, state type by game_kind), n_nodes_out[n]; stats_out[n] = work counters. */
 int32_t diee_mcts_search(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
                          const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
                          uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
                          int32_t *status_out, diee_node *nodes_out, void *node_states_out,
-                         int32_t *n_nodes_out, uint64_t *sim_plies_out);
+                         int32_t *n_nodes_out, diee_search_stats *stats_out);
 /* device-resident form: states/players/best_moves/status are device pointers; the node pool
- * lives in the ctx (HBM) and is reused between calls.  sim_plies_dev nullable (uint64[n]). */
+ * lives in the ctx (HBM) and is reused between calls.  stats_dev nullable (diee_search_stats[n]). */
 int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
                              const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
                              uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
-                             int32_t *status_out, uint64_t *sim_plies_dev);
+                             int32_t *status_out, diee_search_stats *stats_dev);
 
 #ifdef __cplusplus
 }

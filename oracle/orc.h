@@ -159,6 +159,13 @@ int orc_mcts_search_ttt(const orc_ttt_state *root, int player, const orc_mcts_cf
                         uint32_t game_id, uint32_t epoch, uint8_t *best, orc_node_stats *nodes_out,
                         orc_ttt_state *states_out, int32_t *n_nodes_out);
 
+/* ---- thread-pool batch drivers (the reference's rayon par_iter over games, versus.rs:303-316) ---- */
+int orc_mcts_search_bg_batch(const orc_bg_state *states, int n, const int8_t *players, const orc_mcts_cfg *cfg,
+                             uint64_t seed, uint32_t first_game_id, uint32_t epoch, orc_move *best, int32_t *status,
+                             int nthreads);
+int orc_bg_playout_batch(const orc_bg_state *states, int n, uint64_t seed, uint32_t first_game_id, int round_limit,
+                         int8_t *winners, int32_t *plies, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -320,3 +320,24 @@ def mcts_search_ttt(state, player, cfg, seed, game_id, epoch):
     rc = lib().orc_mcts_search_ttt(_p(np.ascontiguousarray(state).reshape(-1)[:1]), C.c_int(player), _p(cfg), C.c_uint64(seed),
                                    C.c_uint32(game_id), C.c_uint32(epoch), C.byref(best), _p(nodes), _p(states), C.byref(n))
     return rc, best.value, nodes[: n.value], states[: n.value]
+
+
+def mcts_search_bg_batch(states, players, cfg, seed, first_game_id, epoch, nthreads):
+    states = np.ascontiguousarray(states).reshape(-1)
+    n = len(states)
+    players = np.ascontiguousarray(players, dtype=np.int8)
+    best = np.zeros(n, dtype=MOVE)
+    status = np.zeros(n, dtype=np.int32)
+    lib().orc_mcts_search_bg_batch(_p(states), C.c_int(n), _p(players), _p(cfg), C.c_uint64(seed), C.c_uint32(first_game_id),
+                                   C.c_uint32(epoch), _p(best), _p(status), C.c_int(nthreads))
+    return best, status
+
+
+def bg_playout_batch(states, seed, first_game_id, round_limit, nthreads):
+    states = np.ascontiguousarray(states).reshape(-1)
+    n = len(states)
+    winners = np.zeros(n, dtype=np.int8)
+    plies = np.zeros(n, dtype=np.int32)
+    lib().orc_bg_playout_batch(_p(states), C.c_int(n), C.c_uint64(seed), C.c_uint32(first_game_id), C.c_int(round_limit),
+                               _p(winners), _p(plies), C.c_int(nthreads))
+    return winners, plies

@@ -186,11 +186,12 @@ class Context:
         nodes = np.zeros((n, cap), dtype=NODE) if dump else None
         nstates = np.zeros((n, cap), dtype=sdt) if dump else None
         n_nodes = np.zeros(n, dtype=np.int32) if dump else None
+        finals = np.zeros((n, cap - 1), dtype=sdt) if dump else None
         self._chk(lib().diee_mcts_search(self._h, C.c_int32(game_kind), _p(states), C.c_int32(n), _p(players), _p(cfg),
                                          C.c_uint64(seed), C.c_uint32(first_game_id), C.c_uint32(epoch), _p(best),
-                                         _p(status), _p(nodes), _p(nstates), _p(n_nodes), _p(stats)))
+                                         _p(status), _p(nodes), _p(nstates), _p(n_nodes), _p(stats), _p(finals)))
         if dump:
-            return best, status, stats, nodes, nstates, n_nodes
+            return best, status, stats, nodes, nstates, n_nodes, finals
         return best, status, stats
 
     # ---- device-pointer forms (ints = raw device addresses, e.g. torch tensor .data_ptr()) ----

@@ -29,7 +29,7 @@ struct diee_ctx {
     // scratch for host-buffer entry points
     DevBuf s_states, s_moves, s_counts, s_ids, s_aux, s_out, s_players, s_best, s_status, s_plies;
     // pure-MCTS node pool (HBM resident, reused between searches)
-    DevBuf p_states, p_parent, p_visits, p_value, p_action, p_nmoves, p_nnodes, ln_table;
+    DevBuf p_states, p_parent, p_visits, p_value, p_action, p_nmoves, p_nnodes, p_simnode, p_finals, ln_table;
     uint32_t ln_table_n = 0;
 };
 
@@ -92,7 +92,8 @@ int32_t diee_ctx_destroy(diee_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->s_states, &ctx->s_moves, &ctx->s_counts, &ctx->s_ids, &ctx->s_aux, &ctx->s_out,
                       &ctx->s_players, &ctx->s_best, &ctx->s_status, &ctx->s_plies, &ctx->p_states, &ctx->p_parent,
-                      &ctx->p_visits, &ctx->p_value, &ctx->p_action, &ctx->p_nmoves, &ctx->p_nnodes, &ctx->ln_table};
+                      &ctx->p_visits, &ctx->p_value, &ctx->p_action, &ctx->p_nmoves, &ctx->p_nnodes, &ctx->p_simnode, &ctx->p_finals,
+                      &ctx->ln_table};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -314,6 +315,8 @@ static int32_t ensure_pool(diee_ctx *ctx, int game_kind, int n, const diee_mcts_
     RESERVE(ctx->p_action, sizeof(uint32_t) * total);
     RESERVE(ctx->p_nmoves, sizeof(uint32_t) * total);
     RESERVE(ctx->p_nnodes, sizeof(int32_t) * (size_t)n);
+    RESERVE(ctx->p_simnode, sizeof(int32_t) * (size_t)cfg->iterations * (size_t)n);
+    RESERVE(ctx->p_finals, state_size(game_kind) * (size_t)cfg->iterations * (size_t)n);
     if (ctx->ln_table_n < cfg->iterations + 2) {
         // ln of every possible (integer-valued) visit count, correctly rounded from double:
         // the contract's replacement for f32::ln (node.rs:91)
@@ -350,15 +353,20 @@ int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *state
     rc = ensure_pool(ctx, game_kind, n, cfg);
     if (rc != DIEE_OK) return rc;
     PoolPtrs pp{ctx->p_states.p, (int32_t *)ctx->p_parent.p, (float *)ctx->p_visits.p, (float *)ctx->p_value.p,
-                (uint32_t *)ctx->p_action.p, (uint32_t *)ctx->p_nmoves.p, (int32_t *)ctx->p_nnodes.p};
+                (uint32_t *)ctx->p_action.p, (uint32_t *)ctx->p_nmoves.p, (int32_t *)ctx->p_nnodes.p,
+                (int32_t *)ctx->p_simnode.p, ctx->p_finals.p};
+    const size_t pairs = (size_t)cfg->iterations * (size_t)n;
+    CU(cudaMemsetAsync(ctx->p_simnode.p, 0xFF, sizeof(int32_t) * pairs, ctx->stream));
+    CU(cudaMemsetAsync(ctx->p_finals.p, 0, state_size(game_kind) * pairs, ctx->stream));
     uint32_t *best32 = (uint32_t *)best_moves_out;
+    int nl = 0;
     if (game_kind == DIEE_GAME_TICTACTOE) {  // kernel writes u32 per game; narrow to u8 afterwards
         RESERVE(ctx->s_best, sizeof(uint32_t) * (size_t)n);
         best32 = (uint32_t *)ctx->s_best.p;
     }
     CU(launch_mcts_search(ctx->stream, game_kind, states, n, players, *cfg, seed, first_game_id, epoch, pp,
-                          (const float *)ctx->ln_table.p, best32, status_out, stats_dev));
-    ctx->launches += 1;
+                          (const float *)ctx->ln_table.p, best32, status_out, stats_dev, &nl));
+    ctx->launches += nl;
     if (game_kind == DIEE_GAME_TICTACTOE) {
         // EMPTY_MOVE = 10 (tictactoe/mod.rs:18); done on the host side of the stream for this tiny case
         std::vector<uint32_t> h((size_t)n);
@@ -376,7 +384,7 @@ int32_t diee_mcts_search(diee_ctx *ctx, int32_t game_kind, const void *states, i
                          const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
                          uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
                          int32_t *status_out, diee_node *nodes_out, void *node_states_out,
-                         int32_t *n_nodes_out, diee_search_stats *stats_out) {
+                         int32_t *n_nodes_out, diee_search_stats *stats_out, void *rollout_finals_out) {
     int32_t rc = check_mcts_args(ctx, game_kind, states, n, players, cfg, best_moves_out, status_out, epoch);
     if (rc != DIEE_OK) return rc;
     if (n == 0) return DIEE_OK;
@@ -404,6 +412,8 @@ int32_t diee_mcts_search(diee_ctx *ctx, int32_t game_kind, const void *states, i
     if (n_nodes_out) CU(cudaMemcpyAsync(n_nodes_out, ctx->p_nnodes.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     const size_t total = ((size_t)cfg->iterations + 1) * (size_t)n;
     if (node_states_out) CU(cudaMemcpyAsync(node_states_out, ctx->p_states.p, ss * total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rollout_finals_out)
+        CU(cudaMemcpyAsync(rollout_finals_out, ctx->p_finals.p, ss * (size_t)cfg->iterations * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<int32_t> parent;
     std::vector<float> visits, value;
     std::vector<uint32_t> action, nmoves;

@@ -214,6 +214,7 @@ __device__ __forceinline__ int bg_movegen(const BgWarp &g, WarpSlab &slab, int l
     const uint32_t oppblot = __ballot_sync(FULL, pv == -1) & M24;
     const uint32_t freem = ~oppblk & M24;
     const int bar_own = p < 0 ? g.bar0 : g.bar1;
+    if (own1 == 0 && bar_own == 0) return 0;  // nothing left to move (the side has borne everything off)
     const uint32_t home = p < 0 ? 0x3Fu : 0xFC0000u;
     const uint32_t outside = own1 & ~home;
 

@@ -14,6 +14,8 @@ struct PoolPtrs {
     uint32_t *action;
     uint32_t *nmoves;
     int32_t *n_nodes;
+    int32_t *sim_node;
+    void *finals;
 };
 
 cudaError_t launch_bg_valid_moves(cudaStream_t st, const diee_bg_state *states, int n, diee_move *moves_out,
@@ -27,6 +29,6 @@ cudaError_t launch_bg_encode_states(cudaStream_t st, const diee_bg_state *states
 cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots, int n, const int8_t *players,
                                const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
                                const PoolPtrs &pp, const float *ln_table, uint32_t *best_out, int32_t *status_out,
-                               diee_search_stats *stats_out);
+                               diee_search_stats *stats_out, int *launches);
 
 }  // namespace diee

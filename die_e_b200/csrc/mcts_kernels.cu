@@ -80,13 +80,46 @@ struct Pool {
     uint32_t *action;
     uint32_t *nmoves;  // n_moves << 16 | n_untried
     int32_t *n_nodes;  // per game
+    int32_t *sim_node; // [game][iteration]: node whose rollout the rollout kernel still has to run, or -1
+    void *finals;      // [game][iteration]: state each simulation's rollout ended in (zero = no rollout)
 };
 
 __device__ __forceinline__ float outcome(int winner, int player) {  // simple_mcts.rs:26-28
     return winner == player ? 1.0f : (winner == -player ? -1.0f : 0.0f);
 }
 
+// The rollout body shared by the fused and the split forms: `limit` plies of Node::simulate's loop
+// (node.rs:180-194) from the state held in `game`.  Returns the result; counts plies.
 template <class G>
+__device__ __forceinline__ float rollout_plies(G &game, WarpSlab &slab, int lane, bool &ovf, const diee_mcts_cfg &cfg,
+                                               bool check_current, int player, uint64_t seed, uint32_t gid, uint32_t c3,
+                                               unsigned long long &plies) {
+    PhiloxLanes rng;
+    for (uint32_t k = 0; k < cfg.simulate_round_limit; ++k) {
+        if (check_current) {
+            const int wc = game.winner();
+            if (wc != NO_WINNER) return outcome(wc, player);
+        }
+        if ((k & 31u) == 0) rng.fill(seed, k, gid, DIEE_STREAM_ROLLOUT, c3, lane);
+        const int src = (int)(k & 31u);
+        const int d0 = die_of(__shfl_sync(FULL, rng.w0, src));
+        const int d1 = die_of(__shfl_sync(FULL, rng.w1, src));
+        const uint32_t w2 = __shfl_sync(FULL, rng.w2, src);
+        const int Ur = game.movegen(slab, lane, ovf);
+        const uint32_t sq = Ur > 0 ? game.move_at(slab, (int)index_of(w2, (uint32_t)Ur)) : SEQ_EMPTY;
+        __syncwarp();
+        game.step(sq, d0, d1, lane);
+        ++plies;
+    }
+    return 0.f;
+}
+
+// SPLIT = reference-exact rollouts only: Node::simulate tests the winner of the START state
+// (node.rs:181, quirk Q5), so a rollout from a non-terminal node returns 0 whatever it plays and the
+// tree never depends on it.  The tree kernel then only records which node each simulation rolls
+// out from, and rollout_kernel runs all games x iterations rollouts concurrently (same stream
+// coordinates, so every rollout plays the same plies as in the fused form).
+template <class G, bool SPLIT>
 __global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32)
 mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int8_t *__restrict__ players,
                    diee_mcts_cfg cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch, Pool pool,
@@ -103,6 +136,8 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     int32_t *parent = pool.parent + base;
     float *visits = pool.visits + base, *value = pool.value + base;
     uint32_t *action = pool.action + base, *nm = pool.nmoves + base;
+    int32_t *sim_node = pool.sim_node + (size_t)gidx * cfg.iterations;
+    typename G::State *finals = reinterpret_cast<typename G::State *>(pool.finals) + (size_t)gidx * cfg.iterations;
     const int player = players[gidx];
     const uint32_t gid = first_game_id + (uint32_t)gidx;
     const bool check_current = cfg.mode_flags & DIEE_MODE_ROLLOUT_CHECK_CURRENT;
@@ -172,6 +207,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
             if (w != NO_WINNER) {
                 result = outcome(w, player);  // :25-30
                 ++terminal_leaves;
+                if (lane == 0) sim_node[it] = -1;
             } else {
                 if (nunt == 0) { status = DIEE_ERR_NO_MOVES_PANIC; break; }  // node.rs:119-121 (Q6)
                 // ---- Node::expand node.rs:118-137: pop the LAST untried move ----
@@ -196,28 +232,17 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                 // ---- Node::simulate node.rs:176-196 ----
                 result = 0.f;
                 const int w0 = game.winner();  // winner of the START state (Q5)
+                bool deferred = false;
                 if (cfg.simulate_round_limit > 0 && w0 != NO_WINNER) {
                     result = outcome(w0, player);
+                } else if (SPLIT) {
+                    deferred = cfg.simulate_round_limit > 0;
                 } else {
-                    PhiloxLanes rng;
-                    const uint32_t c3 = (epoch << 16) | (it & 0xFFFFu);
-                    for (uint32_t k = 0; k < cfg.simulate_round_limit; ++k) {
-                        if (check_current) {
-                            const int wc = game.winner();
-                            if (wc != NO_WINNER) { result = outcome(wc, player); break; }
-                        }
-                        if ((k & 31u) == 0) rng.fill(seed, k, gid, DIEE_STREAM_ROLLOUT, c3, lane);
-                        const int src = (int)(k & 31u);
-                        const int d0 = die_of(__shfl_sync(FULL, rng.w0, src));
-                        const int d1 = die_of(__shfl_sync(FULL, rng.w1, src));
-                        const uint32_t w2 = __shfl_sync(FULL, rng.w2, src);
-                        const int Ur = game.movegen(slab, lane, ovf);
-                        const uint32_t sq = Ur > 0 ? game.move_at(slab, (int)index_of(w2, (uint32_t)Ur)) : SEQ_EMPTY;
-                        __syncwarp();
-                        game.step(sq, d0, d1, lane);
-                        ++plies;
-                    }
+                    result = rollout_plies<G>(game, slab, lane, ovf, cfg, check_current, player, seed, gid,
+                                              (epoch << 16) | (it & 0xFFFFu), plies);
                 }
+                if (lane == 0) sim_node[it] = deferred ? child : -1;
+                if (!deferred) game.store(finals + it, lane);  // where the rollout ended
             }
             // ---- backpropagate :96-103 (no sign flip) ----
             if (lane == 0) {
@@ -263,23 +288,69 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     }
 }
 
+// all deferred rollouts of a split search: one warp per (game, iteration)
+template <class G>
+__global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32)
+rollout_kernel(int n_games, diee_mcts_cfg cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch, Pool pool,
+               const int8_t *__restrict__ players, int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out) {
+    __shared__ WarpSlab slabs[MCTS_WARPS_PER_CTA];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long pair = (long long)blockIdx.x * MCTS_WARPS_PER_CTA + wib;
+    if (pair >= (long long)n_games * cfg.iterations) return;
+    const int g = (int)(pair / cfg.iterations);
+    const uint32_t it = (uint32_t)(pair - (long long)g * cfg.iterations);
+    const int node = pool.sim_node[pair];
+    if (node < 0) return;
+    const size_t cap = (size_t)cfg.iterations + 1;
+    G game;
+    game.load(reinterpret_cast<const typename G::State *>(pool.states) + (size_t)g * cap + node, lane);
+    bool ovf = false;
+    unsigned long long plies = 0;
+    rollout_plies<G>(game, slabs[wib], lane, ovf, cfg, false, players[g], seed, first_game_id + (uint32_t)g,
+                     (epoch << 16) | (it & 0xFFFFu), plies);
+    game.store(reinterpret_cast<typename G::State *>(pool.finals) + pair, lane);
+    if (lane == 0) {
+        if (stats_out) atomicAdd(reinterpret_cast<unsigned long long *>(&stats_out[g].rollout_plies), plies);
+        if (ovf) atomicCAS(&status_out[g], DIEE_OK, DIEE_ERR_OVERFLOW);
+    }
+}
+
 static inline int mcts_grid(int n) { return (n + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA; }
+
+template <class G>
+static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const int8_t *players, const diee_mcts_cfg &cfg,
+                                uint64_t seed, uint32_t first_game_id, uint32_t epoch, const Pool &pool, const float *ln_table,
+                                uint32_t *best_out, int32_t *status_out, diee_search_stats *stats_out, int *launches) {
+    const bool split = !(cfg.mode_flags & DIEE_MODE_ROLLOUT_CHECK_CURRENT);
+    const typename G::State *r = static_cast<const typename G::State *>(roots);
+    if (split) {
+        mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
+            r, n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
+        const long long pairs = (long long)n * cfg.iterations;
+        const long long blocks = (pairs + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA;
+        rollout_kernel<G><<<(unsigned)blocks, MCTS_WARPS_PER_CTA * 32, 0, st>>>(n, cfg, seed, first_game_id, epoch, pool, players,
+                                                                             status_out, stats_out);
+        *launches = 2;
+    } else {
+        mcts_search_kernel<G, false><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
+            r, n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
+        *launches = 1;
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots, int n, const int8_t *players,
                                const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
                                const PoolPtrs &pp, const float *ln_table, uint32_t *best_out, int32_t *status_out,
-                               diee_search_stats *stats_out) {
+                               diee_search_stats *stats_out, int *launches) {
+    *launches = 0;
     if (n <= 0) return cudaSuccess;
-    Pool pool{pp.states, pp.parent, pp.visits, pp.value, pp.action, pp.nmoves, pp.n_nodes};
+    Pool pool{pp.states, pp.parent, pp.visits, pp.value, pp.action, pp.nmoves, pp.n_nodes, pp.sim_node, pp.finals};
     if (game_kind == DIEE_GAME_BACKGAMMON)
-        mcts_search_kernel<BgGame><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
-            static_cast<const diee_bg_state *>(roots), n, players, cfg, seed, first_game_id, epoch, pool, ln_table,
-            best_out, status_out, stats_out);
-    else
-        mcts_search_kernel<TttGame><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
-            static_cast<const diee_ttt_state *>(roots), n, players, cfg, seed, first_game_id, epoch, pool, ln_table,
-            best_out, status_out, stats_out);
-    return cudaGetLastError();
+        return launch_typed<BgGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out,
+                                    status_out, stats_out, launches);
+    return launch_typed<TttGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out,
+                                 status_out, stats_out, launches);
 }
 
 }  // namespace diee

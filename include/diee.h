@@ -183,12 +183,17 @@ int32_t diee_bg_encode_states_dev(diee_ctx *ctx, const diee_bg_state *states, in
  * best_moves_out: diee_move[n] (backgammon) or uint8[n] (tictactoe; 10 = EMPTY_MOVE).
  * status_out[i]: DIEE_OK / DIEE_ERR_NO_MOVES_PANIC / DIEE_ERR_OVERFLOW per game.
  * Optional pool read-back (all nullable): nodes_out[n*(iterations+1)], node_states_out (same
- * count, state type by game_kind), n_nodes_out[n]; stats_out[n] = work counters. */
+ * count, state type by game_kind), n_nodes_out[n]; stats_out[n] = work counters;
+ * rollout_finals_out[n*iterations] = the state each simulation's rollout ended in (all-zero where
+ * the iteration ran no rollout), which makes the rollouts themselves checkable against the oracle.
+ * With reference-exact rollouts (no DIEE_MODE_ROLLOUT_CHECK_CURRENT) a rollout cannot influence the
+ * tree (quirk Q5), so the search runs as two launches: the tree kernel, then every game's
+ * rollouts concurrently -- same stream coordinates, same plies, same results. */
 int32_t diee_mcts_search(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
                          const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
                          uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
                          int32_t *status_out, diee_node *nodes_out, void *node_states_out,
-                         int32_t *n_nodes_out, diee_search_stats *stats_out);
+                         int32_t *n_nodes_out, diee_search_stats *stats_out, void *rollout_finals_out);
 /* device-resident form: states/players/best_moves/status are device pointers; the node pool
  * lives in the ctx (HBM) and is reused between calls.  stats_dev nullable (diee_search_stats[n]). */
 int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,

@@ -155,6 +155,9 @@ float orc_ln_f32(float x); /* (float)log((double)x): the contract's ln */
 int orc_mcts_search_bg(const orc_bg_state *root, int player, const orc_mcts_cfg *cfg, uint64_t seed,
                        uint32_t game_id, uint32_t epoch, orc_move *best, orc_node_stats *nodes_out,
                        orc_bg_state *states_out, int32_t *n_nodes_out);
+int orc_mcts_search_bg_ex(const orc_bg_state *root, int player, const orc_mcts_cfg *cfg, uint64_t seed,
+                          uint32_t game_id, uint32_t epoch, orc_move *best, orc_node_stats *nodes_out,
+                          orc_bg_state *states_out, int32_t *n_nodes_out, orc_bg_state *rollout_finals_out);
 int orc_mcts_search_ttt(const orc_ttt_state *root, int player, const orc_mcts_cfg *cfg, uint64_t seed,
                         uint32_t game_id, uint32_t epoch, uint8_t *best, orc_node_stats *nodes_out,
                         orc_ttt_state *states_out, int32_t *n_nodes_out);

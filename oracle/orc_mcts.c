@@ -135,8 +135,9 @@ static float outcome(int winner, int player) { /* simple_mcts.rs:26-28, node.rs:
 /* Node::simulate  node.rs:176-196.  Default (reference-exact) tests the winner of the START
  * state each iteration (Q5); ORC_MODE_ROLLOUT_CHECK_CURRENT tests the rolled-out state. */
 static float simulate(const store_t *st, const node_t *nd, int player, uint32_t limit, uint64_t seed,
-                      uint32_t game_id, uint32_t c3, uint64_t *plies_acc) {
-    unsigned char cur[32];
+                      uint32_t game_id, uint32_t c3, uint64_t *plies_acc, unsigned char *final_out) {
+    unsigned char curbuf[32];
+    unsigned char *cur = final_out ? final_out : curbuf; /* the rolled-out state is observable for parity tests */
     memcpy(cur, nd->state, 32);
     orc_move mv[ORC_MAX_MOVES];
     for (uint32_t k = 0; k < limit; ++k) {
@@ -155,7 +156,7 @@ static float simulate(const store_t *st, const node_t *nd, int player, uint32_t 
 
 static int search(const game_vt *g, const void *root, int player, const orc_mcts_cfg *cfg, uint64_t seed,
                   uint32_t game_id, uint32_t epoch, orc_move *best, orc_node_stats *nodes_out,
-                  void *states_out, int32_t *n_nodes_out) {
+                  void *states_out, int32_t *n_nodes_out, void *rollout_finals_out) {
     *best = EMPTY;
     if (n_nodes_out) *n_nodes_out = 0;
     if (g->winner(root) != ORC_NO_WINNER) return ORC_OK; /* simple_mcts.rs:12-14 */
@@ -189,8 +190,11 @@ static int search(const game_vt *g, const void *root, int player, const orc_mcts
         int child = add_node(&st, next, sel, a);
         nd = &st.nodes[sel];
         nd->children[nd->n_children++] = child;
+        unsigned char fin[32];
+        memset(fin, 0, sizeof fin);
         float v = simulate(&st, &st.nodes[child], player, cfg->simulate_round_limit, seed, game_id,
-                           (epoch << 16) | (it & 0xFFFFu), NULL);
+                           (epoch << 16) | (it & 0xFFFFu), NULL, fin);
+        if (rollout_finals_out) memcpy((unsigned char *)rollout_finals_out + (size_t)it * (size_t)g->state_size, fin, (size_t)g->state_size);
         backprop(&st, child, v);
     }
     if (rc == ORC_OK) { /* select_most_visits  :71-86 */
@@ -226,14 +230,22 @@ static int search(const game_vt *g, const void *root, int player, const orc_mcts
 int orc_mcts_search_bg(const orc_bg_state *root, int player, const orc_mcts_cfg *cfg, uint64_t seed,
                        uint32_t game_id, uint32_t epoch, orc_move *best, orc_node_stats *nodes_out,
                        orc_bg_state *states_out, int32_t *n_nodes_out) {
-    return search(&BG, root, player, cfg, seed, game_id, epoch, best, nodes_out, states_out, n_nodes_out);
+    return search(&BG, root, player, cfg, seed, game_id, epoch, best, nodes_out, states_out, n_nodes_out, NULL);
+}
+
+/* same, also returning the state each simulation's rollout ended in (iterations entries; zero where no rollout ran) */
+int orc_mcts_search_bg_ex(const orc_bg_state *root, int player, const orc_mcts_cfg *cfg, uint64_t seed,
+                          uint32_t game_id, uint32_t epoch, orc_move *best, orc_node_stats *nodes_out,
+                          orc_bg_state *states_out, int32_t *n_nodes_out, orc_bg_state *rollout_finals_out) {
+    if (rollout_finals_out) memset(rollout_finals_out, 0, sizeof(orc_bg_state) * cfg->iterations);
+    return search(&BG, root, player, cfg, seed, game_id, epoch, best, nodes_out, states_out, n_nodes_out, rollout_finals_out);
 }
 
 int orc_mcts_search_ttt(const orc_ttt_state *root, int player, const orc_mcts_cfg *cfg, uint64_t seed,
                         uint32_t game_id, uint32_t epoch, uint8_t *best, orc_node_stats *nodes_out,
                         orc_ttt_state *states_out, int32_t *n_nodes_out) {
     orc_move b;
-    int rc = search(&TTT, root, player, cfg, seed, game_id, epoch, &b, nodes_out, states_out, n_nodes_out);
+    int rc = search(&TTT, root, player, cfg, seed, game_id, epoch, &b, nodes_out, states_out, n_nodes_out, NULL);
     *best = b.from1 == ORC_NONE ? 10 : (uint8_t)b.from1; /* EMPTY_MOVE = 10  tictactoe/mod.rs:18 */
     return rc;
 }

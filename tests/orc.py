@@ -273,14 +273,18 @@ def mcts_cfg(iterations=100, c=2.0, limit=400, alpha=0.3, eps=0.25, mode=0):
     return cfg
 
 
-def mcts_search_bg(state, player, cfg, seed, game_id, epoch):
+def mcts_search_bg(state, player, cfg, seed, game_id, epoch, want_finals=False):
     it = int(cfg["iterations"][0])
     nodes = np.zeros(it + 1, dtype=NODE_STATS)
     states = np.zeros(it + 1, dtype=BG_STATE)
+    finals = np.zeros(it, dtype=BG_STATE)
     best = np.zeros(1, dtype=MOVE)
     n = C.c_int32(0)
-    rc = lib().orc_mcts_search_bg(_p(np.ascontiguousarray(state).reshape(-1)[:1]), C.c_int(player), _p(cfg), C.c_uint64(seed),
-                                  C.c_uint32(game_id), C.c_uint32(epoch), _p(best), _p(nodes), _p(states), C.byref(n))
+    rc = lib().orc_mcts_search_bg_ex(_p(np.ascontiguousarray(state).reshape(-1)[:1]), C.c_int(player), _p(cfg), C.c_uint64(seed),
+                                     C.c_uint32(game_id), C.c_uint32(epoch), _p(best), _p(nodes), _p(states), C.byref(n),
+                                     _p(finals))
+    if want_finals:
+        return rc, best, nodes[: n.value], states[: n.value], finals
     return rc, best, nodes[: n.value], states[: n.value]
 
 

@@ -16,11 +16,13 @@ def ctx():
 
 
 def _cmp_trees(oracle, ffi, ctx, kind, states, players, cfg, seed, first, epoch):
-    best, status, stats, nodes, nstates, n_nodes = ctx.mcts_search(kind, states, players, cfg, seed, first, epoch, dump=True)
+    best, status, stats, nodes, nstates, n_nodes, finals = ctx.mcts_search(kind, states, players, cfg, seed, first, epoch, dump=True)
     total_plies = 0
     for i in range(len(states)):
         if kind == ffi.GAME_BACKGAMMON:
-            rc, obest, onodes, ostates = oracle.mcts_search_bg(states[i:i + 1], int(players[i]), cfg, seed, first + i, epoch)
+            rc, obest, onodes, ostates, ofin = oracle.mcts_search_bg(states[i:i + 1], int(players[i]), cfg, seed, first + i,
+                                                                     epoch, want_finals=True)
+            assert finals[i].tobytes() == ofin.tobytes(), i   # every rollout ended in the same state
         else:
             rc, obest, onodes, ostates = oracle.mcts_search_ttt(states[i:i + 1], int(players[i]), cfg, seed, first + i, epoch)
         assert status[i] == rc, (i, status[i], rc)

@@ -38,6 +38,7 @@ SYMBOLS = [
     "diee_bg_valid_moves", "diee_bg_valid_moves_dev", "diee_bg_apply_moves", "diee_bg_apply_moves_dev",
     "diee_bg_playout", "diee_bg_playout_dev", "diee_bg_encode_moves", "diee_bg_decode_moves",
     "diee_bg_encode_states", "diee_bg_encode_states_dev", "diee_mcts_search", "diee_mcts_search_dev",
+    "diee_net_create", "diee_net_destroy", "diee_net_param_count", "diee_net_forward", "diee_net_forward_dev",
 ]
 
 
@@ -63,6 +64,8 @@ def lib():
         L.diee_version.restype = C.c_char_p
         L.diee_launch_count.restype = C.c_int64
         L.diee_launch_count.argtypes = [C.c_void_p]
+        L.diee_net_param_count.restype = C.c_int64
+        L.diee_net_param_count.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -210,6 +213,43 @@ class Context:
         self._chk(lib().diee_mcts_search_dev(self._h, C.c_int32(game_kind), _p(d_states), C.c_int32(n), _p(d_players), _p(cfg),
                                              C.c_uint64(seed), C.c_uint32(first_game_id), C.c_uint32(epoch), _p(d_best),
                                              _p(d_status), _p(d_stats)))
+
+
+class Net:
+    """a diee_net handle (policy/value ResNet on one ctx)"""
+
+    def __init__(self, ctx, tensors, game_kind=GAME_BACKGAMMON):
+        self.ctx = ctx
+        arrs = [np.ascontiguousarray(t, dtype=np.float32) for t in tensors]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        numels = np.array([a.size for a in arrs], dtype=np.int64)
+        self._h = C.c_void_p(0)
+        ctx._chk(lib().diee_net_create(ctx._h, C.c_int32(game_kind), ptrs, _p(numels), C.c_int32(len(arrs)), C.byref(self._h)))
+
+    def close(self):
+        if self._h and self.ctx._h:
+            lib().diee_net_destroy(self.ctx._h, self._h)
+        self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def param_count(self):
+        return int(lib().diee_net_param_count(self._h))
+
+    def forward(self, states):
+        states = np.ascontiguousarray(states, dtype=BG_STATE).reshape(-1)
+        n = len(states)
+        policy = np.zeros((n, ACTION_SPACE), dtype=np.float32)
+        value = np.zeros(n, dtype=np.float32)
+        self.ctx._chk(lib().diee_net_forward(self.ctx._h, self._h, _p(states), C.c_int32(n), _p(policy), _p(value)))
+        return policy, value
+
+    def forward_dev(self, d_states, n, d_policy, d_value):
+        self.ctx._chk(lib().diee_net_forward_dev(self.ctx._h, self._h, _p(d_states), C.c_int32(n), _p(d_policy), _p(d_value)))
 
 
 _default_ctx = None

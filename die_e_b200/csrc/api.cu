@@ -15,55 +15,7 @@
 
 using namespace diee;
 
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-};
-
-struct diee_ctx {
-    int device = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    int64_t launches = 0;
-    // scratch for host-buffer entry points
-    DevBuf s_states, s_moves, s_counts, s_ids, s_aux, s_out, s_players, s_best, s_status, s_plies;
-    // pure-MCTS node pool (HBM resident, reused between searches)
-    DevBuf p_states, p_parent, p_visits, p_value, p_action, p_nmoves, p_nnodes, p_simnode, p_finals, ln_table;
-    uint32_t ln_table_n = 0;
-};
-
-static int32_t fail(diee_ctx *ctx, int32_t code, const char *fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    if (ctx) ctx->err = buf;
-    return code;
-}
-
-#define CU(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) return fail(ctx, DIEE_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
-    } while (0)
-
-static int32_t reserve(diee_ctx *ctx, DevBuf &b, size_t bytes) {
-    if (bytes <= b.cap) return DIEE_OK;
-    if (b.p) CU(cudaFree(b.p));
-    b.p = nullptr;
-    b.cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
-    CU(cudaMalloc(&b.p, want));
-    b.cap = want;
-    return DIEE_OK;
-}
-#define RESERVE(buf, bytes)                                  \
-    do {                                                     \
-        int32_t r_ = reserve(ctx, buf, bytes);               \
-        if (r_ != DIEE_OK) return r_;                        \
-    } while (0)
+#include "ctx.h"
 
 extern "C" {
 

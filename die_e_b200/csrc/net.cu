@@ -1,0 +1,278 @@
+// net.cu -- host side of the policy/value net: weight folding/packing, TMA tensor maps, the
+// layer schedule, and the extern "C" entry points diee_net_* (include/diee.h).
+// Reference: src/alphazero/nnet.rs:57-155 (architecture, registration order, forward_t / forward_policy).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "ctx.h"
+#include "net_launch.h"
+
+using namespace diee;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// activations: bf16 NHWC [n][4][6][C]; box = [64 ch][6][4][16 boards], 128B swizzle, OOB -> zero
+static bool make_act_map(CUtensorMap *m, const void *base, int n_boards, int C) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)C, 6, 4, (cuuint64_t)n_boards};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 12, (cuuint64_t)C * 48};
+    cuuint32_t box[4] = {64, 6, 4, 16};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// weights: bf16 [c_out][K]; box = [64 k][bn rows]
+static bool make_w_map(CUtensorMap *m, const void *base, int c_out, int K, int bn) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)c_out};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    cuuint32_t es[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct ConvLayer {
+    __nv_bfloat16 *w = nullptr;  // [c_out_pad][K]
+    float *bias = nullptr;       // [c_out_pad]
+    CUtensorMap wmap;
+    int c_out_pad = 0, K = 0, ntaps = 9, chunks = 4, bn = 128;
+};
+
+struct diee_net {
+    int filters = 0, blocks = 0;
+    std::vector<ConvLayer> convs;  // init, then conv1/conv2 per block
+    ConvLayer pconv, vconv;
+    float *wpt = nullptr, *bp = nullptr, *wv = nullptr;
+    float bv = 0.f;
+    // activation scratch (grown on demand)
+    DevBuf in0, actA, actB, actC, pfeat, vfeat, s_states, s_policy, s_value;
+    int64_t param_count = 0;
+};
+
+static float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+// conv (+ eval-mode BatchNorm, eps 1e-5) folded in fp64 and packed [c_out][tap][c_in] as bf16
+static int32_t build_conv(diee_ctx *ctx, ConvLayer &L, const float *w, const float *b, const float *g, const float *beta,
+                          const float *mean, const float *var, int c_out, int c_in, int c_out_pad, int k_pad, int bn) {
+    const int K = k_pad ? k_pad : 9 * c_in;
+    std::vector<__nv_bfloat16> wp((size_t)c_out_pad * K, __float2bfloat16(0.f));
+    std::vector<float> bp((size_t)c_out_pad, 0.f);
+    for (int co = 0; co < c_out; ++co) {
+        const double scale = (double)g[co] / std::sqrt((double)var[co] + 1e-5);
+        bp[co] = (float)(((double)b[co] - (double)mean[co]) * scale + (double)beta[co]);
+        for (int ci = 0; ci < c_in; ++ci)
+            for (int tap = 0; tap < 9; ++tap) {
+                const double v = (double)w[((size_t)co * c_in + ci) * 9 + tap] * scale;
+                wp[(size_t)co * K + (size_t)tap * c_in + ci] = __float2bfloat16((float)v);
+            }
+    }
+    L.c_out_pad = c_out_pad; L.K = K; L.bn = bn;
+    L.ntaps = k_pad ? 1 : 9;
+    L.chunks = k_pad ? k_pad / 64 : c_in / 64;
+    CU(cudaMalloc(&L.w, wp.size() * sizeof(__nv_bfloat16)));
+    CU(cudaMalloc(&L.bias, bp.size() * sizeof(float)));
+    CU(cudaMemcpy(L.w, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (!make_w_map(&L.wmap, L.w, c_out_pad, K, bn)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed");
+    return DIEE_OK;
+}
+
+extern "C" {
+
+int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *t, const int64_t *numels, int32_t n_tensors,
+                        diee_net **out) {
+    if (!ctx || !t || !numels || !out) return fail(ctx, DIEE_ERR_INVALID, "net_create: bad argument");
+    *out = nullptr;
+    if (game_kind != DIEE_GAME_BACKGAMMON) return fail(ctx, DIEE_ERR_INVALID, "net_create: only the backgammon geometry (6x4x6 input) is built");
+    if (n_tensors < 22 + 12 || (n_tensors - 22) % 12 != 0) return fail(ctx, DIEE_ERR_INVALID, "net_create: expected 22 + 12*blocks tensors, got %d", n_tensors);
+    const int blocks = (n_tensors - 22) / 12;
+    if (numels[0] % 54 != 0) return fail(ctx, DIEE_ERR_INVALID, "net_create: init conv weight has %lld elements", (long long)numels[0]);
+    const int F = (int)(numels[0] / 54);
+    if (F % 128 != 0 || F > 1024) return fail(ctx, DIEE_ERR_INVALID, "net_create: filters=%d must be a multiple of 128", F);
+    // shape checks along the registration order (nnet.rs:62-98, :37-44)
+    auto expect = [&](int idx, int64_t want) { return numels[idx] == want; };
+    int idx = 0;
+    bool ok = expect(0, (int64_t)F * 54) && expect(1, F);
+    for (int k = 2; k < 6; ++k) ok = ok && expect(k, F);
+    idx = 6;
+    for (int b = 0; b < blocks && ok; ++b) {
+        ok = expect(idx, (int64_t)F * F * 9) && expect(idx + 1, F) && expect(idx + 2, (int64_t)F * F * 9) && expect(idx + 3, F);
+        for (int k = 4; k < 12; ++k) ok = ok && expect(idx + k, F);
+        idx += 12;
+    }
+    ok = ok && expect(idx, (int64_t)32 * F * 9) && expect(idx + 1, 32);
+    for (int k = 2; k < 6; ++k) ok = ok && expect(idx + k, 32);
+    ok = ok && expect(idx + 6, (int64_t)DIEE_ACTION_SPACE * 768) && expect(idx + 7, DIEE_ACTION_SPACE);
+    ok = ok && expect(idx + 8, (int64_t)3 * F * 9) && expect(idx + 9, 3);
+    for (int k = 10; k < 14; ++k) ok = ok && expect(idx + k, 3);
+    ok = ok && expect(idx + 14, 72) && expect(idx + 15, 1);
+    if (!ok) return fail(ctx, DIEE_ERR_INVALID, "net_create: tensor shapes do not match the ResNet registration order (nnet.rs:57-107)");
+
+    CU(cudaSetDevice(ctx->device));
+    if (!get_encode_fn()) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    diee_net *net = new diee_net();
+    net->filters = F; net->blocks = blocks;
+    for (int i = 0; i < n_tensors; ++i) net->param_count += numels[i];
+    int32_t rc;
+    // init conv: C_in = 6, K = 54 padded to 64, one "tap" over the im2col operand
+    {
+        // repack [F][6][3][3] -> build_conv's [co][tap][ci] with c_in = 6, then pad K to 64
+        ConvLayer L;
+        std::vector<float> w6((size_t)F * 54);
+        memcpy(w6.data(), t[0], sizeof(float) * w6.size());
+        // build with k_pad = 64: K index = tap*6 + ci (< 54)
+        const int K = 64;
+        std::vector<__nv_bfloat16> wp((size_t)F * K, __float2bfloat16(0.f));
+        std::vector<float> bpv((size_t)F, 0.f);
+        for (int co = 0; co < F; ++co) {
+            const double scale = (double)t[2][co] / std::sqrt((double)t[5][co] + 1e-5);
+            bpv[co] = (float)(((double)t[1][co] - (double)t[4][co]) * scale + (double)t[3][co]);
+            for (int ci = 0; ci < 6; ++ci)
+                for (int tap = 0; tap < 9; ++tap)
+                    wp[(size_t)co * K + tap * 6 + ci] = __float2bfloat16((float)((double)w6[((size_t)co * 6 + ci) * 9 + tap] * scale));
+        }
+        L.c_out_pad = F; L.K = K; L.bn = 128; L.ntaps = 1; L.chunks = 1;
+        CU(cudaMalloc(&L.w, wp.size() * sizeof(__nv_bfloat16)));
+        CU(cudaMalloc(&L.bias, bpv.size() * sizeof(float)));
+        CU(cudaMemcpy(L.w, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(L.bias, bpv.data(), bpv.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (!make_w_map(&L.wmap, L.w, F, K, 128)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed");
+        net->convs.push_back(L);
+    }
+    idx = 6;
+    for (int b = 0; b < blocks; ++b) {  // ResBlock::new registers conv1, conv2, bn1, bn2 (nnet.rs:37-44)
+        ConvLayer c1, c2;
+        rc = build_conv(ctx, c1, t[idx], t[idx + 1], t[idx + 4], t[idx + 5], t[idx + 6], t[idx + 7], F, F, F, 0, 128);
+        if (rc != DIEE_OK) return rc;
+        rc = build_conv(ctx, c2, t[idx + 2], t[idx + 3], t[idx + 8], t[idx + 9], t[idx + 10], t[idx + 11], F, F, F, 0, 128);
+        if (rc != DIEE_OK) return rc;
+        net->convs.push_back(c1);
+        net->convs.push_back(c2);
+        idx += 12;
+    }
+    rc = build_conv(ctx, net->pconv, t[idx], t[idx + 1], t[idx + 2], t[idx + 3], t[idx + 4], t[idx + 5], 32, F, 32, 0, 32);
+    if (rc != DIEE_OK) return rc;
+    {   // policy Linear(768 -> 1352): torch flattens NCHW (feature = c*24 + pos); ours is NHWC (pos*32 + c)
+        std::vector<float> wpt((size_t)768 * DIEE_ACTION_SPACE);
+        const float *W = t[idx + 6];
+        for (int j = 0; j < DIEE_ACTION_SPACE; ++j)
+            for (int c = 0; c < 32; ++c)
+                for (int pos = 0; pos < 24; ++pos) wpt[(size_t)(pos * 32 + c) * DIEE_ACTION_SPACE + j] = W[(size_t)j * 768 + c * 24 + pos];
+        CU(cudaMalloc(&net->wpt, wpt.size() * sizeof(float)));
+        CU(cudaMemcpy(net->wpt, wpt.data(), wpt.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&net->bp, DIEE_ACTION_SPACE * sizeof(float)));
+        CU(cudaMemcpy(net->bp, t[idx + 7], DIEE_ACTION_SPACE * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    rc = build_conv(ctx, net->vconv, t[idx + 8], t[idx + 9], t[idx + 10], t[idx + 11], t[idx + 12], t[idx + 13], 3, F, 16, 0, 16);
+    if (rc != DIEE_OK) return rc;
+    {   // value Linear(72 -> 1): feature c*24+pos -> pos*16 + c
+        std::vector<float> wv((size_t)24 * 16, 0.f);
+        for (int c = 0; c < 3; ++c)
+            for (int pos = 0; pos < 24; ++pos) wv[pos * 16 + c] = t[idx + 14][c * 24 + pos];
+        CU(cudaMalloc(&net->wv, wv.size() * sizeof(float)));
+        CU(cudaMemcpy(net->wv, wv.data(), wv.size() * sizeof(float), cudaMemcpyHostToDevice));
+        net->bv = t[idx + 15][0];
+    }
+    (void)bf16_round;
+    *out = net;
+    return DIEE_OK;
+}
+
+int32_t diee_net_destroy(diee_ctx *ctx, diee_net *net) {
+    if (!ctx || !net) return DIEE_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (ConvLayer &L : net->convs) { cudaFree(L.w); cudaFree(L.bias); }
+    cudaFree(net->pconv.w); cudaFree(net->pconv.bias); cudaFree(net->vconv.w); cudaFree(net->vconv.bias);
+    cudaFree(net->wpt); cudaFree(net->bp); cudaFree(net->wv);
+    DevBuf *bufs[] = {&net->in0, &net->actA, &net->actB, &net->actC, &net->pfeat, &net->vfeat, &net->s_states, &net->s_policy, &net->s_value};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    delete net;
+    return DIEE_OK;
+}
+
+// forward_t (nnet.rs:120-133): policy = softmax(policy_head(tower(x))), value = tanh(value_head(tower(x)))
+int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, float *policy_out,
+                             float *value_out) {
+    if (!ctx || !net || n < 0 || (n && (!states || !policy_out || !value_out))) return fail(ctx, DIEE_ERR_INVALID, "net_forward: bad argument");
+    if (n == 0) return DIEE_OK;
+    CU(cudaSetDevice(ctx->device));
+    const int F = net->filters;
+    const size_t rows = (size_t)n * 24;
+    RESERVE(net->in0, rows * 64 * 2);
+    RESERVE(net->actA, rows * F * 2);
+    RESERVE(net->actB, rows * F * 2);
+    RESERVE(net->actC, rows * F * 2);
+    RESERVE(net->pfeat, rows * 32 * 4);
+    RESERVE(net->vfeat, rows * 16 * 4);
+    CUtensorMap m_in, mA, mB, mC;
+    if (!make_act_map(&m_in, net->in0.p, n, 64) || !make_act_map(&mA, net->actA.p, n, F) || !make_act_map(&mB, net->actB.p, n, F) ||
+        !make_act_map(&mC, net->actC.p, n, F))
+        return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (activations) failed");
+    cudaStream_t st = ctx->stream;
+    CU(launch_encode_im2col(st, states, n, net->in0.p));
+    const ConvLayer &L0 = net->convs[0];
+    CU(launch_conv(st, L0.bn, m_in, L0.wmap, n, L0.ntaps, L0.chunks, L0.bias, nullptr, net->actA.p, 0, F, 1));
+    ctx->launches += 2;
+    // x lives in A; y = relu(bn1(conv1(x))) -> B; x' = relu(bn2(conv2(y)) + x) -> C; rotate
+    void *bx = net->actA.p, *by = net->actB.p, *bz = net->actC.p;
+    CUtensorMap *mx = &mA, *my = &mB, *mz = &mC;
+    for (int b = 0; b < net->blocks; ++b) {
+        const ConvLayer &c1 = net->convs[1 + 2 * b], &c2 = net->convs[2 + 2 * b];
+        CU(launch_conv(st, c1.bn, *mx, c1.wmap, n, 9, c1.chunks, c1.bias, nullptr, by, 0, F, 1));
+        CU(launch_conv(st, c2.bn, *my, c2.wmap, n, 9, c2.chunks, c2.bias, bx, bz, 0, F, 1));
+        ctx->launches += 2;
+        void *tp = bx; bx = bz; bz = tp;
+        CUtensorMap *tm = mx; mx = mz; mz = tm;
+    }
+    CU(launch_conv(st, net->pconv.bn, *mx, net->pconv.wmap, n, 9, net->pconv.chunks, net->pconv.bias, nullptr, net->pfeat.p, 1, 32, 1));
+    CU(launch_conv(st, net->vconv.bn, *mx, net->vconv.wmap, n, 9, net->vconv.chunks, net->vconv.bias, nullptr, net->vfeat.p, 1, 16, 1));
+    CU(launch_heads_fc(st, (const float *)net->pfeat.p, (const float *)net->vfeat.p, net->wpt, net->bp, net->wv, net->bv, n, policy_out, value_out));
+    ctx->launches += 3;
+    return DIEE_OK;
+}
+
+int32_t diee_net_forward(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, float *policy_out, float *value_out) {
+    if (!ctx || !net || n < 0 || (n && (!states || !policy_out || !value_out))) return fail(ctx, DIEE_ERR_INVALID, "net_forward: bad argument");
+    if (n == 0) return DIEE_OK;
+    for (int i = 0; i < n; ++i)
+        if (states[i].roll[0] == 0 && states[i].roll[1] == 0) return fail(ctx, DIEE_ERR_NOT_ROLLED, "net_forward: state %d has not been rolled", i);
+    CU(cudaSetDevice(ctx->device));
+    RESERVE(net->s_states, sizeof(diee_bg_state) * (size_t)n);
+    RESERVE(net->s_policy, sizeof(float) * DIEE_ACTION_SPACE * (size_t)n);
+    RESERVE(net->s_value, sizeof(float) * (size_t)n);
+    CU(cudaMemcpyAsync(net->s_states.p, states, sizeof(diee_bg_state) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t rc = diee_net_forward_dev(ctx, net, (const diee_bg_state *)net->s_states.p, n, (float *)net->s_policy.p, (float *)net->s_value.p);
+    if (rc != DIEE_OK) return rc;
+    CU(cudaMemcpyAsync(policy_out, net->s_policy.p, sizeof(float) * DIEE_ACTION_SPACE * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(value_out, net->s_value.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return DIEE_OK;
+}
+
+int64_t diee_net_param_count(const diee_net *net) { return net ? net->param_count : 0; }
+
+}  // extern "C"

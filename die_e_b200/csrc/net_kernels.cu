@@ -1,0 +1,421 @@
+// net_kernels.cu -- policy/value ResNet forward for sm_100a.
+//
+// Reference: src/alphazero/nnet.rs (ResNet::new :57-107, ResBlock :17-45, forward_t :120-133).
+// Every 3x3 convolution over the 4x6 board is an implicit GEMM on the 5th-generation tensor
+// cores:  M = boards*24 positions, N = output channels, K = 9 taps * C_in.
+//   * activations live in HBM as NHWC bf16 ([board][h][w][c]); a 4-D TMA tensor map
+//     (c, w, h, board) with a box of [64 ch][6][4][16 boards] loads, for tap (kh,kw), the box
+//     shifted by (kw-1, kh-1): the out-of-bounds halo is ZERO-FILLED by TMA, so the 3x3 padding
+//     costs nothing and no im2col matrix is ever materialised;
+//   * weights are pre-packed [c_out][tap][c_in] bf16 with BatchNorm folded in (eval mode), loaded
+//     by a 2-D tensor map; both operands land in shared memory in the 128-byte swizzle that
+//     tcgen05 smem descriptors expect;
+//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM accumulators
+//     (3 M-tiles x BN fp32 columns for a 16-board tile); tcgen05.commit releases smem stages and
+//     finally signals the epilogue warps, which read TMEM with tcgen05.ld, add the folded bias
+//     (+ residual), apply ReLU and store bf16 NHWC (or fp32 for the two head convolutions).
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.
+// The first layer (6 -> F channels, K = 54) consumes a [positions][64] bf16 matrix that
+// encode_im2col_kernel builds directly from the packed 32-byte states (as_tensor,
+// backgammon_logic.rs:198-252, fused with the tap gather), through the same kernel with one tap.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/diee.h"
+#include "net_launch.h"
+
+namespace diee {
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns of this warp's TMEM quadrant
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile with 128-byte rows in the 128B swizzle: 8-row groups are 1024 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO(1)<<16 | SBO(64)<<32 | version 1<<46 | SWIZZLE_128B 2<<61)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor, kind::f16: D=F32 (1<<4), A=B=BF16 (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- the convolution kernel
+constexpr int CONV_NB = 16;                      // boards per CTA tile
+constexpr int CONV_ROWS = CONV_NB * 24;          // 384 positions = 3 MMA M-tiles
+constexpr int CONV_MT = CONV_ROWS / 128;
+constexpr int CONV_A_BYTES = CONV_ROWS * 128;    // one K-block (64 bf16 channels) of the activation tile
+constexpr int CONV_THREADS = 192;
+
+template <int BN>
+struct ConvCfg {
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = CONV_A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN >= 128) ? 3 : 4;
+    static constexpr int TMEM_COLS = (CONV_MT * BN <= 32) ? 32 : (CONV_MT * BN <= 64) ? 64 : (CONV_MT * BN <= 128) ? 128
+                                     : (CONV_MT * BN <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+};
+
+// out_mode: 0 = bf16 NHWC [rows][c_out_total], 1 = fp32 NHWC
+template <int BN>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int n_boards,
+                  int ntaps, int chunks, const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual,
+                  void *__restrict__ out, int out_mode, int c_out_total, int relu) {
+    using Cfg = ConvCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *tail = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(tail);
+    uint64_t *empty_bar = full_bar + Cfg::STAGES;
+    uint64_t *tmem_full_bar = empty_bar + Cfg::STAGES;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+    float *bias_smem = reinterpret_cast<float *>(tail + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int board0 = blockIdx.x * CONV_NB;
+    const int n0 = blockIdx.y * BN;
+    const int num_kb = ntaps * chunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmapA);
+        prefetch_tmap(&tmapB);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    for (int i = threadIdx.x; i < BN; i += CONV_THREADS) bias_smem[i] = bias[n0 + i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t *sa = smem + s * Cfg::STAGE_BYTES;
+                uint8_t *sb = sa + CONV_A_BYTES;
+                mbar_expect_tx(&full_bar[s], (uint32_t)Cfg::STAGE_BYTES);
+                const int tap = kb / chunks, chunk = kb - tap * chunks;
+                const int kh = ntaps == 9 ? tap / 3 : 1, kw = ntaps == 9 ? tap - (tap / 3) * 3 : 1;
+                tma_load_4d(sa, &tmapA, &full_bar[s], chunk * 64, kw - 1, kh - 1, board0);
+                tma_load_2d(sb, &tmapB, &full_bar[s], kb * 64, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected thread) =====
+        constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % Cfg::STAGES;
+            const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint32_t sb = sa + CONV_A_BYTES;
+#pragma unroll
+                for (int mt = 0; mt < CONV_MT; ++mt) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzled row
+                        const uint64_t ad = umma_desc_sw128(sa + mt * (128 * 128) + kk * 32);
+                        const uint64_t bd = umma_desc_sw128(sb + kk * 32);
+                        umma_bf16(tmem_base + (uint32_t)(mt * BN), ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
+                if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulators complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> bias (+residual) -> ReLU -> HBM =====
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;  // TMEM lane quadrant this warp may read
+        const long long total_rows = (long long)n_boards * 24;
+#pragma unroll 1
+        for (int mt = 0; mt < CONV_MT; ++mt) {
+            const long long grow = (long long)board0 * 24 + mt * 128 + q * 32 + lane;
+            const bool valid = grow < total_rows;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN + c0);
+                const int ncol = (BN - c0) >= 32 ? 32 : 16;
+                if (ncol == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+                tmem_ld_wait();
+                if (valid) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = j < ncol ? __uint_as_float(v[j]) + bias_smem[c0 + j] : 0.f;
+                    const size_t off = (size_t)grow * c_out_total + n0 + c0;
+                    if (residual) {
+                        const uint4 *rp = reinterpret_cast<const uint4 *>(residual + off);
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            const uint4 r = rp[g4];
+                            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[h]);
+                                f[g4 * 8 + h * 2] += __bfloat162float(b2.x);
+                                f[g4 * 8 + h * 2 + 1] += __bfloat162float(b2.y);
+                            }
+                        }
+                    }
+                    if (relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (out_mode == 0) {
+                        uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(out) + off);
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g4 * 8 + h * 2], f[g4 * 8 + h * 2 + 1]);
+                                w[h] = *reinterpret_cast<const uint32_t *>(&b2);
+                            }
+                            if (g4 * 8 < ncol) op[g4] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    } else {
+                        float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + off);
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4)
+                            if (g4 * 4 < ncol) op[g4] = make_float4(f[g4 * 4], f[g4 * 4 + 1], f[g4 * 4 + 2], f[g4 * 4 + 3]);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------- first-layer operand: as_tensor + tap gather
+// out[(board*24 + pos)][k], k = tap*6 + channel (k < 54), zero-padded to 64; bf16 (all values are small integers)
+__global__ void encode_im2col_kernel(const diee_bg_state *__restrict__ states, int n, __nv_bfloat16 *__restrict__ out) {
+    const long long total = (long long)n * 24 * 64;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx & 63);
+        const long long rp = idx >> 6;
+        const int pos = (int)(rp % 24);
+        const long long b = rp / 24;
+        float val = 0.f;
+        if (k < 54) {
+            const int tap = k / 6, c = k - tap * 6;
+            const int hh = pos / 6 + tap / 3 - 1, ww = pos % 6 + tap % 3 - 1;
+            if (hh >= 0 && hh < 4 && ww >= 0 && ww < 6) {
+                const diee_bg_state &s = states[b];
+                const int pt = hh * 6 + ww, half = pt < 12 ? 0 : 1;
+                switch (c) {  // as_tensor channel order, backgammon_logic.rs:240-250
+                    case 0: val = (float)s.pts[pt]; break;
+                    case 1: val = (float)s.player; break;
+                    case 2: val = (float)s.bar[half]; break;
+                    case 3: val = (float)s.off[half]; break;
+                    case 4: val = (float)s.roll[half]; break;
+                    default: val = s.second ? 1.f : 0.f; break;
+                }
+            }
+        }
+        out[idx] = __float2bfloat16(val);
+    }
+}
+
+// ---------------------------------------------------------------- heads: Linear + softmax / Linear + tanh
+// pfeat: fp32 [n*24][32] (policy conv, ReLU'd); wpt: fp32 [768][1352] with feature index pos*32+c;
+// vfeat: fp32 [n*24][16] (3 used); wv: fp32 [24*16].  nnet.rs:75-98, :127.
+constexpr int FC_BOARDS = 8;
+__global__ void __launch_bounds__(256)
+heads_fc_kernel(const float *__restrict__ pfeat, const float *__restrict__ vfeat, const float *__restrict__ wpt,
+                const float *__restrict__ bp, const float *__restrict__ wv, float bv, int n, float *__restrict__ policy_out,
+                float *__restrict__ value_out) {
+    __shared__ float feat[FC_BOARDS][768];
+    const int b0 = blockIdx.x * FC_BOARDS;
+    const int nb = min(FC_BOARDS, n - b0);
+    for (int i = threadIdx.x; i < FC_BOARDS * 768; i += 256) {
+        const int b = i / 768, f = i - b * 768;
+        feat[b][f] = b < nb ? pfeat[(size_t)(b0 + b) * 768 + f] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < DIEE_ACTION_SPACE; j += 256) {
+        float acc[FC_BOARDS];
+#pragma unroll
+        for (int b = 0; b < FC_BOARDS; ++b) acc[b] = bp[j];
+        for (int f = 0; f < 768; ++f) {
+            const float w = wpt[(size_t)f * DIEE_ACTION_SPACE + j];
+#pragma unroll
+            for (int b = 0; b < FC_BOARDS; ++b) acc[b] = fmaf(w, feat[b][f], acc[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < FC_BOARDS; ++b)
+            if (b < nb) policy_out[(size_t)(b0 + b) * DIEE_ACTION_SPACE + j] = acc[b];
+    }
+    __threadfence_block();
+    __syncthreads();
+    // softmax(1) per board: one warp per board
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < nb) {
+        float *row = policy_out + (size_t)(b0 + warp) * DIEE_ACTION_SPACE;
+        float mx = -INFINITY;
+        for (int j = lane; j < DIEE_ACTION_SPACE; j += 32) mx = fmaxf(mx, row[j]);
+        for (int d = 16; d; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+        float sum = 0.f;
+        for (int j = lane; j < DIEE_ACTION_SPACE; j += 32) { const float e = expf(row[j] - mx); row[j] = e; sum += e; }
+        for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        const float inv = 1.f / sum;
+        for (int j = lane; j < DIEE_ACTION_SPACE; j += 32) row[j] *= inv;
+        // value head
+        float acc = 0.f;
+        const float *vf = vfeat + (size_t)(b0 + warp) * 24 * 16;
+        for (int f = lane; f < 24 * 16; f += 32) acc = fmaf(wv[f], vf[f], acc);
+        for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+        if (lane == 0) value_out[b0 + warp] = tanhf(acc + bv);
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+template <int BN>
+static cudaError_t launch_conv_bn(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,
+                                  int chunks, const float *bias, const __nv_bfloat16 *residual, void *out, int out_mode,
+                                  int c_out_total, int relu) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((n_boards + CONV_NB - 1) / CONV_NB, c_out_total / BN);
+    conv3x3_tc_kernel<BN><<<grid, CONV_THREADS, ConvCfg<BN>::SMEM_BYTES, st>>>(ta, tb, n_boards, ntaps, chunks, bias, residual, out,
+                                                                              out_mode, c_out_total, relu);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv(cudaStream_t st, int bn, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps, int chunks,
+                        const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu) {
+    const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(residual);
+    switch (bn) {
+        case 128: return launch_conv_bn<128>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu);
+        case 32: return launch_conv_bn<32>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu);
+        case 16: return launch_conv_bn<16>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_encode_im2col(cudaStream_t st, const diee_bg_state *states, int n, void *out) {
+    if (n <= 0) return cudaSuccess;
+    long long total = (long long)n * 24 * 64;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    encode_im2col_kernel<<<blocks, 256, 0, st>>>(states, n, static_cast<__nv_bfloat16 *>(out));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_heads_fc(cudaStream_t st, const float *pfeat, const float *vfeat, const float *wpt, const float *bp,
+                            const float *wv, float bv, int n, float *policy_out, float *value_out) {
+    if (n <= 0) return cudaSuccess;
+    heads_fc_kernel<<<(n + FC_BOARDS - 1) / FC_BOARDS, 256, 0, st>>>(pfeat, vfeat, wpt, bp, wv, bv, n, policy_out, value_out);
+    return cudaGetLastError();
+}
+
+}  // namespace diee

@@ -1,0 +1,15 @@
+// net_launch.h -- internal: launchers of net_kernels.cu
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/diee.h"
+
+namespace diee {
+cudaError_t launch_conv(cudaStream_t st, int bn, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps, int chunks,
+                        const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu);
+cudaError_t launch_encode_im2col(cudaStream_t st, const diee_bg_state *states, int n, void *out);
+cudaError_t launch_heads_fc(cudaStream_t st, const float *pfeat, const float *vfeat, const float *wpt, const float *bp,
+                            const float *wv, float bv, int n, float *policy_out, float *value_out);
+}  // namespace diee

@@ -201,6 +201,29 @@ int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *state
                              uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
                              int32_t *status_out, diee_search_stats *stats_dev);
 
+/* ---- policy/value net: ResNet (alphazero/nnet.rs:57-155), inference only ----
+ * Architecture (backgammon): conv3x3(6->F)+BN+ReLU, `blocks` x [conv+BN+ReLU+conv+BN+add+ReLU],
+ * policy head conv3x3(F->32)+BN+ReLU+flatten+Linear(768->1352)+softmax, value head
+ * conv3x3(F->3)+BN+ReLU+flatten+Linear(72->1)+tanh; BatchNorm in eval mode (running stats, eps 1e-5).
+ * diee_net_create takes the 22 + 12*blocks tensors as host f32 arrays in the reference's registration
+ * order (nnet.rs:62-98, ResBlock::new :37-44), one layer after the other:
+ *   conv:  weight [co,ci,3,3], bias [co]         batch_norm: weight, bias, running_mean, running_var
+ *   linear: weight [out,in], bias [out]
+ *   init conv, init bn | per block: conv1, conv2, bn1, bn2 | policy conv, bn, linear | value conv, bn, linear
+ * (die_e_b200/nnet.py reads them out of a tch VarStore `.ot` file.)  BatchNorm is folded into the
+ * convolutions at load time; the convolutions run on the tensor cores (tcgen05) in bf16 with fp32
+ * accumulation.  forward = forward_t (nnet.rs:120-133): policy_out f32 [n,1352] (softmaxed),
+ * value_out f32 [n] (tanh).  States are the packed 32-byte states; as_tensor is fused in. */
+typedef struct diee_net diee_net;
+int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *tensors, const int64_t *numels,
+                        int32_t n_tensors, diee_net **out);
+int32_t diee_net_destroy(diee_ctx *ctx, diee_net *net);
+int64_t diee_net_param_count(const diee_net *net);
+int32_t diee_net_forward(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, float *policy_out,
+                         float *value_out);
+int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, float *policy_out,
+                             float *value_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,91 @@
+"""GPU tests of the policy/value net (tcgen05 implicit-GEMM convolutions) through the C ABI.
+
+Floating point: the product computes in bf16 with fp32 accumulation.  Two bars are asserted:
+  (1) against the torch oracle that follows the SAME numeric recipe (net_oracle.forward_bf16_emulated:
+      folded BatchNorm, bf16 weights/activations, wide accumulation) the outputs agree to within
+      accumulation-order noise for shallow nets (value |dv| <= 2e-3, policy |dp| <= 0.5 % of the row
+      maximum for <= 2 blocks); through all 39 convolutions single bf16 rounding flips get amplified, so
+      the 19-block bar is the bf16 noise floor itself (|dv| <= 6e-2, |dp| <= 10 % of the row maximum);
+  (2) against the fp64 oracle of the reference architecture the bf16 error itself is bounded
+      (value |dv| <= 0.1, policy total-variation distance <= 0.05) and printed.
+north_star's 1e-5 (relative, vs the fp32 reference) is NOT met by the bf16 path and is not claimed."""
+import numpy as np
+import pytest
+
+import net_oracle
+import positions
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from die_e_b200 import _ffi
+    return _ffi.Context(0)
+
+
+def _inputs(oracle, n, seed=1):
+    states = positions.midgame_positions(seed=seed, n=n, max_adv=100)
+    x = np.concatenate([oracle.bg_as_tensor(states[i:i + 1]) for i in range(n)])
+    return states, x
+
+
+@pytest.mark.parametrize("filters,blocks,n,bn", [(128, 1, 20, "identity"), (256, 2, 37, "random"), (256, 19, 48, "random")])
+def test_forward_matches_oracles(ctx, oracle, filters, blocks, n, bn):
+    from die_e_b200 import _ffi, nnet
+    tens = nnet.synthetic_tensors(seed=7, filters=filters, blocks=blocks, bn_stats=bn)
+    net = _ffi.Net(ctx, tens)
+    states, x = _inputs(oracle, n)
+    p, v = net.forward(states)
+    assert np.isfinite(p).all() and np.isfinite(v).all()
+    assert np.allclose(p.sum(1), 1.0, atol=1e-4)
+    pe, ve = net_oracle.forward_bf16_emulated(tens, x, blocks)
+    p64, v64 = net_oracle.forward(tens, x, blocks)
+    d_emul_v = np.abs(v - ve).max()
+    d_emul_p = (np.abs(p - pe).max(1) / pe.max(1)).max()
+    d64_v = np.abs(v - v64).max()
+    tv64 = 0.5 * np.abs(p - p64).sum(1).max()
+    print(f"\n[net F={filters} B={blocks} n={n}] vs bf16-emulated: dv={d_emul_v:.2e} dp/max={d_emul_p:.2e} | "
+          f"vs fp64: dv={d64_v:.2e} TV={tv64:.2e} (oracle's own bf16 cost: dv={np.abs(ve - v64).max():.2e})")
+    if blocks <= 2:
+        assert d_emul_v <= 2e-3 and d_emul_p <= 5e-3
+    else:
+        assert d_emul_v <= 6e-2 and d_emul_p <= 1e-1
+    assert d64_v <= 0.1 and tv64 <= 0.05
+    assert (p.argmax(1) == pe.argmax(1)).mean() >= 0.9
+    net.close()
+
+
+def test_batch_edges_and_determinism(ctx, oracle):
+    from die_e_b200 import _ffi, nnet
+    tens = nnet.synthetic_tensors(seed=9, filters=128, blocks=1, bn_stats="random")
+    net = _ffi.Net(ctx, tens)
+    states, x = _inputs(oracle, 50, seed=3)
+    p_all, v_all = net.forward(states)
+    for n in (1, 15, 16, 17, 33):
+        p, v = net.forward(states[:n])
+        assert (p == p_all[:n]).all() and (v == v_all[:n]).all()   # results do not depend on the batch tiling
+    p0, v0 = net.forward(states[:0])
+    assert p0.shape == (0, 1352)
+    bad = states[:2].copy()
+    bad["roll"][1] = (0, 0)
+    with pytest.raises(_ffi.DieeError):
+        net.forward(bad)
+    with pytest.raises(_ffi.DieeError):
+        _ffi.Net(ctx, tens[:-1])
+    net.close()
+
+
+def test_resnet_host_object(ctx, oracle, tmp_path):
+    from die_e_b200 import nnet
+    net = nnet.ResNet.new(seed=5, filters=128, blocks=1, bn_stats="random", ctx=ctx)
+    states, x = _inputs(oracle, 9)
+    p, v = net.forward_t(x)                      # the reference's call shape: [N,6,4,6] float tensor
+    p2, v2 = net.forward_t(states)
+    assert p.shape == (9, 1352) and v.shape == (9, 1) and (p == p2).all() and (v == v2).all()
+    assert (net.forward_policy(states) == p).all()
+    path = tmp_path / "best_model.ot"
+    net.save(path)
+    net2 = nnet.ResNet.from_path(path, ctx=ctx)
+    p3, v3 = net2.forward_t(states)
+    assert (p3 == p).all() and (v3 == v).all()

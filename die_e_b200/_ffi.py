@@ -28,6 +28,11 @@ NODE = np.dtype([("parent", "i4"), ("visits", "f4"), ("value", "f4"), ("action",
                  ("n_moves", "i4"), ("n_untried", "i4")])
 SEARCH_STATS = np.dtype([("rollout_plies", "u8"), ("select_levels", "u4"), ("select_children", "u4"),
                          ("expansions", "u4"), ("terminal_leaves", "u4")])
+ANODE = np.dtype([("parent", "i4"), ("first_child", "i4"), ("n_children", "i4"), ("visits", "f4"), ("value", "f4"),
+                  ("prior", "f4"), ("action", MOVE), ("state", BG_STATE)])
+TRAJ = np.dtype([("state", BG_STATE), ("game_id", "u4"), ("ply", "u2"), ("outcome", "i1"), ("pad", "u1"),
+                 ("n_pi", "u2"), ("pad2", "u2"), ("pi_offset", "u4")])
+assert ANODE.itemsize == 60 and TRAJ.itemsize == 48
 assert SEARCH_STATS.itemsize == 24
 assert BG_STATE.itemsize == 32 and MOVE.itemsize == 4 and TTT_STATE.itemsize == 16 and NODE.itemsize == 24
 
@@ -39,6 +44,7 @@ SYMBOLS = [
     "diee_bg_playout", "diee_bg_playout_dev", "diee_bg_encode_moves", "diee_bg_decode_moves",
     "diee_bg_encode_states", "diee_bg_encode_states_dev", "diee_mcts_search", "diee_mcts_search_dev",
     "diee_net_create", "diee_net_destroy", "diee_net_param_count", "diee_net_forward", "diee_net_forward_dev",
+    "diee_dirichlet", "diee_alpha_search", "diee_selfplay_run", "diee_net_eval_count",
 ]
 
 
@@ -66,6 +72,8 @@ def lib():
         L.diee_launch_count.argtypes = [C.c_void_p]
         L.diee_net_param_count.restype = C.c_int64
         L.diee_net_param_count.argtypes = [C.c_void_p]
+        L.diee_net_eval_count.restype = C.c_uint64
+        L.diee_net_eval_count.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -82,6 +90,15 @@ def _p(a):
 def philox(seed, c0, c1, c2, c3):
     out = np.zeros(4, dtype=np.uint32)
     lib().diee_philox(C.c_uint64(seed), C.c_uint32(c0), C.c_uint32(c1), C.c_uint32(c2), C.c_uint32(c3), _p(out))
+    return out
+
+
+def dirichlet(seed, epoch, alpha, n=ACTION_SPACE):
+    """the shared root-noise vector of one search wave (mcts/noise.rs:27-34); host-side, no GPU needed"""
+    out = np.zeros(n, dtype=np.float32)
+    rc = lib().diee_dirichlet(C.c_uint64(seed), C.c_uint32(epoch), C.c_float(alpha), C.c_int32(n), _p(out))
+    if rc != OK:
+        raise DieeError(rc, "diee_dirichlet: bad argument")
     return out
 
 
@@ -196,6 +213,46 @@ class Context:
         if dump:
             return best, status, stats, nodes, nstates, n_nodes, finals
         return best, status, stats
+
+    # ---- AlphaZero search / self-play ----
+    def net_eval_count(self):
+        return int(lib().diee_net_eval_count(self._h))
+
+    def alpha_search(self, net, states, game_ids, cfg, seed, epoch=0, max_nodes=0, dump=False):
+        states = np.ascontiguousarray(states, dtype=BG_STATE).reshape(-1)
+        n = len(states)
+        game_ids = np.ascontiguousarray(game_ids, dtype=np.uint32).reshape(-1)
+        assert len(game_ids) == n
+        cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]
+        if max_nodes <= 0:
+            max_nodes = 1 + (int(cfg["iterations"][0]) + 1) * 128
+        ids = np.zeros((n, MAX_MOVES), dtype=np.uint16)
+        moves = np.zeros((n, MAX_MOVES), dtype=MOVE)
+        visits = np.zeros((n, MAX_MOVES), dtype=np.float32)
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        nodes = np.zeros((n, max_nodes), dtype=ANODE) if dump else None
+        n_nodes = np.zeros(n, dtype=np.int32) if dump else None
+        self._chk(lib().diee_alpha_search(self._h, net._h, _p(states), C.c_int32(n), _p(game_ids), _p(cfg), C.c_uint64(seed),
+                                          C.c_uint32(epoch), C.c_int32(max_nodes), _p(ids), _p(moves), _p(visits), _p(counts),
+                                          _p(status), _p(nodes), _p(n_nodes)))
+        if dump:
+            return ids, moves, visits, counts, status, nodes, n_nodes
+        return ids, moves, visits, counts, status
+
+    def selfplay_run(self, net, n_games, cfg, temperature, seed, first_game_id=0, max_nodes=0, rec_cap=None, pi_cap=None):
+        cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]
+        limit = int(cfg["simulate_round_limit"][0])
+        rec_cap = rec_cap or n_games * (2 * limit + 4)
+        pi_cap = pi_cap or rec_cap * 48
+        rec = np.zeros(rec_cap, dtype=TRAJ)
+        pi_ids = np.zeros(pi_cap, dtype=np.uint16)
+        pi_vals = np.zeros(pi_cap, dtype=np.float32)
+        n_rec, n_pi, n_waves = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._chk(lib().diee_selfplay_run(self._h, net._h, C.c_int32(n_games), _p(cfg), C.c_float(temperature), C.c_uint64(seed),
+                                          C.c_uint32(first_game_id), C.c_int32(max_nodes), _p(rec), C.c_int32(rec_cap), _p(pi_ids),
+                                          _p(pi_vals), C.c_int32(pi_cap), C.byref(n_rec), C.byref(n_pi), C.byref(n_waves)))
+        return rec[: n_rec.value], pi_ids[: n_pi.value], pi_vals[: n_pi.value], n_waves.value
 
     # ---- device-pointer forms (ints = raw device addresses, e.g. torch tensor .data_ptr()) ----
     def bg_playout_dev(self, d_starts, n, seed, first_game_id, round_limit, d_winners, d_plies, d_finals=0):

@@ -45,7 +45,11 @@ int32_t diee_ctx_destroy(diee_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->s_states, &ctx->s_moves, &ctx->s_counts, &ctx->s_ids, &ctx->s_aux, &ctx->s_out,
                       &ctx->s_players, &ctx->s_best, &ctx->s_status, &ctx->s_plies, &ctx->p_states, &ctx->p_parent,
                       &ctx->p_visits, &ctx->p_value, &ctx->p_action, &ctx->p_nmoves, &ctx->p_nnodes, &ctx->p_simnode, &ctx->p_finals,
-                      &ctx->ln_table};
+                      &ctx->ln_table, &ctx->a_state, &ctx->a_parent, &ctx->a_first, &ctx->a_nchild, &ctx->a_visits, &ctx->a_value,
+                      &ctx->a_prior, &ctx->a_action, &ctx->a_nnodes, &ctx->a_selg, &ctx->a_seln, &ctx->a_status, &ctx->a_any,
+                      &ctx->a_batch, &ctx->a_policy, &ctx->a_valueout, &ctx->a_dir, &ctx->a_states_in, &ctx->a_ids_in,
+                      &ctx->a_root_ids, &ctx->a_root_moves, &ctx->a_root_visits, &ctx->a_root_counts, &ctx->a_moves_in,
+                      &ctx->a_rolls_in};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

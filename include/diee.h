@@ -224,6 +224,47 @@ int32_t diee_net_forward(diee_ctx *ctx, diee_net *net, const diee_bg_state *stat
 int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, float *policy_out,
                              float *value_out);
 
+/* ---- AlphaZero search: alpha_mcts_parallel (mcts/alpha_mcts.rs:91-202) ----
+ * Lock-step search over n games with the net evaluated once per iteration for the whole batch.
+ * game_ids[i] = global id of game i (keys its random streams); epoch = the wave number (keys the
+ * shared Dirichlet vector and the expansion dice).  Returns, per game, the root's children in
+ * legal-move order: action ids (encode), moves and visit counts -- what get_prob_tensor_parallel
+ * (mcts/utils.rs:42-58) reads.  max_nodes = node slab per game (0 = 1 + (iterations+1)*128: no observed position has more than 123 legal plays);
+ * status_out[i] = DIEE_ERR_OVERFLOW if it was exhausted.  nodes_out (nullable, [n*max_nodes]) dumps the pool.
+ * Contract where the reference leaves arithmetic to libtorch/rand: masked-policy sums are sequential
+ * f32 in legal-move order; games are slots in the order given; diee_dirichlet() is the noise vector. */
+typedef struct {
+    int32_t parent, first_child, n_children;
+    float visits, value, prior;
+    diee_move action;
+    diee_bg_state state;
+} diee_anode;
+/* one MemoryFragment (alphazero/alphazero.rs:69-73) in packed form: state instead of the [1,6,4,6] tensor,
+ * pi^(1/T) as (action id, weight) pairs pi_ids/pi_vals[pi_offset .. pi_offset+n_pi) */
+typedef struct {
+    diee_bg_state state;
+    uint32_t game_id;
+    uint16_t ply;
+    int8_t outcome;
+    uint8_t pad;
+    uint16_t n_pi;
+    uint16_t pad2;
+    uint32_t pi_offset;
+} diee_traj_record;
+int32_t diee_dirichlet(uint64_t seed, uint32_t epoch, float alpha, int32_t n, float *out);
+int32_t diee_alpha_search(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, const uint32_t *game_ids,
+                          const diee_mcts_cfg *cfg, uint64_t seed, uint32_t epoch, int32_t max_nodes, uint16_t *root_ids_out,
+                          diee_move *root_moves_out, float *root_visits_out, int32_t *root_counts_out, int32_t *status_out,
+                          diee_anode *nodes_out, int32_t *n_nodes_out);
+/* self_play_parallel (alphazero/alpha_parallel.rs:101-231): n_games games from the opening position in
+ * lock-step until every game has a winner or hit cfg->simulate_round_limit; records are appended in the
+ * reference's emission order (quirk Q10 included).  Game i has id first_game_id + i. */
+int32_t diee_selfplay_run(diee_ctx *ctx, diee_net *net, int32_t n_games, const diee_mcts_cfg *cfg, float temperature,
+                          uint64_t seed, uint32_t first_game_id, int32_t max_nodes, diee_traj_record *rec_out, int32_t rec_cap,
+                          uint16_t *pi_ids_out, float *pi_vals_out, int32_t pi_cap, int32_t *n_rec_out, int32_t *n_pi_out,
+                          int32_t *n_waves_out);
+uint64_t diee_net_eval_count(const diee_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

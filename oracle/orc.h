@@ -162,6 +162,34 @@ int orc_mcts_search_ttt(const orc_ttt_state *root, int player, const orc_mcts_cf
                         uint32_t game_id, uint32_t epoch, uint8_t *best, orc_node_stats *nodes_out,
                         orc_ttt_state *states_out, int32_t *n_nodes_out);
 
+/* ---- AlphaZero search + self-play (mcts/alpha_mcts.rs, alphazero/alpha_parallel.rs) ---- */
+typedef void (*orc_eval_fn)(const orc_bg_state *states, int n, float *policy /*[n*1352]*/, float *value /*[n]*/, void *user);
+typedef struct {
+    int32_t parent, first_child, n_children;
+    float visits, value, prior;
+    orc_move action;
+    orc_bg_state state;
+} orc_anode; /* 60 bytes */
+typedef struct {
+    orc_bg_state state;
+    uint32_t game_id;
+    uint16_t ply;
+    int8_t outcome;
+    uint8_t pad;
+    uint16_t n_pi;
+    uint16_t pad2;
+    uint32_t pi_offset;
+} orc_traj_record; /* 48 bytes */
+void orc_dirichlet(uint64_t seed, uint32_t epoch, float alpha, int n, float *out);
+int orc_alpha_mcts_parallel(const orc_bg_state *states, int n, const uint32_t *game_ids, const orc_mcts_cfg *cfg,
+                            uint64_t seed, uint32_t epoch, orc_eval_fn eval, void *user, int max_nodes,
+                            orc_anode *nodes_out, int32_t *n_nodes_out, int32_t *status_out);
+int orc_root_pi(const orc_anode *nodes, float temperature_inv, uint16_t *ids_out, float *pi_out);
+int orc_weighted_select(const uint16_t *ids, const float *pi, int n, uint64_t seed, uint32_t game_id, uint32_t ply);
+int orc_self_play(int n_games, const orc_mcts_cfg *cfg, float temperature, uint64_t seed, uint32_t first_game_id,
+                  orc_eval_fn eval, void *user, int max_nodes, orc_traj_record *rec_out, int rec_cap, uint16_t *pi_ids_out,
+                  float *pi_vals_out, int pi_cap, int *n_rec_out, int *n_pi_out, int *n_waves_out);
+
 /* ---- thread-pool batch drivers (the reference's rayon par_iter over games, versus.rs:303-316) ---- */
 int orc_mcts_search_bg_batch(const orc_bg_state *states, int n, const int8_t *players, const orc_mcts_cfg *cfg,
                              uint64_t seed, uint32_t first_game_id, uint32_t epoch, orc_move *best, int32_t *status,

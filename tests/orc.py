@@ -345,3 +345,54 @@ def bg_playout_batch(states, seed, first_game_id, round_limit, nthreads):
     lib().orc_bg_playout_batch(_p(states), C.c_int(n), C.c_uint64(seed), C.c_uint32(first_game_id), C.c_int(round_limit),
                                _p(winners), _p(plies), C.c_int(nthreads))
     return winners, plies
+
+
+# ---- AlphaZero search / self-play oracle ----
+ANODE_A = np.dtype([("parent", "i4"), ("first_child", "i4"), ("n_children", "i4"), ("visits", "f4"), ("value", "f4"),
+                    ("prior", "f4"), ("action", MOVE), ("state", BG_STATE)])
+TRAJ = np.dtype([("state", BG_STATE), ("game_id", "u4"), ("ply", "u2"), ("outcome", "i1"), ("pad", "u1"),
+                 ("n_pi", "u2"), ("pad2", "u2"), ("pi_offset", "u4")])
+EVAL_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+
+
+def make_eval(fn):
+    """fn(states: BG_STATE array) -> (policy [n,1352] f32, value [n] f32); returns a C callback"""
+    def cb(states_p, n, policy_p, value_p, _user):
+        st = np.ctypeslib.as_array(C.cast(states_p, C.POINTER(C.c_uint8)), shape=(n * 32,)).view(BG_STATE).copy()
+        p, v = fn(st)
+        np.ctypeslib.as_array(C.cast(policy_p, C.POINTER(C.c_float)), shape=(n * 1352,))[:] = np.asarray(p, dtype=np.float32).reshape(-1)
+        np.ctypeslib.as_array(C.cast(value_p, C.POINTER(C.c_float)), shape=(n,))[:] = np.asarray(v, dtype=np.float32).reshape(-1)
+    return EVAL_FN(cb)
+
+
+def dirichlet(seed, epoch, alpha, n=1352):
+    out = np.zeros(n, dtype=np.float32)
+    lib().orc_dirichlet(C.c_uint64(seed), C.c_uint32(epoch), C.c_float(alpha), C.c_int(n), _p(out))
+    return out
+
+
+def alpha_mcts_parallel(states, game_ids, cfg, seed, epoch, eval_cb, max_nodes):
+    states = np.ascontiguousarray(states).reshape(-1)
+    n = len(states)
+    game_ids = np.ascontiguousarray(game_ids, dtype=np.uint32)
+    nodes = np.zeros((n, max_nodes), dtype=ANODE_A)
+    n_nodes = np.zeros(n, dtype=np.int32)
+    status = np.zeros(n, dtype=np.int32)
+    lib().orc_alpha_mcts_parallel(_p(states), C.c_int(n), _p(game_ids), _p(cfg), C.c_uint64(seed), C.c_uint32(epoch), eval_cb,
+                                  C.c_void_p(0), C.c_int(max_nodes), _p(nodes), _p(n_nodes), _p(status))
+    return nodes, n_nodes, status
+
+
+def self_play(n_games, cfg, temperature, seed, first_game_id, eval_cb, max_nodes):
+    limit = int(cfg["simulate_round_limit"][0])
+    rec_cap = n_games * (2 * limit + 4)
+    pi_cap = rec_cap * 48
+    rec = np.zeros(rec_cap, dtype=TRAJ)
+    pi_ids = np.zeros(pi_cap, dtype=np.uint16)
+    pi_vals = np.zeros(pi_cap, dtype=np.float32)
+    n_rec, n_pi, n_waves = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = lib().orc_self_play(C.c_int(n_games), _p(cfg), C.c_float(temperature), C.c_uint64(seed), C.c_uint32(first_game_id),
+                             eval_cb, C.c_void_p(0), C.c_int(max_nodes), _p(rec), C.c_int(rec_cap), _p(pi_ids), _p(pi_vals),
+                             C.c_int(pi_cap), C.byref(n_rec), C.byref(n_pi), C.byref(n_waves))
+    assert rc == 0, rc
+    return rec[: n_rec.value], pi_ids[: n_pi.value], pi_vals[: n_pi.value], n_waves.value

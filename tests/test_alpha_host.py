@@ -1,0 +1,53 @@
+"""CPU checks for the AlphaZero path: the host-side Dirichlet sampler of the product equals the oracle's
+(bit for bit), and the oracle's search/self-play behave sanely with a synthetic net callback."""
+import numpy as np
+
+
+def test_dirichlet_product_equals_oracle(oracle):
+    from die_e_b200 import _ffi
+    for seed, epoch, alpha in [(1, 0, 0.3), (0xD1EE, 7, 0.3), (5, 3, 1.0), (9, 1, 2.5), (2, 2, 0.03)]:
+        a = _ffi.dirichlet(seed, epoch, alpha)
+        b = oracle.dirichlet(seed, epoch, alpha)
+        assert a.tobytes() == b.tobytes()
+        assert abs(float(a.sum()) - 1.0) < 1e-5 and (a >= 0).all()
+    assert _ffi.dirichlet(1, 0, 0.3).tobytes() != _ffi.dirichlet(1, 1, 0.3).tobytes()
+
+
+def _uniform_eval(states):
+    n = len(states)
+    p = np.full((n, 1352), 1.0 / 1352, dtype=np.float32)
+    v = (states["off"][:, 0].astype(np.float32) - states["off"][:, 1].astype(np.float32)) / 15.0
+    return p, v * states["player"].astype(np.float32) * -1.0
+
+
+def test_oracle_alpha_search_invariants(oracle):
+    import positions
+    states = positions.midgame_positions(seed=3, n=6, max_adv=60)
+    cfg = oracle.mcts_cfg(iterations=30, c=2.0, limit=400)
+    cb = oracle.make_eval(_uniform_eval)
+    nodes, n_nodes, status = oracle.alpha_mcts_parallel(states, np.arange(6), cfg, 11, 0, cb, 1 + 31 * 40)
+    assert (status == 0).all()
+    for g in range(6):
+        t = nodes[g, :n_nodes[g]]
+        root = t[0]
+        nc = int(root["n_children"])
+        assert nc == len(oracle.bg_valid_moves(states[g:g + 1]))
+        ch = t[root["first_child"]:root["first_child"] + nc]
+        if nc:
+            assert abs(float(ch["prior"].sum()) - 1.0) < 1e-4
+            # every iteration passes through the root: visits = 1 + iterations (+ stale hits on game 0, Q9)
+            assert root["visits"] >= 31
+            assert ch["visits"].sum() == root["visits"] - 1 or g == 0
+
+
+def test_oracle_self_play_records(oracle):
+    cfg = oracle.mcts_cfg(iterations=4, c=2.0, limit=60)
+    cb = oracle.make_eval(_uniform_eval)
+    rec, pi_ids, pi_vals, waves = oracle.self_play(3, cfg, 1.25, 5, 100, cb, 1 + 5 * 40)
+    assert len(rec) > 0 and waves >= 60 or waves > 0
+    assert set(np.unique(rec["outcome"])) <= {-1, 0, 1}
+    assert (rec["game_id"] >= 100).all() and (rec["game_id"] < 103).all()
+    for r in rec[:50]:
+        ids = pi_ids[r["pi_offset"]:r["pi_offset"] + r["n_pi"]]
+        want = [oracle.bg_encode(np.array([r["state"]]), m) for m in oracle.bg_valid_moves(np.array([r["state"]]))]
+        assert list(ids) == want

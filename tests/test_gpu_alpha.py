@@ -1,0 +1,105 @@
+"""GPU parity tests of the AlphaZero search and the self-play driver against the CPU oracle.
+
+The oracle's net is a callback that evaluates each batch with the PRODUCT's net on the GPU, so both
+sides see identical net outputs ("visit counts given identical net outputs"); the net
+forward is batch-tiling invariant (tests/test_gpu_net.py), so a state gets the same outputs whatever
+batch it is in.  Bar: bit-exact -- every node's parent / child range / visits / value / prior /
+action / state, the per-game status, and every self-play record (state, outcome, ply, pi ids, pi values)."""
+import numpy as np
+import pytest
+
+import positions
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from die_e_b200 import _ffi
+    return _ffi.Context(0)
+
+
+@pytest.fixture(scope="module")
+def net(ctx):
+    from die_e_b200 import _ffi, nnet
+    return _ffi.Net(ctx, nnet.synthetic_tensors(seed=21, filters=128, blocks=1, bn_stats="random"))
+
+
+def _eval_cb(oracle, net):
+    return oracle.make_eval(lambda st: net.forward(st))
+
+
+def _cmp_pools(oracle, got_nodes, got_n, want_nodes, want_n):
+    assert (got_n == want_n).all()
+    for g in range(len(got_n)):
+        k = int(want_n[g])
+        a, b = got_nodes[g, :k], want_nodes[g, :k]
+        for f in ("parent", "first_child", "n_children"):
+            assert (a[f] == b[f]).all(), (g, f)
+        for f in ("visits", "value", "prior", "action", "state"):
+            assert a[f].tobytes() == b[f].tobytes(), (g, f)
+
+
+@pytest.mark.parametrize("n,iters,seed", [(16, 25, 3), (40, 12, 9)])
+def test_alpha_search_bit_exact(ctx, net, oracle, n, iters, seed):
+    states = positions.midgame_positions(seed=seed, n=n, max_adv=110)
+    ids = np.arange(100, 100 + n, dtype=np.uint32)
+    cfg = oracle.mcts_cfg(iterations=iters, c=2.0, limit=400, alpha=0.3, eps=0.25)
+    max_nodes = 1 + (iters + 1) * 40
+    r_ids, r_moves, r_vis, r_cnt, status, nodes, n_nodes = ctx.alpha_search(net, states, ids, cfg, seed, epoch=4,
+                                                                            max_nodes=max_nodes, dump=True)
+    o_nodes, o_n, o_status = oracle.alpha_mcts_parallel(states, ids, cfg, seed, 4, _eval_cb(oracle, net), max_nodes)
+    assert (status == o_status).all() and (status == 0).all()
+    _cmp_pools(oracle, nodes, n_nodes, o_nodes, o_n)
+    for g in range(n):
+        root = o_nodes[g, 0]
+        nc = int(root["n_children"])
+        assert r_cnt[g] == nc
+        ch = o_nodes[g, root["first_child"]:root["first_child"] + nc]
+        assert r_vis[g, :nc].tobytes() == ch["visits"].tobytes()
+        assert r_moves[g, :nc].tobytes() == ch["action"].tobytes()
+        assert [int(x) for x in r_ids[g, :nc]] == [oracle.bg_encode(states[g:g + 1], m) for m in oracle.moves_to_list(ch["action"], nc)]
+
+
+def test_alpha_search_endgame_quirks(ctx, net, oracle):
+    """positions one move from the end: terminal leaves (value +-1 w.r.t. the root player), stale slots that
+    hit game 0's root (Q9), a root with no legal move (Q12) and an already finished game"""
+    def pts(d):
+        p = [0] * 24
+        for k, v in d.items():
+            p[k] = v
+        return p
+    states = np.concatenate([
+        oracle.make_state(pts({3: -2, 20: 3}), off=(13, 12), roll=(5, 3), player=-1),
+        oracle.make_state(pts({0: -1, 23: 1}), off=(14, 14), roll=(3, 4), player=-1),
+        oracle.make_state(pts({0: -1, 23: 1}), off=(14, 14), roll=(6, 6), player=1),
+        oracle.make_state(pts({20: -1, 19: 2, 18: 2, 2: 1}), off=(14, 10), roll=(1, 2), player=-1),
+        oracle.make_state(pts({5: -2, 4: -3, 18: 2, 19: 3}), off=(10, 10), roll=(2, 1), player=1),
+        oracle.make_state(pts({1: -1}), off=(14, 15), roll=(2, 1), player=-1),
+    ])
+    ids = np.arange(6, dtype=np.uint32)
+    cfg = oracle.mcts_cfg(iterations=20, c=2.0, limit=400)
+    r = ctx.alpha_search(net, states, ids, cfg, 77, epoch=0, max_nodes=600, dump=True)
+    o_nodes, o_n, o_status = oracle.alpha_mcts_parallel(states, ids, cfg, 77, 0, _eval_cb(oracle, net), 600)
+    assert (r[4] == o_status).all()
+    _cmp_pools(oracle, r[5], r[6], o_nodes, o_n)
+    # pool exhaustion is reported per game, identically
+    r2 = ctx.alpha_search(net, states[:2], ids[:2], cfg, 77, epoch=0, max_nodes=8, dump=True)
+    o2 = oracle.alpha_mcts_parallel(states[:2], ids[:2], cfg, 77, 0, _eval_cb(oracle, net), 8)
+    assert (r2[4] == o2[2]).all()
+
+
+@pytest.mark.parametrize("n_games,iters,limit", [(12, 6, 400), (10, 4, 40)])
+def test_self_play_bit_exact(ctx, net, oracle, n_games, iters, limit):
+    cfg = oracle.mcts_cfg(iterations=iters, c=2.0, limit=limit, alpha=0.3, eps=0.25)
+    max_nodes = 1 + (iters + 1) * 128
+    rec, pi_ids, pi_vals, waves = ctx.selfplay_run(net, n_games, cfg, 1.25, seed=31, first_game_id=1000, max_nodes=max_nodes)
+    o_rec, o_ids, o_vals, o_waves = oracle.self_play(n_games, cfg, 1.25, 31, 1000, _eval_cb(oracle, net), max_nodes)
+    assert waves == o_waves and len(rec) == len(o_rec) and len(rec) > 0
+    assert rec.tobytes() == o_rec.tobytes()
+    assert pi_ids.tobytes() == o_ids.tobytes() and pi_vals.tobytes() == o_vals.tobytes()
+    if limit == 400:
+        assert set(np.unique(rec["outcome"])) == {-1, 1}          # every game was played to a winner
+        assert len(np.unique(rec["game_id"])) == n_games
+    else:
+        assert (rec["outcome"] == 0).any()                         # round-capped games (Q10)

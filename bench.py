@@ -42,6 +42,18 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peaks():
+    """(burst, sustained) dense bf16 TFLOP/s"""
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["bf16_tflops"]), float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+NET_FLOP_PER_EVAL = 1.0825e9  # SURVEY 8(a) N1: dense-tap 2*MAC count of one forward (256 filters, 19 blocks)
+
+
 class ClockSampler:
     """samples nvidia-smi clocks / throttle reasons during the timed region"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -174,6 +186,51 @@ def run_ours(args, rank, world):
         metric, unit = "mcts_simulations_per_sec", "simulations/s"
         wl = (f"backgammon pure MCTS (BASELINE configs[2]): {G} games/GPU, iterations={args.iterations}, c=2, "
               f"simulate_round_limit={args.round_limit}, rollout={args.rollout}, no-move nodes=PASS_CHILD")
+    elif args.workload in ("alpha", "selfplay"):
+        from die_e_b200 import nnet
+        cfg = np.zeros(1, dtype=ffi.MCTS_CFG)
+        cfg[0] = (args.iterations, 2.0, args.round_limit, 0.3, 0.25, 0)
+        net = ffi.Net(ctx, nnet.synthetic_tensors(seed=SEED, filters=256, blocks=19, bn_stats="identity"))
+        h_states = midgame_states(ctx, ffi, first_gid, G)
+        h_ids = np.arange(first_gid, first_gid + G, dtype=np.uint32)
+        d_states = torch.from_numpy(h_states.view(np.uint8).reshape(G, 32)).to(dev)
+        d_ids = torch.from_numpy(h_ids.view(np.int32)).to(dev)
+        d_rids = torch.zeros(G, ffi.MAX_MOVES, dtype=torch.int16, device=dev)
+        d_rmoves = torch.zeros(G, ffi.MAX_MOVES, dtype=torch.int32, device=dev)
+        d_rvis = torch.zeros(G, ffi.MAX_MOVES, dtype=torch.float32, device=dev)
+        d_rcnt = torch.zeros(G, dtype=torch.int32, device=dev)
+        d_status = torch.zeros(G, dtype=torch.int32, device=dev)
+        units_per_step = G * args.iterations
+        if args.workload == "alpha":
+            def step_dev(i):
+                ctx.alpha_search_dev(net, d_states.data_ptr(), G, d_ids.data_ptr(), cfg, SEED, i & 0xFFFF, 0, d_rids.data_ptr(),
+                                     d_rmoves.data_ptr(), d_rvis.data_ptr(), d_rcnt.data_ptr(), d_status.data_ptr())
+            p_states = torch.from_numpy(h_states.view(np.uint8).reshape(G, 32).copy()).pin_memory()
+            np_states = p_states.numpy().view(ffi.BG_STATE).reshape(-1)
+            h2d, d2h = G * 36, G * (ffi.MAX_MOVES * 10 + 8)
+
+            def step_e2e(i):
+                return ctx.alpha_search(net, np_states, h_ids, cfg, SEED, i & 0xFFFF)
+            metric, unit = "alphazero_simulations_per_sec", "simulations/s"
+            wl = (f"backgammon AlphaZero search (BASELINE configs[3]): {G} games/GPU in lock-step, iterations={args.iterations}, c=2, "
+                  "Dirichlet alpha=0.3 eps=0.25, policy/value ResNet 256x19 (synthetic weights) evaluated once per iteration for the "
+                  "whole batch; one step = one alpha_mcts_parallel (one game-move of every game)")
+        else:
+            units_per_step = G  # games
+            sp_info = {}
+
+            def step_dev(i):
+                t0 = time.perf_counter()
+                e0 = ctx.net_eval_count()
+                rec, pi_ids, pi_vals, waves = ctx.selfplay_run(net, G, cfg, 1.25, SEED + i, first_gid)
+                sp_info.update(records=len(rec), waves=waves, evals=ctx.net_eval_count() - e0, wall=time.perf_counter() - t0,
+                               rec=(rec, pi_ids, pi_vals))
+            h2d, d2h = 0, 0
+            step_e2e = None
+            metric, unit = "selfplay_games_per_sec", "games/s"
+            wl = (f"backgammon AlphaZero self-play (BASELINE configs[3]): {G} games/GPU from the opening to a winner, "
+                  f"iterations={args.iterations}, c=2, alpha=0.3 eps=0.25, temperature=1.25, round limit {args.round_limit}; "
+                  "one step = one self_play_parallel")
     else:
         h_states = initial_states(ffi, first_gid, G)
         d_states = torch.from_numpy(h_states.view(np.uint8).reshape(G, 32)).to(dev)
@@ -219,10 +276,13 @@ def run_ours(args, rank, world):
         if args.workload == "playout":
             evs[i][1].synchronize()
             units += float(d_plies.sum().item())
-        else:
+        elif args.workload == "mcts":
             evs[i][1].synchronize()
             st = d_stats.cpu().numpy().view(ffi.SEARCH_STATS).reshape(-1)
             stats_acc = st if stats_acc is None else np.concatenate([stats_acc, st])
+            units += units_per_step
+        else:
+            evs[i][1].synchronize()
             units += units_per_step
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -230,18 +290,34 @@ def run_ours(args, rank, world):
     launches = ctx.launch_count() - launches0
     kern_ms = [a.elapsed_time(b) for a, b in evs]
     dev_ms = float(sum(kern_ms))
-    assert int(d_status.abs().sum().item()) == 0 if args.workload == "mcts" else True
+    assert int(d_status.abs().sum().item()) == 0 if args.workload in ("mcts", "alpha") else True
 
     # ---- timed: end to end through the host-buffer C-ABI call ----
-    step_e2e(0)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_units = 0.0
-    for i in range(args.steps):
-        r = step_e2e(args.warmup + i)
-        e2e_units += units_per_step if args.workload == "mcts" else float(r[1].sum())
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    gathered = None
+    if args.workload == "selfplay":
+        # diee_selfplay_run IS the public host call (opening positions are made inside, records land in host
+        # buffers); what is added here is the one exchange step: all-gather of the trajectories over NCCL
+        e2e_units, e2e_s = units, t_wall
+        if world > 1:
+            from die_e_b200 import parallel
+            barrier()
+            tg = time.perf_counter()
+            gathered = parallel.allgather_trajectories(*sp_info["rec"])
+            barrier()
+            sp_info["allgather_s"] = time.perf_counter() - tg
+            e2e_s += sp_info["allgather_s"]
+            sp_info["gathered_records"] = len(gathered[0])
+        d2h = int(sp_info["records"]) * 48
+    else:
+        step_e2e(0)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_units = 0.0
+        for i in range(args.steps):
+            r = step_e2e(args.warmup + i)
+            e2e_units += float(r[1].sum()) if args.workload == "playout" else units_per_step
+        barrier()
+        e2e_s = time.perf_counter() - t0
 
     # ---- reduce over ranks: max time, summed units ----
     if world > 1:
@@ -263,22 +339,45 @@ def run_ours(args, rank, world):
             extra = {"bytes_per_simulation": round(b_sim, 1), "rollout_plies_per_simulation": round(plies_per_sim, 2),
                      "rollout_plies_per_sec": round(value * plies_per_sim, 1),
                      "mean_select_depth": round(float(stats_acc["select_levels"].sum()) / n_sims_local, 3)}
-        else:
+        elif args.workload == "playout":
             alg_bytes = 64.0 * units / args.steps / world  # 32 B read + 32 B write per ply
             extra = {"bytes_per_ply": 64, "games_per_sec": round(G * world * args.steps / (dev_ms / 1e3), 1),
                      "mean_plies_per_game": round(units / (G * world * args.steps), 2)}
+        else:
+            alg_bytes = 0.0
+            extra = {}
         avg_launch_ms = float(np.mean(kern_ms))
         achieved = alg_bytes / (avg_launch_ms / 1e3) / 1e9
+        roof = None
+        if args.workload in ("alpha", "selfplay"):
+            burst, sustained, tsrc = tensor_peaks()
+            if args.workload == "alpha":
+                evals = G * (args.iterations + 1)
+                step_s = avg_launch_ms / 1e3
+                extra = {"net_evals_per_step": evals, "net_evals_per_sec": round(evals / step_s, 1)}
+            else:
+                evals = sp_info["evals"]
+                step_s = avg_launch_ms / 1e3
+                extra = {"net_evals_per_step": int(evals), "waves_per_step": sp_info["waves"], "records_per_step": sp_info["records"],
+                         "simulations_per_sec": round(evals / step_s, 1), "allgather_s": sp_info.get("allgather_s"),
+                         "gathered_records": sp_info.get("gathered_records")}
+            tf = NET_FLOP_PER_EVAL * evals / step_s / 1e12
+            roof = {"bound": "tensor", "achieved": round(tf, 2), "peak": sustained, "unit": "TFLOP/s", "frac": round(tf / sustained, 4),
+                    "traffic": None, "peak_source": tsrc + " (sustained figure: the kernel runs inside a long step)",
+                    "kernel": "conv3x3_tc_kernel<128> (tcgen05, 38 of the 42 launches of one forward)",
+                    "note": "achieved = 1.0825 GFLOP per evaluated position x positions / step time, i.e. the WHOLE step "
+                            "(tree kernels, heads, host sampling included) charged against the tensor peak"}
         out = {
             "metric": metric, "value": round(value, 1), "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int8 boards / f32 UCB", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "int8 boards / f32 UCB" if args.workload in ("mcts", "playout") else "bf16 net (fp32 accumulate) / f32 PUCT",
+            "data": "synthetic",
             "config": {"workload": wl, "seed": hex(SEED), "timing": "CUDA events per step on the launch stream, "
                        "max over ranks; L2 flushed (256 MiB fill) between timed steps", "wall_s": round(t_wall, 3),
                        "parallelism": f"games sharded over {world} GPU(s), no collective", **extra},
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 4), "peak": hbm_peak, "unit": "GB/s",
+            "roofline": roof or {"bound": "hbm", "achieved": round(achieved, 4), "peak": hbm_peak, "unit": "GB/s",
                          "frac": round(achieved / hbm_peak, 8), "traffic": None, "peak_source": peak_src,
-                         "kernel": "mcts_search_kernel<BgGame>" if args.workload == "mcts" else "bg_playout_kernel",
+                         "kernel": "rollout_kernel<BgGame> + mcts_search_kernel<BgGame>" if args.workload == "mcts" else "bg_playout_kernel",
                          "note": "the path is integer-issue/latency bound, not HBM bound: the whole rollout runs in "
                                  "registers + shared memory (SURVEY 8d M-roofline (2)); see DESIGN.md and profiles/"},
             "e2e": {"value": round(e2e_units / e2e_s, 1), "unit": unit, "h2d_bytes_per_step": h2d * world,
@@ -288,7 +387,31 @@ def run_ours(args, rank, world):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return out, (h_states if args.workload == "mcts" else h_states)
+    return out, h_states
+
+
+def cpu_alpha_leg(args, h_states, threads):
+    """the reference's AlphaZero search on the host: the C oracle's single-threaded lock-step loop
+    (alpha_mcts.rs:153) around a PyTorch-CPU fp32 forward of the same ResNet (all cores)"""
+    import orc
+    import net_oracle
+    import torch
+    from die_e_b200 import nnet
+    torch.set_num_threads(threads)
+    tens = nnet.synthetic_tensors(seed=SEED, filters=256, blocks=19, bn_stats="identity")
+
+    def ev(st):
+        x = np.concatenate([orc.bg_as_tensor(st[i:i + 1]) for i in range(len(st))])
+        p, v = net_oracle.forward(tens, x, 19, dtype=torch.float32)
+        return p.astype(np.float32), v.astype(np.float32)
+    cb = orc.make_eval(ev)
+    n = min(len(h_states), 16)
+    iters = min(args.iterations, 20)  # bounded sample: the per-simulation cost does not depend on the iteration count
+    cfg = orc.mcts_cfg(iters, 2.0, args.round_limit, 0.3, 0.25, 0)
+    t0 = time.perf_counter()
+    orc.alpha_mcts_parallel(h_states[:n], np.arange(n), cfg, SEED, 0, cb, 1 + (iters + 1) * 128)
+    dt = time.perf_counter() - t0
+    return n * iters / dt, f"{n} of the {len(h_states)} games x {iters} of the {args.iterations} iterations, {dt:.1f} s", dt
 
 
 def cpu_leg(args, h_states, seconds_target, threads, ffi_cfg_mode):
@@ -296,6 +419,8 @@ def cpu_leg(args, h_states, seconds_target, threads, ffi_cfg_mode):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import orc
     orc.build()
+    if args.workload in ("alpha", "selfplay"):
+        return cpu_alpha_leg(args, h_states, threads)
     if args.workload == "mcts":
         cfg = orc.mcts_cfg(args.iterations, 2.0, args.round_limit, 0.3, 0.25, ffi_cfg_mode)
         # calibrate on a few games, then size the sample for ~seconds_target
@@ -331,7 +456,7 @@ def host_states_for_reference(args):
     for g in range(G):
         w = orc.philox(SEED, 0, g, orc.STREAM_INIT, 0)
         s["roll"][g] = (orc.die(w[0]), orc.die(w[1]))
-    if args.workload == "mcts":
+    if args.workload in ("mcts", "alpha", "selfplay"):
         n = min(G, 512)  # the bounded sample never needs more
         s = s[:n]
         for g in range(n):
@@ -348,7 +473,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mcts", choices=["mcts", "playout"])
+    ap.add_argument("--workload", default="mcts", choices=["mcts", "playout", "alpha", "selfplay"])
     ap.add_argument("--games", type=int, default=None)
     ap.add_argument("--iterations", type=int, default=100)
     ap.add_argument("--round-limit", type=int, default=400)
@@ -357,7 +482,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.games is None:
-        args.games = 1024 if args.workload == "mcts" else 65536
+        args.games = 65536 if args.workload == "playout" else 1024
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     threads = os.cpu_count() or 1
@@ -377,9 +502,10 @@ def main():
         tot_units = sum(v * dt for v, dt in vals)
         tot_s = sum(dt for _, dt in vals)
         value = tot_units / tot_s
-        unit = "simulations/s" if args.workload == "mcts" else "plies/s"
+        unit = {"mcts": "simulations/s", "alpha": "simulations/s", "selfplay": "simulations/s", "playout": "plies/s"}[args.workload]
         line = {
-            "impl": "reference", "metric": "mcts_simulations_per_sec" if args.workload == "mcts" else "playout_plies_per_sec",
+            "impl": "reference", "metric": {"mcts": "mcts_simulations_per_sec", "alpha": "alphazero_simulations_per_sec",
+                                            "selfplay": "alphazero_simulations_per_sec", "playout": "playout_plies_per_sec"}[args.workload],
             "value": round(value, 1), "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * tot_s / max(1, args.steps), 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8 boards / f32 UCB", "data": "synthetic",
@@ -400,7 +526,11 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             v, sample, _ = cpu_leg(args, h_states, args.cpu_seconds, threads, mode)
-            out["cpu_baseline"] = {"value": round(v, 1), "unit": out["unit"], "cores": threads, "kind": "port", "sample": sample}
+            if args.workload == "selfplay":  # games/s extrapolated from the measured simulations/s
+                sims_per_game = args.iterations * out["config"]["waves_per_step"]
+                sample += f"; {v:.1f} simulations/s extrapolated to games/s with {sims_per_game} simulations per game-slot"
+                v = v / sims_per_game
+            out["cpu_baseline"] = {"value": round(v, 4), "unit": out["unit"], "cores": threads, "kind": "port", "sample": sample}
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out), flush=True)

@@ -9,6 +9,9 @@ from ._ffi import Context, DieeError, default_context
 from .backgammon import Backgammon
 from .tictactoe import TicTacToe
 from .mcts import MctsConfig, mct_search, mct_search_batch
+from .nnet import ResNet
+from .alphazero import AlphaZero, AlphaZeroConfig, MemoryFragment, alpha_mcts_parallel, memory_to_arrays
 
 __all__ = ["Context", "DieeError", "default_context", "Backgammon", "TicTacToe", "MctsConfig", "mct_search",
-           "mct_search_batch", "_ffi"]
+           "mct_search_batch", "ResNet", "AlphaZero", "AlphaZeroConfig", "MemoryFragment", "alpha_mcts_parallel",
+           "memory_to_arrays", "_ffi"]

@@ -44,7 +44,7 @@ SYMBOLS = [
     "diee_bg_playout", "diee_bg_playout_dev", "diee_bg_encode_moves", "diee_bg_decode_moves",
     "diee_bg_encode_states", "diee_bg_encode_states_dev", "diee_mcts_search", "diee_mcts_search_dev",
     "diee_net_create", "diee_net_destroy", "diee_net_param_count", "diee_net_forward", "diee_net_forward_dev",
-    "diee_dirichlet", "diee_alpha_search", "diee_selfplay_run", "diee_net_eval_count",
+    "diee_dirichlet", "diee_alpha_search", "diee_alpha_search_dev", "diee_selfplay_run", "diee_net_eval_count",
 ]
 
 
@@ -239,6 +239,13 @@ class Context:
         if dump:
             return ids, moves, visits, counts, status, nodes, n_nodes
         return ids, moves, visits, counts, status
+
+    def alpha_search_dev(self, net, d_states, n, d_ids, cfg, seed, epoch, max_nodes, d_root_ids, d_root_moves, d_root_visits,
+                         d_root_counts, d_status):
+        cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]
+        self._chk(lib().diee_alpha_search_dev(self._h, net._h, _p(d_states), C.c_int32(n), _p(d_ids), _p(cfg), C.c_uint64(seed),
+                                              C.c_uint32(epoch), C.c_int32(max_nodes), _p(d_root_ids), _p(d_root_moves),
+                                              _p(d_root_visits), _p(d_root_counts), _p(d_status)))
 
     def selfplay_run(self, net, n_games, cfg, temperature, seed, first_game_id=0, max_nodes=0, rec_cap=None, pi_cap=None):
         cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]

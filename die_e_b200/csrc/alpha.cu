@@ -189,6 +189,26 @@ int32_t diee_alpha_search(diee_ctx *ctx, diee_net *net, const diee_bg_state *sta
     return DIEE_OK;
 }
 
+// device-resident form: all pointers are device pointers, results are valid after diee_sync()
+int32_t diee_alpha_search_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, const uint32_t *game_ids,
+                              const diee_mcts_cfg *cfg, uint64_t seed, uint32_t epoch, int32_t max_nodes, uint16_t *root_ids_out,
+                              diee_move *root_moves_out, float *root_visits_out, int32_t *root_counts_out, int32_t *status_out) {
+    int32_t rc = check_alpha_args(ctx, net, n, cfg, epoch);
+    if (rc != DIEE_OK) return rc;
+    if (n == 0) return DIEE_OK;
+    if (!states || !game_ids || !root_ids_out || !root_moves_out || !root_visits_out || !root_counts_out || !status_out)
+        return fail(ctx, DIEE_ERR_INVALID, "alpha_search_dev: bad argument");
+    if (max_nodes <= 0) max_nodes = default_max_nodes(cfg);
+    CU(cudaSetDevice(ctx->device));
+    AlphaPool P;
+    rc = alpha_search_device(ctx, net, states, n, game_ids, cfg, seed, epoch, max_nodes, P);
+    if (rc != DIEE_OK) return rc;
+    CU(launch_alpha_root_out(ctx->stream, P, n, root_ids_out, (uint32_t *)root_moves_out, root_visits_out, root_counts_out));
+    CU(cudaMemcpyAsync(status_out, ctx->a_status.p, 4 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->launches += 1;
+    return DIEE_OK;
+}
+
 uint64_t diee_net_eval_count(const diee_ctx *ctx) { return ctx ? ctx->net_evals : 0; }
 
 // self_play_parallel (alpha_parallel.rs:101-231).  Live games stay resident on the device between

@@ -256,6 +256,9 @@ int32_t diee_alpha_search(diee_ctx *ctx, diee_net *net, const diee_bg_state *sta
                           const diee_mcts_cfg *cfg, uint64_t seed, uint32_t epoch, int32_t max_nodes, uint16_t *root_ids_out,
                           diee_move *root_moves_out, float *root_visits_out, int32_t *root_counts_out, int32_t *status_out,
                           diee_anode *nodes_out, int32_t *n_nodes_out);
+int32_t diee_alpha_search_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, const uint32_t *game_ids,
+                              const diee_mcts_cfg *cfg, uint64_t seed, uint32_t epoch, int32_t max_nodes, uint16_t *root_ids_out,
+                              diee_move *root_moves_out, float *root_visits_out, int32_t *root_counts_out, int32_t *status_out);
 /* self_play_parallel (alphazero/alpha_parallel.rs:101-231): n_games games from the opening position in
  * lock-step until every game has a winner or hit cfg->simulate_round_limit; records are appended in the
  * reference's emission order (quirk Q10 included).  Game i has id first_game_id + i. */

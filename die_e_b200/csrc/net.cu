@@ -53,6 +53,18 @@ static bool make_w_map(CUtensorMap *m, const void *base, int c_out, int K, int b
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// generic K-major bf16 matrix [rows][K]; box = [64 k][box_rows]
+static bool make_kmajor_map(CUtensorMap *m, const void *base, long long rows, int K, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct ConvLayer {
     __nv_bfloat16 *w = nullptr;  // [c_out_pad][K]
     float *bias = nullptr;       // [c_out_pad]
@@ -64,7 +76,9 @@ struct diee_net {
     int filters = 0, blocks = 0;
     std::vector<ConvLayer> convs;  // init, then conv1/conv2 per block
     ConvLayer pconv, vconv;
-    float *wpt = nullptr, *bp = nullptr, *wv = nullptr;
+    __nv_bfloat16 *wp = nullptr;  // policy Linear weight [1408][768] bf16, K index = pos*32 + c
+    CUtensorMap wp_map;
+    float *bp = nullptr, *wv = nullptr;
     float bv = 0.f;
     // activation scratch (grown on demand)
     DevBuf in0, actA, actB, actC, pfeat, vfeat, s_states, s_policy, s_value;
@@ -175,13 +189,14 @@ int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *t,
     rc = build_conv(ctx, net->pconv, t[idx], t[idx + 1], t[idx + 2], t[idx + 3], t[idx + 4], t[idx + 5], 32, F, 32, 0, 32);
     if (rc != DIEE_OK) return rc;
     {   // policy Linear(768 -> 1352): torch flattens NCHW (feature = c*24 + pos); ours is NHWC (pos*32 + c)
-        std::vector<float> wpt((size_t)768 * DIEE_ACTION_SPACE);
+        std::vector<__nv_bfloat16> wp((size_t)1408 * 768, __float2bfloat16(0.f));
         const float *W = t[idx + 6];
         for (int j = 0; j < DIEE_ACTION_SPACE; ++j)
             for (int c = 0; c < 32; ++c)
-                for (int pos = 0; pos < 24; ++pos) wpt[(size_t)(pos * 32 + c) * DIEE_ACTION_SPACE + j] = W[(size_t)j * 768 + c * 24 + pos];
-        CU(cudaMalloc(&net->wpt, wpt.size() * sizeof(float)));
-        CU(cudaMemcpy(net->wpt, wpt.data(), wpt.size() * sizeof(float), cudaMemcpyHostToDevice));
+                for (int pos = 0; pos < 24; ++pos) wp[(size_t)j * 768 + pos * 32 + c] = __float2bfloat16(W[(size_t)j * 768 + c * 24 + pos]);
+        CU(cudaMalloc(&net->wp, wp.size() * sizeof(__nv_bfloat16)));
+        CU(cudaMemcpy(net->wp, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+        if (!make_kmajor_map(&net->wp_map, net->wp, 1408, 768, 128)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (policy linear) failed");
         CU(cudaMalloc(&net->bp, DIEE_ACTION_SPACE * sizeof(float)));
         CU(cudaMemcpy(net->bp, t[idx + 7], DIEE_ACTION_SPACE * sizeof(float), cudaMemcpyHostToDevice));
     }
@@ -206,7 +221,7 @@ int32_t diee_net_destroy(diee_ctx *ctx, diee_net *net) {
     cudaStreamSynchronize(ctx->stream);
     for (ConvLayer &L : net->convs) { cudaFree(L.w); cudaFree(L.bias); }
     cudaFree(net->pconv.w); cudaFree(net->pconv.bias); cudaFree(net->vconv.w); cudaFree(net->vconv.bias);
-    cudaFree(net->wpt); cudaFree(net->bp); cudaFree(net->wv);
+    cudaFree(net->wp); cudaFree(net->bp); cudaFree(net->wv);
     DevBuf *bufs[] = {&net->in0, &net->actA, &net->actB, &net->actC, &net->pfeat, &net->vfeat, &net->s_states, &net->s_policy, &net->s_value};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -226,7 +241,7 @@ int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *
     RESERVE(net->actA, rows * F * 2);
     RESERVE(net->actB, rows * F * 2);
     RESERVE(net->actC, rows * F * 2);
-    RESERVE(net->pfeat, rows * 32 * 4);
+    RESERVE(net->pfeat, rows * 32 * 2);
     RESERVE(net->vfeat, rows * 16 * 4);
     CUtensorMap m_in, mA, mB, mC;
     if (!make_act_map(&m_in, net->in0.p, n, 64) || !make_act_map(&mA, net->actA.p, n, F) || !make_act_map(&mB, net->actB.p, n, F) ||
@@ -248,10 +263,12 @@ int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *
         void *tp = bx; bx = bz; bz = tp;
         CUtensorMap *tm = mx; mx = mz; mz = tm;
     }
-    CU(launch_conv(st, net->pconv.bn, *mx, net->pconv.wmap, n, 9, net->pconv.chunks, net->pconv.bias, nullptr, net->pfeat.p, 1, 32, 1));
+    CU(launch_conv(st, net->pconv.bn, *mx, net->pconv.wmap, n, 9, net->pconv.chunks, net->pconv.bias, nullptr, net->pfeat.p, 0, 32, 1));
     CU(launch_conv(st, net->vconv.bn, *mx, net->vconv.wmap, n, 9, net->vconv.chunks, net->vconv.bias, nullptr, net->vfeat.p, 1, 16, 1));
-    CU(launch_heads_fc(st, (const float *)net->pfeat.p, (const float *)net->vfeat.p, net->wpt, net->bp, net->wv, net->bv, n, policy_out, value_out));
-    ctx->launches += 3;
+    CUtensorMap m_pf;
+    if (!make_kmajor_map(&m_pf, net->pfeat.p, n, 768, 128)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (policy features) failed");
+    CU(launch_heads(st, m_pf, net->wp_map, net->bp, (const float *)net->vfeat.p, net->wv, net->bv, n, policy_out, value_out));
+    ctx->launches += 4;
     return DIEE_OK;
 }
 

@@ -322,56 +322,134 @@ __global__ void encode_im2col_kernel(const diee_bg_state *__restrict__ states, i
     }
 }
 
-// ---------------------------------------------------------------- heads: Linear + softmax / Linear + tanh
-// pfeat: fp32 [n*24][32] (policy conv, ReLU'd); wpt: fp32 [768][1352] with feature index pos*32+c;
-// vfeat: fp32 [n*24][16] (3 used); wv: fp32 [24*16].  nnet.rs:75-98, :127.
-constexpr int FC_BOARDS = 8;
-__global__ void __launch_bounds__(256)
-heads_fc_kernel(const float *__restrict__ pfeat, const float *__restrict__ vfeat, const float *__restrict__ wpt,
-                const float *__restrict__ bp, const float *__restrict__ wv, float bv, int n, float *__restrict__ policy_out,
-                float *__restrict__ value_out) {
-    __shared__ float feat[FC_BOARDS][768];
-    const int b0 = blockIdx.x * FC_BOARDS;
-    const int nb = min(FC_BOARDS, n - b0);
-    for (int i = threadIdx.x; i < FC_BOARDS * 768; i += 256) {
-        const int b = i / 768, f = i - b * 768;
-        feat[b][f] = b < nb ? pfeat[(size_t)(b0 + b) * 768 + f] : 0.f;
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < DIEE_ACTION_SPACE; j += 256) {
-        float acc[FC_BOARDS];
-#pragma unroll
-        for (int b = 0; b < FC_BOARDS; ++b) acc[b] = bp[j];
-        for (int f = 0; f < 768; ++f) {
-            const float w = wpt[(size_t)f * DIEE_ACTION_SPACE + j];
-#pragma unroll
-            for (int b = 0; b < FC_BOARDS; ++b) acc[b] = fmaf(w, feat[b][f], acc[b]);
-        }
-#pragma unroll
-        for (int b = 0; b < FC_BOARDS; ++b)
-            if (b < nb) policy_out[(size_t)(b0 + b) * DIEE_ACTION_SPACE + j] = acc[b];
-    }
-    __threadfence_block();
-    __syncthreads();
-    // softmax(1) per board: one warp per board
+// ---------------------------------------------------------------- heads
+// Policy Linear(768 -> 1352) (nnet.rs:79-84) as one more tcgen05 GEMM: A = bf16 policy-conv features
+// [board][768] (K index = pos*32 + c, the NHWC order the conv epilogue writes), B = the Linear weight
+// re-ordered to that K order and zero-padded to 1408 rows, both K-major in the 128B swizzle.
+// One CTA = 128 boards x 128 logits, 12 K-blocks of 64; fp32 logits + bias go straight to policy_out.
+constexpr int FC_STAGES = 4;
+constexpr int FC_STAGE_BYTES = 2 * 128 * 128;
+constexpr int FC_SMEM_BYTES = FC_STAGES * FC_STAGE_BYTES + 1024 + 256 + 128 * 4;
+constexpr int FC_N_PAD = 1408;  // 11 tiles of 128 >= 1352
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+fc_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int n_boards,
+             const float *__restrict__ bias, float *__restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *tail = smem + FC_STAGES * FC_STAGE_BYTES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(tail);
+    uint64_t *empty_bar = full_bar + FC_STAGES;
+    uint64_t *tmem_full_bar = empty_bar + FC_STAGES;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+    float *bias_smem = reinterpret_cast<float *>(tail + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp < nb) {
-        float *row = policy_out + (size_t)(b0 + warp) * DIEE_ACTION_SPACE;
-        float mx = -INFINITY;
-        for (int j = lane; j < DIEE_ACTION_SPACE; j += 32) mx = fmaxf(mx, row[j]);
-        for (int d = 16; d; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
-        float sum = 0.f;
-        for (int j = lane; j < DIEE_ACTION_SPACE; j += 32) { const float e = expf(row[j] - mx); row[j] = e; sum += e; }
-        for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
-        const float inv = 1.f / sum;
-        for (int j = lane; j < DIEE_ACTION_SPACE; j += 32) row[j] *= inv;
-        // value head
-        float acc = 0.f;
-        const float *vf = vfeat + (size_t)(b0 + warp) * 24 * 16;
-        for (int f = lane; f < 24 * 16; f += 32) acc = fmaf(wv[f], vf[f], acc);
-        for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
-        if (lane == 0) value_out[b0 + warp] = tanhf(acc + bv);
+    const int board0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+    constexpr int num_kb = 768 / 64;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmapA);
+        prefetch_tmap(&tmapB);
+        for (int s = 0; s < FC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
     }
+    if (warp == 1) tmem_alloc(tmem_ptr_smem, 128);
+    for (int i = threadIdx.x; i < 128; i += CONV_THREADS) bias_smem[i] = (n0 + i) < DIEE_ACTION_SPACE ? bias[n0 + i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % FC_STAGES;
+                mbar_wait(&empty_bar[s], ((uint32_t)(kb / FC_STAGES) & 1u) ^ 1u);
+                uint8_t *sa = smem + s * FC_STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], (uint32_t)FC_STAGE_BYTES);
+                tma_load_2d(sa, &tmapA, &full_bar[s], kb * 64, board0);
+                tma_load_2d(sa + 128 * 128, &tmapB, &full_bar[s], kb * 64, n0);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % FC_STAGES;
+            mbar_wait(&full_bar[s], (uint32_t)(kb / FC_STAGES) & 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + s * FC_STAGE_BYTES), sb = sa + 128 * 128;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem_base, umma_desc_sw128(sa + kk * 32), umma_desc_sw128(sb + kk * 32), idesc, (kb | kk) != 0 ? 1u : 0u);
+                umma_commit(&empty_bar[s]);
+                if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int row = board0 + q * 32 + lane;
+        const bool valid = row < n_boards;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (valid) {
+                float4 *op = reinterpret_cast<float4 *>(out + (size_t)row * DIEE_ACTION_SPACE + n0 + c0);
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4)
+                    if (n0 + c0 + g4 * 4 + 3 < DIEE_ACTION_SPACE)
+                        op[g4] = make_float4(__uint_as_float(v[g4 * 4]) + bias_smem[c0 + g4 * 4],
+                                             __uint_as_float(v[g4 * 4 + 1]) + bias_smem[c0 + g4 * 4 + 1],
+                                             __uint_as_float(v[g4 * 4 + 2]) + bias_smem[c0 + g4 * 4 + 2],
+                                             __uint_as_float(v[g4 * 4 + 3]) + bias_smem[c0 + g4 * 4 + 3]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 128);
+    }
+}
+
+// softmax(1) over the 1352 logits in place (nnet.rs:127) and the value head Linear(72 -> 1) + tanh
+// (nnet.rs:87-98): one warp per board.  vfeat: fp32 [n*24][16] (3 channels used); wv: fp32 [24*16].
+__global__ void __launch_bounds__(256)
+softmax_value_kernel(const float *__restrict__ vfeat, const float *__restrict__ wv, float bv, int n, float *__restrict__ policy,
+                     float *__restrict__ value_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= n) return;
+    float *row = policy + (size_t)b * DIEE_ACTION_SPACE;
+    float x[43];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 43; ++i) {
+        const int j = lane + 32 * i;
+        x[i] = j < DIEE_ACTION_SPACE ? row[j] : -INFINITY;
+        mx = fmaxf(mx, x[i]);
+    }
+    for (int d = 16; d; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 43; ++i) { x[i] = expf(x[i] - mx); sum += x[i]; }
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int i = 0; i < 43; ++i) {
+        const int j = lane + 32 * i;
+        if (j < DIEE_ACTION_SPACE) row[j] = x[i] * inv;
+    }
+    float acc = 0.f;
+    const float *vf = vfeat + (size_t)b * 24 * 16;
+    for (int f = lane; f < 24 * 16; f += 32) acc = fmaf(wv[f], vf[f], acc);
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    if (lane == 0) value_out[b] = tanhf(acc + bv);
 }
 
 // ---------------------------------------------------------------- launchers
@@ -411,10 +489,20 @@ cudaError_t launch_encode_im2col(cudaStream_t st, const diee_bg_state *states, i
     return cudaGetLastError();
 }
 
-cudaError_t launch_heads_fc(cudaStream_t st, const float *pfeat, const float *vfeat, const float *wpt, const float *bp,
-                            const float *wv, float bv, int n, float *policy_out, float *value_out) {
+cudaError_t launch_heads(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, const float *bp, const float *vfeat,
+                         const float *wv, float bv, int n, float *policy_out, float *value_out) {
     if (n <= 0) return cudaSuccess;
-    heads_fc_kernel<<<(n + FC_BOARDS - 1) / FC_BOARDS, 256, 0, st>>>(pfeat, vfeat, wpt, bp, wv, bv, n, policy_out, value_out);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(fc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((n + 127) / 128, FC_N_PAD / 128);
+    fc_tc_kernel<<<grid, CONV_THREADS, FC_SMEM_BYTES, st>>>(ta, tb, n, bp, policy_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    softmax_value_kernel<<<(n + 7) / 8, 256, 0, st>>>(vfeat, wv, bv, n, policy_out, value_out);
     return cudaGetLastError();
 }
 

@@ -10,6 +10,6 @@ namespace diee {
 cudaError_t launch_conv(cudaStream_t st, int bn, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps, int chunks,
                         const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu);
 cudaError_t launch_encode_im2col(cudaStream_t st, const diee_bg_state *states, int n, void *out);
-cudaError_t launch_heads_fc(cudaStream_t st, const float *pfeat, const float *vfeat, const float *wpt, const float *bp,
-                            const float *wv, float bv, int n, float *policy_out, float *value_out);
+cudaError_t launch_heads(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, const float *bp, const float *vfeat,
+                         const float *wv, float bv, int n, float *policy_out, float *value_out);
 }  // namespace diee

@@ -74,8 +74,8 @@ def forward_bf16_emulated(tensors, x, blocks):
         y = _bf16(F.relu(F.conv2d(x, _bf16(w1), bb1.float().double(), padding=1)))
         x = _bf16(F.relu(F.conv2d(y, _bf16(w2), bb2.float().double(), padding=1) + x))
     wp, bp = _fold(pol[0], pol[1])
-    p = F.relu(F.conv2d(x, _bf16(wp), bp.float().double(), padding=1)).float().double().flatten(1)
-    p = F.softmax(F.linear(p, pol[2][0].float().double(), pol[2][1].float().double()), dim=1)
+    p = _bf16(F.relu(F.conv2d(x, _bf16(wp), bp.float().double(), padding=1))).flatten(1)
+    p = F.softmax(F.linear(p, _bf16(pol[2][0]), pol[2][1].float().double()), dim=1)
     wv, bv = _fold(val[0], val[1])
     v = F.relu(F.conv2d(x, _bf16(wv), bv.float().double(), padding=1)).float().double().flatten(1)
     v = torch.tanh(F.linear(v, val[2][0].float().double(), val[2][1].float().double())).reshape(-1)

@@ -168,6 +168,8 @@ int32_t diee_bg_playout_dev(diee_ctx *ctx, const diee_bg_state *starts, int32_t 
                             int32_t *plies_out, diee_bg_state *finals_out) {
     if (!ctx || n < 0 || round_limit < 0 || (n && (!starts || !winners_out || !plies_out)))
         return fail(ctx, DIEE_ERR_INVALID, "bg_playout: bad argument");
+    if (((uintptr_t)starts | (uintptr_t)finals_out) & 15u)  // states move as two 16-byte vectors per lane
+        return fail(ctx, DIEE_ERR_INVALID, "bg_playout: device state arrays must be 16-byte aligned");
     CU(cudaSetDevice(ctx->device));
     CU(launch_bg_playout(ctx->stream, starts, n, seed, first_game_id, round_limit, winners_out, plies_out, finals_out));
     ctx->launches += n > 0;

@@ -46,44 +46,7 @@ bg_apply_kernel(diee_bg_state *__restrict__ states, const diee_move *__restrict_
     bg_store(g, states + gidx, lane);
 }
 
-// C2: whole random-vs-random games fused in one launch.  HBM traffic: 32 B in, 32+1+4 B out per
-// game; everything in between lives in registers and the warp's shared-memory slab.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-bg_playout_kernel(const diee_bg_state *__restrict__ starts, int n, uint64_t seed, uint32_t first_game_id,
-                  int round_limit, int8_t *__restrict__ winners_out, int32_t *__restrict__ plies_out,
-                  diee_bg_state *__restrict__ finals_out) {
-    __shared__ WarpSlab slabs[WARPS_PER_CTA];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int gidx = blockIdx.x * WARPS_PER_CTA + wib;
-    if (gidx >= n) return;
-    WarpSlab &slab = slabs[wib];
-    BgWarp g;
-    bg_load(g, starts + gidx, lane);
-    const uint32_t gid = first_game_id + (uint32_t)gidx;
-    PhiloxLanes rng;
-    int ply = 0;
-    int w = bg_winner(g);
-    bool overflow = false;
-    while (w == 0 && ply < round_limit) {
-        if ((ply & 31) == 0) rng.fill(seed, (uint32_t)ply, gid, DIEE_STREAM_GAME, 0u, lane);
-        const int src = ply & 31;
-        const int d0 = die_of(__shfl_sync(FULL, rng.w0, src));
-        const int d1 = die_of(__shfl_sync(FULL, rng.w1, src));
-        const uint32_t w2 = __shfl_sync(FULL, rng.w2, src);
-        const int U = bg_movegen(g, slab, lane, overflow);
-        uint32_t seq = SEQ_EMPTY;
-        if (U > 0) seq = slab.raw[index_of(w2, (uint32_t)U)];
-        __syncwarp();
-        bg_step(g, seq, d0, d1, lane);
-        ++ply;
-        w = bg_winner(g);
-    }
-    if (lane == 0) {
-        winners_out[gidx] = overflow ? (int8_t)DIEE_ERR_OVERFLOW : (int8_t)w;
-        plies_out[gidx] = ply;
-    }
-    if (finals_out) bg_store(g, finals_out + gidx, lane);
-}
+// C2 (whole random-vs-random games) lives in lane_kernels.cu: one lane per game.
 
 // encode / decode one play per state: one thread per state
 __global__ void bg_encode_moves_kernel(const diee_bg_state *__restrict__ states, const diee_move *__restrict__ moves,
@@ -133,13 +96,6 @@ cudaError_t launch_bg_valid_moves(cudaStream_t st, const diee_bg_state *states, 
 cudaError_t launch_bg_apply(cudaStream_t st, diee_bg_state *states, const diee_move *moves, const uint8_t *next_rolls, int n) {
     if (n <= 0) return cudaSuccess;
     bg_apply_kernel<<<warp_grid(n), WARPS_PER_CTA * 32, 0, st>>>(states, moves, next_rolls, n);
-    return cudaGetLastError();
-}
-cudaError_t launch_bg_playout(cudaStream_t st, const diee_bg_state *starts, int n, uint64_t seed, uint32_t first_game_id,
-                              int round_limit, int8_t *winners_out, int32_t *plies_out, diee_bg_state *finals_out) {
-    if (n <= 0) return cudaSuccess;
-    bg_playout_kernel<<<warp_grid(n), WARPS_PER_CTA * 32, 0, st>>>(starts, n, seed, first_game_id, round_limit,
-                                                                    winners_out, plies_out, finals_out);
     return cudaGetLastError();
 }
 cudaError_t launch_bg_encode_moves(cudaStream_t st, const diee_bg_state *states, const diee_move *moves, int n, uint16_t *ids_out) {

@@ -1,0 +1,463 @@
+// bg_lane.cuh -- lane-per-game backgammon engine for the rollout / playout kernels (sm_100a).
+//
+// bg_device.cuh gives one WARP to a game (needed where one game must finish fast: the tree
+// kernel).  Rollouts are the opposite regime: games x iterations independent plies streams, each
+// strictly sequential, so the throughput form is one LANE per game with the whole board in
+// registers as bit planes and no cross-lane traffic at all.
+//
+// What is computed (reference: alibasaran/die-e src/backgammon/backgammon_logic.rs): the same
+// get_valid_moves :403-414 as bg_device.cuh -- candidates per die (:555-617, :662-682) sorted by
+// (die, from, to) (:619-620), recursion with the used die removed (:705-720), DFS flatten
+// (:722-750), first-wins dedup by resulting board (:753-774) -- but a rollout only needs the
+// NUMBER of distinct plays U and the k-th of them (node.rs:186-190), so the list is never built:
+//
+//   * the board is kept mover-relative ("canonical": the side to move runs toward bit 0, its home
+//     board is bits 0..5, it enters from the bar on 24 - die) as 4 + 4 bit planes of the per-point
+//     checker counts, so own>=1 / own==1 / opponent>=2 / opponent==1 are two or three logic ops and
+//     a turn change is a bit reversal of the planes;
+//   * roots are visited in the reference's order (die ascending, then `from` ascending in REAL
+//     coordinates = descending canonical bits for player +1); each root's children come from one
+//     shift-and-mask (plus the bear-off scan when the side can bear off within this play);
+//   * two plays give the same board iff their canonical (removals, arrivals) are equal.  A play is
+//     (point moved by the low die, point moved by the high die); distinct pairs give distinct
+//     boards except (a) the same checker moving on through a point it did not hit / another checker
+//     refilling the vacated point -- both collapse to one net move F -> a, deduplicated in four
+//     25-bit register masks indexed by F -- and (b) both sub-moves bearing off with the dice swapped.
+//     Outside the bear-off regime this makes "is this child new?" a closed-form mask per root;
+//     inside it the children are tested one by one against a per-lane bit matrix;
+//   * per root the mask of NEW children is parked in per-lane scratch (shared memory, lane-strided,
+//     conflict-free); after U is known the k-th play is found by a popcount walk over that scratch.
+//
+// The file compiles for the host too (tests/lane_harness.cpp checks it exhaustively against the
+// CPU oracle without a GPU); on the device everything is inlined into the kernels of lane_kernels.cu.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/diee.h"
+
+#if defined(__CUDACC__)
+#define LANE_HD __host__ __device__ __forceinline__
+#else
+#define LANE_HD static inline
+#endif
+
+namespace diee {
+namespace lane {
+
+constexpr uint32_t L_M24 = 0x00FFFFFFu;
+constexpr int L_BAR = 24;  // source index of a bar entry
+constexpr int L_OFF = 25;  // arrival index of a collected checker
+constexpr int L_SLOTS = 32;               // root slots: 2 die orders x (<= 15 occupied points | the bar)
+constexpr int L_ROWS = 25;                // pair matrix rows (bear-off regime only)
+constexpr int L_SCRATCH = L_SLOTS + L_ROWS;  // u32 words of scratch per lane
+constexpr uint32_t L_SINGLE = 0x80000000u;   // new-mask flag: the root itself is a (new) one-move play
+
+LANE_HD int l_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+LANE_HD int l_low(uint32_t x) {  // index of the lowest set bit, x != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+LANE_HD int l_high(uint32_t x) {  // index of the highest set bit, x != 0
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
+LANE_HD uint32_t l_rev24(uint32_t x) {  // mirror the 24 points
+#if defined(__CUDA_ARCH__)
+    return __brev(x) >> 8;
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 24; ++i) r |= ((x >> i) & 1u) << (23 - i);
+    return r;
+#endif
+}
+
+// ---------------- Philox4x32-10 (same stream contract as include/diee.h) ----------------
+LANE_HD void l_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+LANE_HD int l_die(uint32_t w) { return 1 + (int)(((uint64_t)w * 6u) >> 32); }
+LANE_HD uint32_t l_index(uint32_t w, uint32_t n) { return (uint32_t)(((uint64_t)w * n) >> 32); }
+
+// ---------------- the board of one game, in one lane's registers ----------------
+struct LaneBoard {
+    uint32_t own[4], opp[4];  // bit planes of the per-point counts, mover-relative
+    int bar_own, bar_opp, off_own, off_opp;
+    int roll0, roll1, player, second;
+};
+
+LANE_HD void l_inc(uint32_t p[4], uint32_t bit) {  // count at `bit` += 1 (ripple carry through the planes)
+    uint32_t c = bit, t;
+    t = p[0] & c; p[0] ^= c; c = t;
+    t = p[1] & c; p[1] ^= c; c = t;
+    t = p[2] & c; p[2] ^= c; c = t;
+    p[3] ^= c;
+}
+LANE_HD void l_dec(uint32_t p[4], uint32_t bit) {  // count at `bit` -= 1 (ripple borrow)
+    uint32_t c = bit, t;
+    t = ~p[0] & c; p[0] ^= c; c = t;
+    t = ~p[1] & c; p[1] ^= c; c = t;
+    t = ~p[2] & c; p[2] ^= c; c = t;
+    p[3] ^= c;
+}
+
+// packed 32-byte state (real coordinates) -> planes.  w[8] = the state as eight little-endian words.
+LANE_HD void l_load(LaneBoard &g, const uint32_t w[8]) {
+    uint32_t neg[4] = {0, 0, 0, 0}, pos[4] = {0, 0, 0, 0};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 24; ++i) {
+        const int v = (int)(signed char)(w[i >> 2] >> (8 * (i & 3)));
+        const uint32_t a = (uint32_t)(v < 0 ? -v : v);
+        const uint32_t nm = v < 0 ? 1u : 0u, pm = v > 0 ? 1u : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; ++k) {
+            neg[k] |= (((a >> k) & 1u) & nm) << i;
+            pos[k] |= (((a >> k) & 1u) & pm) << i;
+        }
+    }
+    const int bar0 = (int)(w[6] & 0xFF), bar1 = (int)((w[6] >> 8) & 0xFF);
+    const int off0 = (int)((w[6] >> 16) & 0xFF), off1 = (int)((w[6] >> 24) & 0xFF);
+    g.roll0 = (int)(w[7] & 0xFF);
+    g.roll1 = (int)((w[7] >> 8) & 0xFF);
+    g.player = (int)(signed char)(w[7] >> 16);
+    g.second = (int)((w[7] >> 24) & 0xFF);
+    if (g.player < 0) {
+        for (int k = 0; k < 4; ++k) { g.own[k] = neg[k]; g.opp[k] = pos[k]; }
+        g.bar_own = bar0; g.bar_opp = bar1; g.off_own = off0; g.off_opp = off1;
+    } else {
+        for (int k = 0; k < 4; ++k) { g.own[k] = l_rev24(pos[k]); g.opp[k] = l_rev24(neg[k]); }
+        g.bar_own = bar1; g.bar_opp = bar0; g.off_own = off1; g.off_opp = off0;
+    }
+}
+
+LANE_HD void l_store(const LaneBoard &g, uint32_t w[8]) {
+    uint32_t neg[4], pos[4];
+    int bar0, bar1, off0, off1;
+    if (g.player < 0) {
+        for (int k = 0; k < 4; ++k) { neg[k] = g.own[k]; pos[k] = g.opp[k]; }
+        bar0 = g.bar_own; bar1 = g.bar_opp; off0 = g.off_own; off1 = g.off_opp;
+    } else {
+        for (int k = 0; k < 4; ++k) { pos[k] = l_rev24(g.own[k]); neg[k] = l_rev24(g.opp[k]); }
+        bar1 = g.bar_own; bar0 = g.bar_opp; off1 = g.off_own; off0 = g.off_opp;
+    }
+    for (int q = 0; q < 6; ++q) w[q] = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 24; ++i) {
+        int n = 0, p = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; ++k) {
+            n |= (int)((neg[k] >> i) & 1u) << k;
+            p |= (int)((pos[k] >> i) & 1u) << k;
+        }
+        const int v = p - n;
+        w[i >> 2] |= (uint32_t)(v & 0xFF) << (8 * (i & 3));
+    }
+    w[6] = (uint32_t)bar0 | ((uint32_t)bar1 << 8) | ((uint32_t)off0 << 16) | ((uint32_t)off1 << 24);
+    w[7] = (uint32_t)g.roll0 | ((uint32_t)g.roll1 << 8) | ((uint32_t)(g.player & 0xFF) << 16) | ((uint32_t)g.second << 24);
+}
+
+// check_winner  backgammon_logic.rs:527-534  (0 = none): -1 is asked first
+LANE_HD int l_winner(const LaneBoard &g) {
+    const int off_m = g.player < 0 ? g.off_own : g.off_opp;  // player -1's collected
+    const int off_p = g.player < 0 ? g.off_opp : g.off_own;
+    return off_m == 15 ? -1 : (off_p == 15 ? 1 : 0);
+}
+
+// one sub-move of get_next_state :467-517 in canonical coordinates (x: 0..23 | L_BAR, t: 0..23 | L_OFF)
+LANE_HD void l_apply_sub(LaneBoard &g, int x, int t) {
+    if (x == L_BAR) g.bar_own -= 1; else l_dec(g.own, 1u << x);
+    if (t == L_OFF) { g.off_own += 1; return; }
+    const uint32_t tb = 1u << t;
+    if ((g.opp[0] & ~(g.opp[1] | g.opp[2] | g.opp[3])) & tb) {  // a single opposing checker is hit
+        g.opp[0] &= ~tb;
+        g.bar_opp += 1;
+    }
+    l_inc(g.own, tb);
+}
+
+// the turn passes: mirror the board, swap the sides, take the next roll (:182-184, :192-196)
+LANE_HD void l_pass_turn(LaneBoard &g, int d0, int d1) {
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t o = l_rev24(g.own[k]), p = l_rev24(g.opp[k]);
+        g.own[k] = p;
+        g.opp[k] = o;
+    }
+    int t = g.bar_own; g.bar_own = g.bar_opp; g.bar_opp = t;
+    t = g.off_own; g.off_own = g.off_opp; g.off_opp = t;
+    g.player = -g.player;
+    g.second = 0;
+    g.roll0 = d0;
+    g.roll1 = d1;
+}
+
+// a chosen play in canonical coordinates; n = 0 (forced pass), 1 or 2 sub-moves
+struct LanePlay {
+    int n, x1, t1, x2, t2;
+};
+
+// apply_move :176-186 / skip_turn :192-196 with the next roll injected
+LANE_HD void l_step(LaneBoard &g, const LanePlay &pl, int d0, int d1) {
+    if (pl.n > 0) {
+        l_apply_sub(g, pl.x1, pl.t1);
+        if (pl.n > 1) l_apply_sub(g, pl.x2, pl.t2);
+        if (g.roll0 == g.roll1 && !g.second) { g.second = 1; return; }
+    }
+    l_pass_turn(g, d0, d1);
+}
+
+// canonical play -> diee_move bytes (real coordinates)
+LANE_HD uint32_t l_play_to_seq(const LanePlay &pl, int player) {
+    if (pl.n == 0) return 0xFEFEFEFEu;
+    int f[2] = {DIEE_NONE, DIEE_NONE}, t[2] = {DIEE_NONE, DIEE_NONE};
+    const int xs[2] = {pl.x1, pl.x2}, ts[2] = {pl.t1, pl.t2};
+    for (int i = 0; i < pl.n; ++i) {
+        f[i] = xs[i] == L_BAR ? -1 : (player < 0 ? xs[i] : 23 - xs[i]);
+        t[i] = ts[i] == L_OFF ? -1 : (player < 0 ? ts[i] : 23 - ts[i]);
+    }
+    return (uint32_t)(f[0] & 0xFF) | ((uint32_t)(t[0] & 0xFF) << 8) | ((uint32_t)(f[1] & 0xFF) << 16) | ((uint32_t)(t[1] & 0xFF) << 24);
+}
+
+// ---------------- candidate generation for one die (canonical) ----------------
+// own1: points with an own checker; freem: points not held by >= 2 opposing checkers; H: the six
+// home-board counts (own minus opponent, +16 bias, byte h = point h), only read when every own
+// checker is home.  Returns the candidate sources (bit 24 = bar entry).  :544-703
+LANE_HD uint32_t l_cands(int m, uint32_t own1, uint32_t freem, int bar, uint64_t H, bool isplus) {
+    if (bar > 0) return ((freem >> (24 - m)) & 1u) << 24;  // :545-548 -> :668-682
+    uint32_t cand = (freem << m) & own1 & L_M24;             // :600-617
+    if ((own1 & ~0x3Fu) == 0) {                               // is_collectible :638-659 (bar == 0 here)
+        // bit h of cm: own checker on home point h AND the signed sum of the higher home points
+        // shows no own surplus (:571-578 / :588-595; opposing checkers can cancel own ones, quirk Q3)
+        uint32_t cm = 0;
+        int suf = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int h = 5; h >= 0; --h) {
+            const int val = (int)((H >> (8 * h)) & 0xFF) - 16;
+            if (val >= 1 && suf <= 0) cm |= 1u << h;
+            suf += val;
+        }
+        const uint32_t ex = own1 & (1u << (m - 1));          // the exact point (:565-568, :584-587)
+        const int hmax = isplus ? m - 1 : m - 2;             // player +1 scans from the exact point, -1 from below it
+        const uint32_t fb = cm & ((1u << (hmax + 1)) - 1u);
+        const uint32_t fbbit = fb ? (1u << l_high(fb)) : 0u;  // first hit of the downward scan
+        cand |= ex | fbbit;
+    }
+    return cand;
+}
+
+LANE_HD int l_to(int x, int m) { return x == L_BAR ? 24 - m : (x >= m ? x - m : L_OFF); }
+LANE_HD int l_take(uint32_t mask, bool isplus) { return isplus ? l_high(mask) : l_low(mask); }  // next in `from` order
+
+// ---------------- get_valid_moves, counted ----------------
+struct LaneGen {
+    uint32_t R0, R1;  // root sources per die order (order 0 = low die first; R1 = 0 for doubles)
+    int lo, hi;       // the dice, low and high
+    int U;            // number of distinct plays
+    bool isplus;
+};
+
+LANE_HD bool l_test_and_set(uint32_t &m, uint32_t bit) {  // true iff the bit was clear
+    const bool fresh = !(m & bit);
+    m |= bit;
+    return fresh;
+}
+
+// Counts the distinct plays of `g` and parks, per root in reference order, the mask of its NEW
+// children in scr[slot * stride].  scr needs L_SCRATCH words (lane-strided).
+LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stride) {
+    const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;  // :406-409
+    const bool dbl = hi == lo;
+    const bool isplus = g.player > 0;
+    const uint32_t o123 = g.own[1] | g.own[2] | g.own[3], p123 = g.opp[1] | g.opp[2] | g.opp[3];
+    const uint32_t own1 = g.own[0] | o123;
+    const uint32_t own_single = g.own[0] & ~o123;
+    const uint32_t oppblot = g.opp[0] & ~p123;
+    const uint32_t freem = ~p123 & L_M24;
+    const int bar = g.bar_own;
+    gen.isplus = isplus;
+    gen.U = 0;
+    gen.R0 = gen.R1 = 0;
+    gen.lo = lo;
+    gen.hi = hi;
+    if (own1 == 0 && bar == 0) return;  // everything is borne off
+
+    // the side can bear off within this play: bar empty and at most one checker outside the home board
+    const uint32_t outside = own1 & ~0x3Fu;
+    const bool bo_regime = bar == 0 && (outside & (outside - 1u)) == 0 && (outside & ~own_single) == 0;
+    uint64_t H = 0;
+    if (bo_regime) {
+        const uint32_t mag[4] = {g.own[0] | g.opp[0], g.own[1] | g.opp[1], g.own[2] | g.opp[2], g.own[3] | g.opp[3]};
+        const uint32_t oppany = g.opp[0] | p123;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int h = 0; h < 6; ++h) {
+            const int a = (int)(((mag[0] >> h) & 1u) | (((mag[1] >> h) & 1u) << 1) | (((mag[2] >> h) & 1u) << 2) | (((mag[3] >> h) & 1u) << 3));
+            const int val = ((oppany >> h) & 1u) ? -a : a;
+            H |= (uint64_t)(uint32_t)(val + 16) << (8 * h);
+        }
+    }
+
+    uint32_t seen_lo = 0, seen_hi = 0, seen_sum = 0, seen_off = 0;  // net single moves F -> a seen so far: a = F-lo, F-hi, F-lo-hi, OFF
+    uint32_t rowvalid = 0;             // rows of the pair matrix written during this call
+    const uint32_t ownsrc = own1 | (bar > 0 ? 1u << L_BAR : 0u);
+    uint32_t *rows = scr + L_SLOTS * stride;
+    int U = 0, slot = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int b = 0; b < 2; ++b) {
+        if (b == 1 && dbl) break;
+        const int m1 = b == 0 ? lo : hi, m2 = b == 0 ? hi : lo;
+        const uint32_t R = l_cands(m1, own1, freem, bar, H, isplus);
+        if (b == 0) gen.R0 = R; else gen.R1 = R;
+        uint32_t r = R;
+        while (r) {
+            const int x = l_take(r, isplus);
+            r &= ~(1u << x);
+            const bool frombar = x == L_BAR;
+            const int t1 = l_to(x, m1);
+            // the board after the first sub-move, as masks
+            uint32_t own1p = own1;
+            if (!frombar && ((own_single >> x) & 1u)) own1p &= ~(1u << x);
+            bool hit1 = false;
+            if (t1 < 24) { own1p |= 1u << t1; hit1 = (oppblot >> t1) & 1u; }
+            uint64_t Hp = H;
+            if (bo_regime) {
+                if (x < 6) Hp -= 1ull << (8 * x);
+                if (t1 < 6) Hp += (uint64_t)(hit1 ? 2 : 1) << (8 * t1);
+            }
+            const uint32_t C = l_cands(m2, own1p, freem, bar - (frombar ? 1 : 0), Hp, isplus);
+            uint32_t newm = 0;
+            if (C == 0) {  // a one-move play (leaf root): net move x -> t1
+                const uint32_t bit = 1u << x;
+                const bool fresh = t1 == L_OFF ? l_test_and_set(seen_off, bit)
+                                               : (b == 0 ? l_test_and_set(seen_lo, bit) : l_test_and_set(seen_hi, bit));
+                if (fresh) newm = L_SINGLE;
+            } else if (!bo_regime) {
+                // closed form.  The only children that collapse to a net single move x' -> x'-lo-hi:
+                const uint32_t runbit = (t1 < 24 && !hit1) ? ((1u << t1) & C) : 0u;         // the same checker moves on
+                const int ly = x + m2;
+                const uint32_t leapbit = (!frombar && ly < 24) ? ((1u << ly) & C) : 0u;      // a checker refills x
+                if (runbit && l_test_and_set(seen_sum, 1u << x)) newm |= runbit;
+                if (leapbit && l_test_and_set(seen_sum, 1u << ly)) newm |= leapbit;
+                const uint32_t plain = C & ~(runbit | leapbit);
+                uint32_t newp;
+                if (dbl) {
+                    // {x,y} was already produced from root y iff y holds an own checker and comes before x
+                    const uint32_t upto = (2u << x) - 1u;  // bits 0..x
+                    const uint32_t later = isplus ? upto : ~(upto >> 1);
+                    newp = bar > 0 ? plain : (plain & (later | ~own1));
+                } else if (b == 0) {
+                    newp = plain;
+                } else {
+                    // (child by low die, root by high die) was produced in order 0 iff the child's source
+                    // already held an own checker there (with one checker on the bar order 0 starts elsewhere)
+                    newp = bar == 1 ? plain : (plain & ~ownsrc);
+                }
+                newm |= newp;
+            } else {
+                // bear-off regime: test every child's canonical net effect
+                uint32_t c = C;
+                while (c) {
+                    const int y = l_take(c, isplus);
+                    c &= ~(1u << y);
+                    const int t2 = l_to(y, m2);
+                    bool fresh;
+                    if ((t1 == y && t1 < 24 && !hit1) || (x == t2 && x < 24)) {
+                        const int F = (t1 == y && t1 < 24 && !hit1) ? x : y;
+                        const int a = (t1 == y && t1 < 24 && !hit1) ? t2 : t1;
+                        fresh = a == L_OFF ? l_test_and_set(seen_off, 1u << F) : l_test_and_set(seen_sum, 1u << F);
+                    } else {
+                        int xl = b == 0 ? x : y, yh = b == 0 ? y : x;  // (moved by the low die, by the high die)
+                        if (dbl || (t1 == L_OFF && t2 == L_OFF)) {       // the dice are interchangeable
+                            const int mn = xl < yh ? xl : yh, mx = xl < yh ? yh : xl;
+                            xl = mn; yh = mx;
+                        }
+                        uint32_t row = ((rowvalid >> xl) & 1u) ? rows[xl * stride] : 0u;
+                        fresh = !((row >> yh) & 1u);
+                        row |= 1u << yh;
+                        rows[xl * stride] = row;
+                        rowvalid |= 1u << xl;
+                    }
+                    if (fresh) newm |= 1u << y;
+                }
+            }
+            scr[slot * stride] = newm;
+            ++slot;
+            U += l_popc(newm);
+        }
+    }
+    gen.U = U;
+}
+
+// the k-th distinct play (0 <= k < gen.U) in reference order
+LANE_HD LanePlay l_pick(const LaneGen &gen, const uint32_t *scr, int stride, int k) {
+    LanePlay pl;
+    pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
+    int slot = 0, acc = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int b = 0; b < 2; ++b) {
+        uint32_t r = b == 0 ? gen.R0 : gen.R1;
+        const int m1 = b == 0 ? gen.lo : gen.hi, m2 = b == 0 ? gen.hi : gen.lo;
+        while (r) {
+            const int x = l_take(r, gen.isplus);
+            r &= ~(1u << x);
+            const uint32_t newm = scr[slot * stride];
+            ++slot;
+            const int c = l_popc(newm);
+            if (k < acc + c) {
+                pl.x1 = x;
+                pl.t1 = l_to(x, m1);
+                if (newm & L_SINGLE) { pl.n = 1; return pl; }
+                uint32_t mm = newm;
+                for (int j = k - acc; j > 0; --j) mm &= ~(1u << l_take(mm, gen.isplus));
+                pl.n = 2;
+                pl.x2 = l_take(mm, gen.isplus);
+                pl.t2 = l_to(pl.x2, m2);
+                return pl;
+            }
+            acc += c;
+        }
+    }
+    return pl;
+}
+
+}  // namespace lane
+}  // namespace diee

@@ -12,6 +12,8 @@
 // IEEE f32 with explicit round-to-nearest intrinsics (no FMA contraction, no fast division) and
 // ln(parent visits) comes from a host-built table of (float)log((double)n): visits are
 // integer-valued, so this is bit-identical to the oracle.
+#include <type_traits>
+
 #include "bg_device.cuh"
 #include "launchers.h"
 
@@ -319,17 +321,23 @@ static inline int mcts_grid(int n) { return (n + MCTS_WARPS_PER_CTA - 1) / MCTS_
 
 template <class G>
 static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const int8_t *players, const diee_mcts_cfg &cfg,
-                                uint64_t seed, uint32_t first_game_id, uint32_t epoch, const Pool &pool, const float *ln_table,
-                                uint32_t *best_out, int32_t *status_out, diee_search_stats *stats_out, int *launches) {
+                                uint64_t seed, uint32_t first_game_id, uint32_t epoch, const Pool &pool, const PoolPtrs &pp,
+                                const float *ln_table, uint32_t *best_out, int32_t *status_out, diee_search_stats *stats_out,
+                                int *launches) {
     const bool split = !(cfg.mode_flags & DIEE_MODE_ROLLOUT_CHECK_CURRENT);
     const typename G::State *r = static_cast<const typename G::State *>(roots);
     if (split) {
         mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
             r, n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
-        const long long pairs = (long long)n * cfg.iterations;
-        const long long blocks = (pairs + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA;
-        rollout_kernel<G><<<(unsigned)blocks, MCTS_WARPS_PER_CTA * 32, 0, st>>>(n, cfg, seed, first_game_id, epoch, pool, players,
-                                                                             status_out, stats_out);
+        if constexpr (std::is_same<G, BgGame>::value) {  // backgammon: one lane per rollout (lane_kernels.cu)
+            const cudaError_t e = launch_bg_rollouts(st, n, cfg, seed, first_game_id, epoch, pp, stats_out);
+            if (e != cudaSuccess) return e;
+        } else {
+            const long long pairs = (long long)n * cfg.iterations;
+            const long long blocks = (pairs + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA;
+            rollout_kernel<G><<<(unsigned)blocks, MCTS_WARPS_PER_CTA * 32, 0, st>>>(n, cfg, seed, first_game_id, epoch, pool,
+                                                                                 players, status_out, stats_out);
+        }
         *launches = 2;
     } else {
         mcts_search_kernel<G, false><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
@@ -347,9 +355,9 @@ cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots
     if (n <= 0) return cudaSuccess;
     Pool pool{pp.states, pp.parent, pp.visits, pp.value, pp.action, pp.nmoves, pp.n_nodes, pp.sim_node, pp.finals};
     if (game_kind == DIEE_GAME_BACKGAMMON)
-        return launch_typed<BgGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out,
+        return launch_typed<BgGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, pp, ln_table, best_out,
                                     status_out, stats_out, launches);
-    return launch_typed<TttGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out,
+    return launch_typed<TttGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, pp, ln_table, best_out,
                                  status_out, stats_out, launches);
 }
 

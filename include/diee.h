@@ -161,7 +161,8 @@ int32_t diee_bg_apply_moves_dev(diee_ctx *ctx, diee_bg_state *states, const diee
                                 const uint8_t *next_rolls, int32_t n);
 /* random-vs-random playout of whole games (Agent::Random both sides, versus.rs:160-268,307-316),
  * fused in one launch: game i uses stream DIEE_STREAM_GAME of game id first_game_id+i; stops at a
- * winner or after round_limit plies.  winners_out: -1/+1, 0 at the cap.  finals_out nullable. */
+ * winner or after round_limit plies.  winners_out: -1/+1, 0 at the cap.  finals_out nullable.
+ * The _dev form needs its state arrays 16-byte aligned (DIEE_ERR_INVALID otherwise). */
 int32_t diee_bg_playout(diee_ctx *ctx, const diee_bg_state *starts, int32_t n, uint64_t seed,
                         uint32_t first_game_id, int32_t round_limit, int8_t *winners_out,
                         int32_t *plies_out, diee_bg_state *finals_out);

@@ -171,8 +171,12 @@ int32_t diee_bg_playout_dev(diee_ctx *ctx, const diee_bg_state *starts, int32_t 
     if (((uintptr_t)starts | (uintptr_t)finals_out) & 15u)  // states move as two 16-byte vectors per lane
         return fail(ctx, DIEE_ERR_INVALID, "bg_playout: device state arrays must be 16-byte aligned");
     CU(cudaSetDevice(ctx->device));
-    CU(launch_bg_playout(ctx->stream, starts, n, seed, first_game_id, round_limit, winners_out, plies_out, finals_out));
-    ctx->launches += n > 0;
+    if (n == 0) return DIEE_OK;
+    int nl = 0;
+    RESERVE(ctx->q_head, sizeof(unsigned long long));
+    CU(launch_bg_playout(ctx->stream, starts, n, seed, first_game_id, round_limit, winners_out, plies_out, finals_out,
+                         (unsigned long long *)ctx->q_head.p, &nl));
+    ctx->launches += nl;
     return DIEE_OK;
 }
 
@@ -312,7 +316,9 @@ int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *state
     if (rc != DIEE_OK) return rc;
     PoolPtrs pp{ctx->p_states.p, (int32_t *)ctx->p_parent.p, (float *)ctx->p_visits.p, (float *)ctx->p_value.p,
                 (uint32_t *)ctx->p_action.p, (uint32_t *)ctx->p_nmoves.p, (int32_t *)ctx->p_nnodes.p,
-                (int32_t *)ctx->p_simnode.p, ctx->p_finals.p};
+                (int32_t *)ctx->p_simnode.p, ctx->p_finals.p, nullptr};
+    RESERVE(ctx->q_head, sizeof(unsigned long long));
+    pp.queue_head = (unsigned long long *)ctx->q_head.p;
     const size_t pairs = (size_t)cfg->iterations * (size_t)n;
     CU(cudaMemsetAsync(ctx->p_simnode.p, 0xFF, sizeof(int32_t) * pairs, ctx->stream));
     CU(cudaMemsetAsync(ctx->p_finals.p, 0, state_size(game_kind) * pairs, ctx->stream));

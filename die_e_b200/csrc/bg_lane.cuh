@@ -254,21 +254,26 @@ LANE_HD uint32_t l_play_to_seq(const LanePlay &pl, int player) {
 // own1: points with an own checker; freem: points not held by >= 2 opposing checkers; H: the six
 // home-board counts (own minus opponent, +16 bias, byte h = point h), only read when every own
 // checker is home.  Returns the candidate sources (bit 24 = bar entry).  :544-703
-LANE_HD uint32_t l_cands(int m, uint32_t own1, uint32_t freem, int bar, uint64_t H, bool isplus) {
+LANE_HD uint32_t l_cands(int m, uint32_t own1, uint32_t freem, int bar, uint64_t H, bool opp_home, bool isplus) {
     if (bar > 0) return ((freem >> (24 - m)) & 1u) << 24;  // :545-548 -> :668-682
     uint32_t cand = (freem << m) & own1 & L_M24;             // :600-617
     if ((own1 & ~0x3Fu) == 0) {                               // is_collectible :638-659 (bar == 0 here)
         // bit h of cm: own checker on home point h AND the signed sum of the higher home points
         // shows no own surplus (:571-578 / :588-595; opposing checkers can cancel own ones, quirk Q3)
-        uint32_t cm = 0;
-        int suf = 0;
+        uint32_t cm;
+        if (!opp_home) {
+            cm = own1 ? (1u << l_high(own1)) : 0u;  // nothing to cancel against: only the highest own point qualifies
+        } else {
+            cm = 0;
+            int suf = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int h = 5; h >= 0; --h) {
-            const int val = (int)((H >> (8 * h)) & 0xFF) - 16;
-            if (val >= 1 && suf <= 0) cm |= 1u << h;
-            suf += val;
+            for (int h = 5; h >= 0; --h) {
+                const int val = (int)((H >> (8 * h)) & 0xFF) - 16;
+                if (val >= 1 && suf <= 0) cm |= 1u << h;
+                suf += val;
+            }
         }
         const uint32_t ex = own1 & (1u << (m - 1));          // the exact point (:565-568, :584-587)
         const int hmax = isplus ? m - 1 : m - 2;             // player +1 scans from the exact point, -1 from below it
@@ -287,7 +292,9 @@ struct LaneGen {
     uint32_t R0, R1;  // root sources per die order (order 0 = low die first; R1 = 0 for doubles)
     int lo, hi;       // the dice, low and high
     int U;            // number of distinct plays
+    int N0;           // closed form, two different dice: distinct plays that start with the low die
     bool isplus;
+    bool closed;      // counted in closed form (no scratch was written)
 };
 
 LANE_HD bool l_test_and_set(uint32_t &m, uint32_t bit) {  // true iff the bit was clear
@@ -296,9 +303,10 @@ LANE_HD bool l_test_and_set(uint32_t &m, uint32_t bit) {  // true iff the bit wa
     return fresh;
 }
 
-// Counts the distinct plays of `g` and parks, per root in reference order, the mask of its NEW
-// children in scr[slot * stride].  scr needs L_SCRATCH words (lane-strided).
-LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stride) {
+// Counts the distinct plays of `g` root by root and parks, per root in reference order, the mask of its
+// NEW children in scr[slot * stride].  scr needs L_SCRATCH words (lane-strided).  Exact in every regime;
+// used where the closed form below does not apply (checkers on the bar, bearing off).
+LANE_HD void l_movegen_walk(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stride) {
     const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;  // :406-409
     const bool dbl = hi == lo;
     const bool isplus = g.player > 0;
@@ -309,7 +317,9 @@ LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stri
     const uint32_t freem = ~p123 & L_M24;
     const int bar = g.bar_own;
     gen.isplus = isplus;
+    gen.closed = false;
     gen.U = 0;
+    gen.N0 = 0;
     gen.R0 = gen.R1 = 0;
     gen.lo = lo;
     gen.hi = hi;
@@ -319,7 +329,8 @@ LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stri
     const uint32_t outside = own1 & ~0x3Fu;
     const bool bo_regime = bar == 0 && (outside & (outside - 1u)) == 0 && (outside & ~own_single) == 0;
     uint64_t H = 0;
-    if (bo_regime) {
+    const bool opp_home = ((g.opp[0] | p123) & 0x3Fu) != 0;  // opposing checkers inside the mover's home board
+    if (bo_regime && opp_home) {
         const uint32_t mag[4] = {g.own[0] | g.opp[0], g.own[1] | g.opp[1], g.own[2] | g.opp[2], g.own[3] | g.opp[3]};
         const uint32_t oppany = g.opp[0] | p123;
 #if defined(__CUDA_ARCH__)
@@ -343,7 +354,7 @@ LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stri
     for (int b = 0; b < 2; ++b) {
         if (b == 1 && dbl) break;
         const int m1 = b == 0 ? lo : hi, m2 = b == 0 ? hi : lo;
-        const uint32_t R = l_cands(m1, own1, freem, bar, H, isplus);
+        const uint32_t R = l_cands(m1, own1, freem, bar, H, opp_home, isplus);
         if (b == 0) gen.R0 = R; else gen.R1 = R;
         uint32_t r = R;
         while (r) {
@@ -357,11 +368,11 @@ LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stri
             bool hit1 = false;
             if (t1 < 24) { own1p |= 1u << t1; hit1 = (oppblot >> t1) & 1u; }
             uint64_t Hp = H;
-            if (bo_regime) {
+            if (bo_regime && opp_home) {
                 if (x < 6) Hp -= 1ull << (8 * x);
                 if (t1 < 6) Hp += (uint64_t)(hit1 ? 2 : 1) << (8 * t1);
             }
-            const uint32_t C = l_cands(m2, own1p, freem, bar - (frombar ? 1 : 0), Hp, isplus);
+            const uint32_t C = l_cands(m2, own1p, freem, bar - (frombar ? 1 : 0), Hp, opp_home, isplus);
             uint32_t newm = 0;
             if (C == 0) {  // a one-move play (leaf root): net move x -> t1
                 const uint32_t bit = 1u << x;
@@ -425,8 +436,8 @@ LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stri
     gen.U = U;
 }
 
-// the k-th distinct play (0 <= k < gen.U) in reference order
-LANE_HD LanePlay l_pick(const LaneGen &gen, const uint32_t *scr, int stride, int k) {
+// the k-th distinct play (0 <= k < gen.U) in reference order, from the masks l_movegen_walk parked
+LANE_HD LanePlay l_pick_walk(const LaneGen &gen, const uint32_t *scr, int stride, int k) {
     LanePlay pl;
     pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
     int slot = 0, acc = 0;
@@ -457,6 +468,286 @@ LANE_HD LanePlay l_pick(const LaneGen &gen, const uint32_t *scr, int stride, int
         }
     }
     return pl;
+}
+
+// ---------------- closed form: contact play, nothing on the bar, no bearing off ----------------
+// Here every candidate is a plain move x -> x-d, so with A(d) = points whose d-target is on the board and
+// not blocked, the sources of die d are S(d) = A(d) & own, and the board after x -> t differs from the
+// board before only at x (vacated iff it held one checker) and t.  Hence root x's children are
+//     S(other die)  minus x if x held one checker  plus t if t can move on and held no own checker,
+// and which of them are NEW follows from masks alone (file header: only the "same checker moves on" child
+// t and the "another checker refills x" child x+d2 collapse to a net single move F -> F-lo-hi, F = x resp.
+// x+d2; every other child that starts from an own point repeats a play of an earlier root -- in the other
+// die order, or for doubles the mirrored pair -- and a child that starts from a point the mover did not
+// hold (t after hitting a blot there) is always new).  So the count needs no loop over roots at all and
+// the k-th play is found by a popcount walk that recomputes one root's mask.
+struct LaneMasks {
+    uint32_t own1, single, blot;  // own >= 1, own == 1, opponent == 1
+    uint32_t A_lo, A_hi;          // points that may move the low / high die
+};
+
+LANE_HD bool l_closed_applies(const LaneBoard &g, LaneMasks &m, int lo, int hi) {
+    const uint32_t o123 = g.own[1] | g.own[2] | g.own[3], p123 = g.opp[1] | g.opp[2] | g.opp[3];
+    m.own1 = g.own[0] | o123;
+    m.single = g.own[0] & ~o123;
+    m.blot = g.opp[0] & ~p123;
+    const uint32_t freem = ~p123 & L_M24;
+    m.A_lo = (freem << lo) & L_M24;
+    m.A_hi = (freem << hi) & L_M24;
+    const uint32_t outside = m.own1 & ~0x3Fu;
+    const bool bo_regime = (outside & (outside - 1u)) == 0 && (outside & ~m.single) == 0;
+    return g.bar_own == 0 && !bo_regime;
+}
+
+// two different dice
+struct LaneTwo {
+    uint32_t R0, R1;       // roots: sources of the low die, of the high die
+    uint32_t G0, L, Z0;    // order 0 per root: gains a child (t moves on), loses a child (x itself), has none
+    uint32_t D0;           // F whose net move F -> F-lo-hi is produced twice in order 0
+    uint32_t NR1, NL1, Z1; // order 1 per root: new run-on child, new refill child (as root masks), no child
+    int nR0, nR1;
+};
+LANE_HD void l_two(const LaneMasks &m, int lo, int hi, bool isplus, LaneTwo &t) {
+    t.R0 = m.A_lo & m.own1;
+    t.R1 = m.A_hi & m.own1;
+    t.nR0 = l_popc(t.R0);
+    t.nR1 = l_popc(t.R1);
+    t.G0 = t.R0 & ((m.A_hi & ~m.own1) << lo);
+    t.L = t.R0 & t.R1 & m.single;
+    const uint32_t RUN0 = t.R0 & ((m.A_hi & ~m.blot) << lo);   // F = x: x -> x-lo -> x-lo-hi without a hit on the way
+    const uint32_t LEAP0 = m.own1 & (t.R0 << hi) & L_M24;      // F = x+hi refills x
+    t.D0 = RUN0 & LEAP0;
+    t.Z0 = t.nR1 == 0 ? (t.R0 & ~t.G0) : (t.nR1 == 1 ? (t.L & ~t.G0) : 0u);
+    const uint32_t G1 = t.R1 & ((m.A_lo & ~m.own1) << hi);
+    const uint32_t RUN1 = t.R1 & ((m.A_lo & ~m.blot) << hi);
+    const uint32_t HIT1 = t.R1 & ((m.A_lo & m.blot) << hi);    // runs on through a blot it hit: a new board
+    const uint32_t LEAP1 = m.own1 & (t.R1 << lo) & L_M24;
+    const uint32_t fresh = ~(RUN0 | LEAP0);
+    // F produced by both a run-on (root F) and a refill (root F-lo): the root that comes first keeps it
+    const uint32_t newrun = isplus ? (RUN1 & fresh) : (RUN1 & fresh & ~LEAP1);
+    const uint32_t newleapF = isplus ? (LEAP1 & fresh & ~RUN1) : (LEAP1 & fresh);
+    t.NR1 = HIT1 | newrun;
+    t.NL1 = newleapF >> lo;
+    t.Z1 = t.nR0 == 0 ? (t.R1 & ~G1) : (t.nR0 == 1 ? (t.L & ~G1) : 0u);
+}
+
+// doubles
+struct LaneDbl {
+    uint32_t R, G, Lx, Z, HIT, NEWRUN, NEWLEAPF;
+    int nR;
+};
+LANE_HD void l_dbl(const LaneMasks &m, int d, bool isplus, LaneDbl &t) {
+    t.R = m.A_lo & m.own1;
+    t.nR = l_popc(t.R);
+    t.G = t.R & ((m.A_lo & ~m.own1) << d);
+    t.Lx = t.R & m.single;
+    const uint32_t RUN = t.R & ((m.A_lo & ~m.blot) << d);
+    t.HIT = t.R & ((m.A_lo & m.blot) << d);
+    const uint32_t LEAP = m.own1 & (t.R << d) & L_M24;
+    t.NEWRUN = isplus ? RUN : (RUN & ~LEAP);
+    t.NEWLEAPF = isplus ? (LEAP & ~RUN) : LEAP;
+    t.Z = t.nR == 1 ? (t.Lx & ~t.G) : 0u;
+}
+
+// mask of the NEW children of doubles root x (L_SINGLE: the root alone is the play)
+LANE_HD uint32_t l_dbl_newmask(const LaneMasks &m, const LaneDbl &t, int d, bool isplus, int x) {
+    const uint32_t xb = 1u << x;
+    if (t.Z & xb) return L_SINGLE;
+    const uint32_t upto = (xb << 1) - 1u;
+    // an own-point child repeats an earlier root's pair unless it comes at or after x in root order
+    uint32_t nm = t.R & (isplus ? upto : ~(upto >> 1));
+    nm &= ~(xb & m.single);
+    const uint32_t tb = x >= d ? (xb >> d) : 0u, lb = (xb << d) & L_M24;
+    nm &= ~(tb | lb);  // the run-on and the refill child are judged on their own
+    if ((t.HIT | t.NEWRUN) & xb) nm |= tb;
+    nm |= t.NEWLEAPF & lb;
+    return nm;
+}
+
+LANE_HD uint32_t l_two_newmask0(const LaneMasks &m, const LaneTwo &t, int lo, int hi, bool isplus, int x) {
+    const uint32_t xb = 1u << x;
+    if (t.Z0 & xb) return L_SINGLE;
+    uint32_t nm = t.R1 & ~(xb & m.single);
+    if (t.G0 & xb) nm |= xb >> lo;
+    // F -> F-lo-hi produced twice: the later root's copy is the duplicate
+    if (isplus) nm &= ~(((xb << hi) & L_M24) & t.D0);
+    else if (t.D0 & xb) nm &= ~(xb >> lo);
+    return nm;
+}
+LANE_HD uint32_t l_two_newmask1(const LaneTwo &t, int lo, int hi, int y) {
+    const uint32_t yb = 1u << y;
+    if (t.Z1 & yb) return L_SINGLE;
+    uint32_t nm = 0;
+    if (t.NR1 & yb) nm |= yb >> hi;
+    if (t.NL1 & yb) nm |= yb << lo;
+    return nm;
+}
+
+// Counts the distinct plays of `g` in closed form; the caller has checked l_closed_applies.
+LANE_HD void l_movegen_closed(const LaneBoard &g, const LaneMasks &m, int lo, int hi, LaneGen &gen) {
+    const bool isplus = g.player > 0;
+    gen.isplus = isplus;
+    gen.closed = true;
+    gen.lo = lo;
+    gen.hi = hi;
+    gen.R1 = 0;
+    gen.N0 = 0;
+    if (lo == hi) {
+        LaneDbl t;
+        l_dbl(m, lo, isplus, t);
+        gen.R0 = t.R;
+        gen.U = t.nR * (t.nR + 1) / 2 - l_popc(t.R & (t.R >> lo)) - l_popc(t.Lx) + l_popc(t.HIT) + l_popc(t.NEWRUN | t.NEWLEAPF) + l_popc(t.Z);
+    } else {
+        LaneTwo t;
+        l_two(m, lo, hi, isplus, t);
+        gen.R0 = t.R0;
+        gen.R1 = t.R1;
+        gen.N0 = t.nR0 * t.nR1 - l_popc(t.L) + l_popc(t.G0) - l_popc(t.D0) + l_popc(t.Z0);
+        gen.U = gen.N0 + l_popc(t.NR1) + l_popc(t.NL1) + l_popc(t.Z1);
+    }
+}
+
+LANE_HD LanePlay l_play_from(int x, int m1, int m2, uint32_t nm, int j, bool isplus) {
+    LanePlay pl;
+    pl.x1 = x;
+    pl.t1 = l_to(x, m1);
+    pl.x2 = pl.t2 = 0;
+    if (nm & L_SINGLE) { pl.n = 1; return pl; }
+    for (; j > 0; --j) nm &= ~(1u << l_take(nm, isplus));
+    pl.n = 2;
+    pl.x2 = l_take(nm, isplus);
+    pl.t2 = l_to(pl.x2, m2);
+    return pl;
+}
+
+// ---------------- closed form: checkers on the bar ----------------
+// Only entries are legal while the bar is occupied (:545-548), so there is one root per die order.
+// Two or more on the bar: both sub-moves are entries and the two orders give the same board.  Exactly one:
+// after it has entered on e = 24 - die, the other die is played from S(other) plus e itself; every such
+// play is new (the other order starts with a different entry) except "enter and move on with the same
+// checker", which both orders produce when neither entry point holds a blot.
+struct LaneBarMasks {
+    uint32_t C0, N1;   // order 0: children of the low-die entry; order 1: NEW children of the high-die entry
+    bool fl, fh;       // the low / high die can enter
+    bool single1;      // order 1 is a one-move play
+    int n0, n1;
+};
+LANE_HD void l_bar(const LaneBoard &g, const LaneMasks &m, int lo, int hi, LaneBarMasks &t) {
+    const uint32_t freem = ~(g.opp[1] | g.opp[2] | g.opp[3]) & L_M24;
+    const int el = 24 - lo, eh = 24 - hi;
+    t.fl = (freem >> el) & 1u;
+    t.fh = (freem >> eh) & 1u;
+    t.C0 = t.N1 = 0;
+    t.single1 = false;
+    if (g.bar_own >= 2) {  // enter twice: (lo, hi), or whichever single entry is possible
+        t.n0 = t.fl ? 1 : 0;
+        t.n1 = (!t.fl && t.fh) ? 1 : 0;
+        if (lo == hi) t.n1 = 0;
+        return;
+    }
+    t.C0 = t.fl ? (m.A_hi & (m.own1 | (1u << el))) : 0u;
+    t.n0 = t.fl ? (t.C0 ? l_popc(t.C0) : 1) : 0;
+    t.n1 = 0;
+    if (lo != hi && t.fh) {
+        const uint32_t C1 = m.A_lo & (m.own1 | (1u << eh));
+        const bool run0 = t.fl && ((m.A_hi & ~m.blot) >> el & 1u);
+        const bool run1 = (m.A_lo & ~m.blot) >> eh & 1u;
+        t.N1 = C1 & ~((run0 && run1) ? (1u << eh) : 0u);
+        t.single1 = C1 == 0;
+        t.n1 = t.single1 ? 1 : l_popc(t.N1);
+    }
+}
+LANE_HD void l_movegen_bar(const LaneBoard &g, const LaneMasks &m, int lo, int hi, LaneGen &gen) {
+    LaneBarMasks t;
+    l_bar(g, m, lo, hi, t);
+    gen.isplus = g.player > 0;
+    gen.closed = true;
+    gen.lo = lo;
+    gen.hi = hi;
+    gen.R0 = gen.R1 = 0;
+    gen.N0 = t.n0;
+    gen.U = t.n0 + t.n1;
+}
+LANE_HD LanePlay l_pick_bar(const LaneBoard &g, const LaneMasks &m, int lo, int hi, int k) {
+    LaneBarMasks t;
+    l_bar(g, m, lo, hi, t);
+    const bool isplus = g.player > 0;
+    LanePlay pl;
+    pl.x1 = L_BAR;
+    pl.x2 = pl.t2 = 0;
+    if (g.bar_own >= 2) {
+        const bool both = t.fl && t.fh;
+        pl.t1 = t.fl ? 24 - lo : 24 - hi;
+        pl.n = both ? 2 : 1;
+        if (both) { pl.x2 = L_BAR; pl.t2 = 24 - hi; }
+        return pl;
+    }
+    if (k < t.n0) {
+        pl.t1 = 24 - lo;
+        return l_play_from(L_BAR, lo, hi, t.C0 ? t.C0 : L_SINGLE, k, isplus);
+    }
+    return l_play_from(L_BAR, hi, lo, t.single1 ? L_SINGLE : t.N1, k - t.n0, isplus);
+}
+
+// Counts the distinct plays of `g`.  Contact play is counted in closed form; otherwise root by root.
+LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stride) {
+    const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;
+    LaneMasks m;
+    if (l_closed_applies(g, m, lo, hi)) l_movegen_closed(g, m, lo, hi, gen);
+    else if (g.bar_own > 0) l_movegen_bar(g, m, lo, hi, gen);
+    else l_movegen_walk(g, gen, scr, stride);
+}
+
+// the k-th distinct play (0 <= k < gen.U) in reference order
+LANE_HD LanePlay l_pick(const LaneBoard &g, const LaneGen &gen, const uint32_t *scr, int stride, int k) {
+    if (!gen.closed) return l_pick_walk(gen, scr, stride, k);
+    const bool isplus = gen.isplus;
+    const int lo = gen.lo, hi = gen.hi;
+    LaneMasks m;
+    l_closed_applies(g, m, lo, hi);
+    if (g.bar_own > 0) return l_pick_bar(g, m, lo, hi, k);
+    int acc = 0;
+    if (lo == hi) {
+        LaneDbl t;
+        l_dbl(m, lo, isplus, t);
+        uint32_t r = t.R;
+        while (r) {
+            const int x = l_take(r, isplus);
+            r &= ~(1u << x);
+            const uint32_t nm = l_dbl_newmask(m, t, lo, isplus, x);
+            const int c = l_popc(nm);
+            if (k < acc + c) return l_play_from(x, lo, lo, nm, k - acc, isplus);
+            acc += c;
+        }
+    } else {
+        LaneTwo t;
+        l_two(m, lo, hi, isplus, t);
+        if (k < gen.N0) {
+            uint32_t r = t.R0;
+            while (r) {
+                const int x = l_take(r, isplus);
+                r &= ~(1u << x);
+                const uint32_t nm = l_two_newmask0(m, t, lo, hi, isplus, x);
+                const int c = l_popc(nm);
+                if (k < acc + c) return l_play_from(x, lo, hi, nm, k - acc, isplus);
+                acc += c;
+            }
+        } else {
+            acc = gen.N0;
+            uint32_t r = t.R1;
+            while (r) {
+                const int y = l_take(r, isplus);
+                r &= ~(1u << y);
+                const uint32_t nm = l_two_newmask1(t, lo, hi, y);
+                const int c = l_popc(nm);
+                if (k < acc + c) return l_play_from(y, hi, lo, nm, k - acc, isplus);
+                acc += c;
+            }
+        }
+    }
+    LanePlay none;
+    none.n = 0; none.x1 = none.t1 = none.x2 = none.t2 = 0;
+    return none;
 }
 
 }  // namespace lane

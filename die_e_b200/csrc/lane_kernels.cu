@@ -1,8 +1,8 @@
 // lane_kernels.cu -- one LANE per game: the throughput kernels of the path.
 //
-//   bg_playout_lane_kernel   C2: whole random-vs-random games
-//   bg_rollout_lane_kernel   T4: every deferred Node::simulate of a split search (node.rs:176-196),
-//                            one lane per (game, iteration)
+//   bg_lane_run_kernel<false>   C2: whole random-vs-random games
+//   bg_lane_run_kernel<true>    T4: every deferred Node::simulate of a split search (node.rs:176-196),
+//                               one lane per (game, iteration)
 //
 // A ply is get_valid_moves -> uniform choice -> apply_move | skip_turn.  The board lives in the lane's
 // registers as bit planes (bg_lane.cuh); the only memory a ply touches is the lane's own column of a
@@ -10,6 +10,9 @@
 // never conflict.  HBM: 32 B in and 32 B (+5 B) out per game / per rollout, nothing in between.
 // Randomness: one Philox4x32-10 block per ply, counter = (ply, game id, stream, epoch<<16|iteration)
 // -- the contract of include/diee.h, identical to the warp-per-game kernels and to the oracle.
+#include <climits>
+#include <cstdlib>
+
 #include "bg_lane.cuh"
 #include "launchers.h"
 
@@ -18,10 +21,6 @@ namespace diee {
 using namespace lane;
 
 constexpr int LANE_CTA = 128;
-
-struct LaneScratch {
-    uint32_t w[L_SCRATCH][LANE_CTA];
-};
 
 __device__ __forceinline__ void lane_load_state(LaneBoard &g, const diee_bg_state *s) {
     const uint4 a = __ldg(reinterpret_cast<const uint4 *>(s));
@@ -36,83 +35,240 @@ __device__ __forceinline__ void lane_store_state(const LaneBoard &g, diee_bg_sta
     reinterpret_cast<uint4 *>(s)[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-// one ply with the Philox block of (ply k, game gid, stream, c3)
-__device__ __forceinline__ void lane_ply(LaneBoard &g, uint32_t *scr, uint64_t seed, uint32_t k, uint32_t gid,
-                                         uint32_t stream, uint32_t c3) {
+#ifdef DIEE_LANE_STATS
+__device__ unsigned long long g_lane_stats[16];  // [p] = steps executed on path p, [8+p] = lanes advanced
+#endif
+
+struct LaneJob {
+    // PLAYOUT (C2): item = game index; ROLLOUT (T4): item = game * iterations + iteration
+    long long n_items;
+    uint32_t iterations;  // ROLLOUT only
+    uint32_t limit;
+    uint64_t seed;
+    uint32_t first_game_id, epoch;
+    int lag_weight;                // scheduling: how much one step of waiting counts against one more waiting lane
+    unsigned long long *next_item; // job queue head (zeroed before the launch)
+    const diee_bg_state *states;   // PLAYOUT: starts[n]; ROLLOUT: node pool states
+    const int32_t *sim_node;       // ROLLOUT: node each simulation rolls out from, or -1
+    diee_bg_state *finals;         // PLAYOUT: nullable
+    int8_t *winners;               // PLAYOUT
+    int32_t *plies;                // PLAYOUT
+};
+
+// The code path the next ply of a game needs.  A warp runs ONE path per step, for all its lanes that
+// wait for that path (see lane_run_kernel).
+// PATH_CLOSED: the distinct plays are counted in closed form (contact play, entering from the bar, or
+// nothing to move); PATH_WALK: the side can bear off within the play, counted root by root.
+enum { PATH_DONE = 0, PATH_CLOSED, PATH_WALK, PATH_COUNT };
+
+__device__ __forceinline__ int lane_path(const LaneBoard &g) {
+    const uint32_t o123 = g.own[1] | g.own[2] | g.own[3];
+    const uint32_t own1 = g.own[0] | o123;
+    if (g.bar_own > 0 || own1 == 0) return PATH_CLOSED;
+    const uint32_t outside = own1 & ~0x3Fu;
+    if ((outside & (outside - 1u)) == 0 && (outside & ~(g.own[0] & ~o123)) == 0) return PATH_WALK;
+    return PATH_CLOSED;
+}
+
+// a rollout whose two sides have collected everything: the remaining plies are skip_turns, i.e. the side
+// to move alternates and the dice shown at the end are those of the last ply
+template <bool ROLLOUT>
+__device__ __forceinline__ void rollout_finish_dead(const LaneJob &job, long long item, LaneBoard &g, uint32_t k_now, uint32_t gid, uint32_t c3) {
     uint32_t o[4];
-    l_philox((uint32_t)seed, (uint32_t)(seed >> 32), k, gid, stream, c3, o);
-    LaneGen gen;
-    l_movegen(g, gen, scr, LANE_CTA);
-    LanePlay pl;
-    pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
-    if (gen.U > 0) pl = l_pick(gen, scr, LANE_CTA, (int)l_index(o[2], (uint32_t)gen.U));
-    l_step(g, pl, l_die(o[0]), l_die(o[1]));
+    l_philox((uint32_t)job.seed, (uint32_t)(job.seed >> 32), job.limit - 1u, gid, DIEE_STREAM_ROLLOUT, c3, o);
+    if ((job.limit - k_now) & 1u) l_pass_turn(g, 0, 0);
+    g.second = 0; g.roll0 = l_die(o[0]); g.roll1 = l_die(o[1]);
+    lane_store_state(g, job.finals + item);
 }
 
+// One lane per item (a game, or one rollout of a search), whole job in one launch.
+//
+// Lanes of a warp are independent games, so nothing forces them to play ply k together, or even to
+// work on the same item for the same time.  The kernel is persistent: a lane that has finished its item
+// takes the next one from the job queue, so short games do not leave lanes empty while a long one ends.
+// Each lane knows which code path its next ply needs (pass / two dice in contact / doubles in contact /
+// entering from the bar / bearing off).  Every step the warp votes: the path with the most waiting lanes
+// wins, lanes that have waited long counting extra so that nobody starves; the warp executes THAT path
+// once, for the lanes waiting on it, and they move on to their next ply.  Divergence between code paths
+// is thereby turned into batching.
+template <bool ROLLOUT>
 __global__ void __launch_bounds__(LANE_CTA)
-bg_playout_lane_kernel(const diee_bg_state *__restrict__ starts, int n, uint64_t seed, uint32_t first_game_id,
-                       int round_limit, int8_t *__restrict__ winners_out, int32_t *__restrict__ plies_out,
-                       diee_bg_state *__restrict__ finals_out) {
-    __shared__ LaneScratch scratch;
-    const int gidx = blockIdx.x * LANE_CTA + threadIdx.x;
-    if (gidx >= n) return;
-    uint32_t *scr = &scratch.w[0][threadIdx.x];
+lane_run_kernel(LaneJob job) {
+    __shared__ uint32_t scratch[L_SCRATCH][LANE_CTA];
+    uint32_t *scr = &scratch[0][threadIdx.x];
+    const int lane = threadIdx.x & 31;
+    const uint32_t stream = ROLLOUT ? DIEE_STREAM_ROLLOUT : DIEE_STREAM_GAME;
     LaneBoard g;
-    lane_load_state(g, starts + gidx);
-    const uint32_t gid = first_game_id + (uint32_t)gidx;
-    int ply = 0;
-    int w = l_winner(g);
-    while (w == 0 && ply < round_limit) {
-        lane_ply(g, scr, seed, (uint32_t)ply, gid, DIEE_STREAM_GAME, 0u);
-        ++ply;
-        w = l_winner(g);
+    long long item = -1;
+    uint32_t gid = 0, c3 = 0, k = 0;
+    int need = PATH_DONE;
+    uint32_t age = 0;  // steps this lane has waited for its path
+    bool queue_open = true;
+
+    for (;;) {
+        // ---- idle lanes take the next items of the job (one atomic per warp) ----
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, need == PATH_DONE);
+        if (idle && queue_open) {
+            long long first = 0;
+            if (lane == 0) first = (long long)atomicAdd(job.next_item, (unsigned long long)__popc(idle));
+            first = __shfl_sync(0xFFFFFFFFu, first, 0);
+            if (first + __popc(idle) >= job.n_items) queue_open = false;
+            if (need == PATH_DONE) {
+                item = first + __popc(idle & ((1u << lane) - 1u));
+                if (item < job.n_items) {
+                    k = 0;
+                    if (ROLLOUT) {
+                        const uint32_t gm = (uint32_t)(item / job.iterations);
+                        const uint32_t it = (uint32_t)(item - (long long)gm * job.iterations);
+                        const int node = job.sim_node[item];
+                        if (node >= 0 && job.limit > 0) {  // node < 0: the iteration ended on a terminal leaf, no rollout
+                            lane_load_state(g, job.states + (size_t)gm * (job.iterations + 1) + node);
+                            gid = job.first_game_id + gm; c3 = (job.epoch << 16) | (it & 0xFFFFu);
+                            if (g.off_own == 15 && g.off_opp == 15) rollout_finish_dead<ROLLOUT>(job, item, g, 0u, gid, c3);
+                            else need = lane_path(g);
+                        }
+                    } else {
+                        lane_load_state(g, job.states + item);
+                        gid = job.first_game_id + (uint32_t)item;
+                        const int w = l_winner(g);
+                        if (w != 0 || job.limit == 0) {
+                            job.winners[item] = (int8_t)w; job.plies[item] = 0;
+                            if (job.finals) lane_store_state(g, job.finals + item);
+                        } else {
+                            need = lane_path(g);
+                        }
+                    }
+                }
+            }
+            continue;  // vote with the newcomers included (or take more, if some of them needed no ply at all)
+        }
+
+        // ---- vote ----
+        int best = PATH_DONE, best_score = INT_MIN;
+#pragma unroll
+        for (int p = 1; p < PATH_COUNT; ++p) {
+            const uint32_t waiting = __ballot_sync(0xFFFFFFFFu, need == p);
+            if (waiting) {
+                const int score = __popc(waiting) + job.lag_weight * (int)__reduce_max_sync(0xFFFFFFFFu, need == p ? age : 0u);
+                if (score > best_score) { best_score = score; best = p; }
+            }
+        }
+        if (best == PATH_DONE) break;
+#ifdef DIEE_LANE_STATS
+        { const uint32_t adv = __ballot_sync(0xFFFFFFFFu, need == best); if (lane == 0) { atomicAdd(&g_lane_stats[best], 1ull); atomicAdd(&g_lane_stats[8 + best], (unsigned long long)__popc(adv)); } }
+#endif
+        if (need != best) { ++age; continue; }
+        age = 0;
+
+        // ---- one ply on path `best` (warp-uniform) for the lanes that wait for it ----
+        uint32_t o[4];
+        l_philox((uint32_t)job.seed, (uint32_t)(job.seed >> 32), k, gid, stream, c3, o);
+        LanePlay pl;
+        pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
+        if (best == PATH_CLOSED) {
+            const int hi = max(g.roll0, g.roll1), lo = min(g.roll0, g.roll1);
+            LaneMasks m;
+            l_closed_applies(g, m, lo, hi);
+            LaneGen gen;
+            gen.U = 0;
+            if (g.bar_own > 0) l_movegen_bar(g, m, lo, hi, gen);
+            else if (m.own1 != 0) l_movegen_closed(g, m, lo, hi, gen);
+            if (gen.U > 0) pl = l_pick(g, gen, scr, LANE_CTA, (int)l_index(o[2], (uint32_t)gen.U));
+        } else {
+            LaneGen gen;
+            l_movegen_walk(g, gen, scr, LANE_CTA);
+            if (gen.U > 0) pl = l_pick_walk(gen, scr, LANE_CTA, (int)l_index(o[2], (uint32_t)gen.U));
+        }
+        l_step(g, pl, l_die(o[0]), l_die(o[1]));
+        ++k;
+
+        // ---- what next ----
+        if (ROLLOUT) {
+            if (k == job.limit) { lane_store_state(g, job.finals + item); need = PATH_DONE; }
+            else if (g.off_own == 15 && g.off_opp == 15) { rollout_finish_dead<ROLLOUT>(job, item, g, k, gid, c3); need = PATH_DONE; }
+            else need = lane_path(g);
+        } else {
+            const int w = l_winner(g);
+            if (w != 0 || k == job.limit) {  // versus.rs:231-235: the game stops at its winner, or at the cap
+                job.winners[item] = (int8_t)w; job.plies[item] = (int32_t)k;
+                if (job.finals) lane_store_state(g, job.finals + item);
+                need = PATH_DONE;
+            } else {
+                need = lane_path(g);
+            }
+        }
     }
-    winners_out[gidx] = (int8_t)w;
-    plies_out[gidx] = ply;
-    if (finals_out) lane_store_state(g, finals_out + gidx);
 }
 
-// Every deferred rollout of a split (reference-exact) search.  Node::simulate tests the winner of its
-// START state (node.rs:181, quirk Q5) and the tree kernel only defers non-terminal starts, so each
-// rollout plays exactly `limit` plies; its result is 0 and only the plies and the final state are kept.
-__global__ void __launch_bounds__(LANE_CTA)
-bg_rollout_lane_kernel(int n_games, uint32_t iterations, uint32_t limit, uint64_t seed, uint32_t first_game_id,
-                       uint32_t epoch, const diee_bg_state *__restrict__ node_states, const int32_t *__restrict__ sim_node,
-                       diee_bg_state *__restrict__ finals, diee_search_stats *__restrict__ stats_out) {
-    __shared__ LaneScratch scratch;
-    const long long pair = (long long)blockIdx.x * LANE_CTA + threadIdx.x;
-    if (pair >= (long long)n_games * iterations) return;
-    const int gm = (int)(pair / iterations);
-    const uint32_t it = (uint32_t)(pair - (long long)gm * iterations);
-    const int node = sim_node[pair];
-    if (node < 0) return;
-    uint32_t *scr = &scratch.w[0][threadIdx.x];
-    LaneBoard g;
-    lane_load_state(g, node_states + (size_t)gm * (iterations + 1) + node);
-    const uint32_t gid = first_game_id + (uint32_t)gm;
-    const uint32_t c3 = (epoch << 16) | (it & 0xFFFFu);
-    for (uint32_t k = 0; k < limit; ++k) lane_ply(g, scr, seed, k, gid, DIEE_STREAM_ROLLOUT, c3);
-    lane_store_state(g, finals + pair);
-    if (stats_out) atomicAdd(reinterpret_cast<unsigned long long *>(&stats_out[gm].rollout_plies), (unsigned long long)limit);
+// every deferred rollout plays exactly `limit` plies (Node::simulate tests its START state, quirk Q5)
+__global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32_t limit, const int32_t *__restrict__ sim_node,
+                                        diee_search_stats *__restrict__ stats_out) {
+    const int gm = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gm >= n_games) return;
+    unsigned long long c = 0;
+    for (uint32_t it = 0; it < iterations; ++it) c += sim_node[(size_t)gm * iterations + it] >= 0 ? limit : 0u;
+    stats_out[gm].rollout_plies += c;
+}
+
+template <bool ROLLOUT>
+static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) {
+    job.lag_weight = 0;
+    if (const char *e = getenv("DIEE_LANE_LAG")) job.lag_weight = atoi(e);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    int blocks_per_sm = 6;  // x 4 warps
+    if (const char *e = getenv("DIEE_LANE_BLOCKS_PER_SM")) blocks_per_sm = atoi(e);
+    long long blocks = (job.n_items + LANE_CTA - 1) / LANE_CTA;
+    if (blocks > (long long)sms * blocks_per_sm) blocks = (long long)sms * blocks_per_sm;
+    cudaError_t e = cudaMemsetAsync(job.next_item, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    lane_run_kernel<ROLLOUT><<<(unsigned)blocks, LANE_CTA, 0, st>>>(job);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_bg_playout(cudaStream_t st, const diee_bg_state *starts, int n, uint64_t seed, uint32_t first_game_id,
-                              int round_limit, int8_t *winners_out, int32_t *plies_out, diee_bg_state *finals_out) {
+                              int round_limit, int8_t *winners_out, int32_t *plies_out, diee_bg_state *finals_out,
+                              unsigned long long *queue_head, int *launches) {
     if (n <= 0) return cudaSuccess;
-    bg_playout_lane_kernel<<<(n + LANE_CTA - 1) / LANE_CTA, LANE_CTA, 0, st>>>(starts, n, seed, first_game_id, round_limit,
-                                                                               winners_out, plies_out, finals_out);
-    return cudaGetLastError();
+    LaneJob job{};
+    job.next_item = queue_head;
+    job.n_items = n; job.limit = (uint32_t)round_limit; job.seed = seed; job.first_game_id = first_game_id;
+    job.states = starts; job.finals = finals_out; job.winners = winners_out; job.plies = plies_out;
+    return launch_lane_job<false>(st, job, launches);
 }
 
 cudaError_t launch_bg_rollouts(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id,
-                               uint32_t epoch, const PoolPtrs &pp, diee_search_stats *stats_out) {
+                               uint32_t epoch, const PoolPtrs &pp, diee_search_stats *stats_out, int *launches) {
     const long long pairs = (long long)n_games * cfg.iterations;
     if (pairs <= 0 || cfg.simulate_round_limit == 0) return cudaSuccess;
-    const long long blocks = (pairs + LANE_CTA - 1) / LANE_CTA;
-    bg_rollout_lane_kernel<<<(unsigned)blocks, LANE_CTA, 0, st>>>(
-        n_games, cfg.iterations, cfg.simulate_round_limit, seed, first_game_id, epoch,
-        static_cast<const diee_bg_state *>(pp.states), pp.sim_node, static_cast<diee_bg_state *>(pp.finals), stats_out);
-    return cudaGetLastError();
+    LaneJob job{};
+    job.n_items = pairs; job.iterations = cfg.iterations; job.limit = cfg.simulate_round_limit; job.seed = seed;
+    job.first_game_id = first_game_id; job.epoch = epoch;
+    job.states = static_cast<const diee_bg_state *>(pp.states); job.sim_node = pp.sim_node;
+    job.finals = static_cast<diee_bg_state *>(pp.finals);
+    job.next_item = pp.queue_head;
+    cudaError_t e = launch_lane_job<true>(st, job, launches);
+    if (e != cudaSuccess) return e;
+    if (stats_out) {
+        bg_rollout_count_kernel<<<(n_games + 127) / 128, 128, 0, st>>>(n_games, cfg.iterations, cfg.simulate_round_limit, pp.sim_node, stats_out);
+        if (launches) *launches += 1;
+        e = cudaGetLastError();
+    }
+    return e;
 }
 
 }  // namespace diee
+
+#ifdef DIEE_LANE_STATS
+extern "C" int diee_debug_lane_stats(unsigned long long *out16, int reset) {
+    cudaMemcpyFromSymbol(out16, diee::g_lane_stats, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(diee::g_lane_stats, z, sizeof z); }
+    return 0;
+}
+#endif

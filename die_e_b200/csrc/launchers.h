@@ -16,16 +16,18 @@ struct PoolPtrs {
     int32_t *n_nodes;
     int32_t *sim_node;
     void *finals;
+    unsigned long long *queue_head;  // job queue head of the persistent lane kernel
 };
 
 cudaError_t launch_bg_valid_moves(cudaStream_t st, const diee_bg_state *states, int n, diee_move *moves_out,
                                   int32_t *counts_out, uint16_t *ids_out);
 cudaError_t launch_bg_apply(cudaStream_t st, diee_bg_state *states, const diee_move *moves, const uint8_t *next_rolls, int n);
 cudaError_t launch_bg_playout(cudaStream_t st, const diee_bg_state *starts, int n, uint64_t seed, uint32_t first_game_id,
-                              int round_limit, int8_t *winners_out, int32_t *plies_out, diee_bg_state *finals_out);
+                              int round_limit, int8_t *winners_out, int32_t *plies_out, diee_bg_state *finals_out,
+                              unsigned long long *queue_head, int *launches);
 // every deferred rollout of a split backgammon search, one lane per (game, iteration)  (lane_kernels.cu)
 cudaError_t launch_bg_rollouts(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id,
-                               uint32_t epoch, const PoolPtrs &pp, diee_search_stats *stats_out);
+                               uint32_t epoch, const PoolPtrs &pp, diee_search_stats *stats_out, int *launches);
 cudaError_t launch_bg_encode_moves(cudaStream_t st, const diee_bg_state *states, const diee_move *moves, int n, uint16_t *ids_out);
 cudaError_t launch_bg_decode_moves(cudaStream_t st, const diee_bg_state *states, const uint16_t *ids, int n, diee_move *moves_out);
 cudaError_t launch_bg_encode_states(cudaStream_t st, const diee_bg_state *states, int n, float *out);

@@ -330,8 +330,8 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
             r, n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
         if constexpr (std::is_same<G, BgGame>::value) {  // backgammon: one lane per rollout (lane_kernels.cu)
-            const cudaError_t e = launch_bg_rollouts(st, n, cfg, seed, first_game_id, epoch, pp, stats_out);
-            if (e != cudaSuccess) return e;
+            *launches = 1;
+            return launch_bg_rollouts(st, n, cfg, seed, first_game_id, epoch, pp, stats_out, launches);
         } else {
             const long long pairs = (long long)n * cfg.iterations;
             const long long blocks = (pairs + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA;

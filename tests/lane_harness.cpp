@@ -35,6 +35,7 @@ static void print_state(const orc_bg_state &s) {
 
 static long long n_checked = 0, n_moves_checked = 0, n_boregime = 0, n_bo_opp_home = 0, n_doubles = 0, n_bar = 0;
 static int max_moves = 0;
+static long long n_closed = 0;
 
 static bool check_position(const orc_bg_state &s) {
     uint32_t w[8];
@@ -65,19 +66,20 @@ static bool check_position(const orc_bg_state &s) {
         if (g.roll0 == g.roll1 && n > 0) ++n_doubles;
         if (g.bar_own > 0 && n > 0) ++n_bar;
         if (n > max_moves) max_moves = n;
+        if (gen.closed && n > 0) ++n_closed;
     }
     if (gen.U != n) {
         fprintf(stderr, "count differs: lane %d oracle %d\n", gen.U, n);
         print_state(s);
         for (int k = 0; k < n; ++k) fprintf(stderr, "  oracle %d: (%d,%d) (%d,%d)\n", k, mv[k].from1, mv[k].to1, mv[k].from2, mv[k].to2);
         for (int k = 0; k < gen.U; ++k) {
-            const uint32_t q = l_play_to_seq(l_pick(gen, scr, 1, k), g.player);
+            const uint32_t q = l_play_to_seq(l_pick(g, gen, scr, 1, k), g.player);
             fprintf(stderr, "  lane   %d: (%d,%d) (%d,%d)\n", k, (int8_t)q, (int8_t)(q >> 8), (int8_t)(q >> 16), (int8_t)(q >> 24));
         }
         return false;
     }
     for (int k = 0; k < n; ++k) {
-        const LanePlay pl = l_pick(gen, scr, 1, k);
+        const LanePlay pl = l_pick(g, gen, scr, 1, k);
         const uint32_t q = l_play_to_seq(pl, g.player);
         uint32_t o;
         memcpy(&o, &mv[k], 4);
@@ -196,7 +198,7 @@ int main(int argc, char **argv) {
             l_movegen(g, gen, scr, 1);
             LanePlay pl;
             pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
-            if (gen.U > 0) pl = l_pick(gen, scr, 1, (int)l_index(o[2], (uint32_t)gen.U));
+            if (gen.U > 0) pl = l_pick(g, gen, scr, 1, (int)l_index(o[2], (uint32_t)gen.U));
             l_step(g, pl, l_die(o[0]), l_die(o[1]));
             ++q;
         }
@@ -219,7 +221,7 @@ int main(int argc, char **argv) {
         if (!check_position(s)) return 1;
     }
     printf("lane engine == oracle on %lld positions, %lld plays (bear-off regime %lld, of which opposing checkers in the home board %lld; "
-           "doubles %lld; from the bar %lld; most plays in one position %d)\n",
-           n_checked, n_moves_checked, n_boregime, n_bo_opp_home, n_doubles, n_bar, max_moves);
+           "doubles %lld; from the bar %lld; counted in closed form %lld; most plays in one position %d)\n",
+           n_checked, n_moves_checked, n_boregime, n_bo_opp_home, n_doubles, n_bar, n_closed, max_moves);
     return 0;
 }

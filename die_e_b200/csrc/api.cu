@@ -34,6 +34,14 @@ int32_t diee_ctx_create(int32_t device, diee_ctx **out) {
         return DIEE_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    for (int i = 0; i < 4; ++i) {
+        if (cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_tree[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_roll[i], cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return DIEE_ERR_CUDA;
+        }
+    }
     *out = ctx;
     return DIEE_OK;
 }
@@ -52,6 +60,12 @@ int32_t diee_ctx_destroy(diee_ctx *ctx) {
                       &ctx->a_rolls_in};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    for (int i = 0; i < 4; ++i) {
+        if (ctx->side[i]) { cudaStreamSynchronize(ctx->side[i]); cudaStreamDestroy(ctx->side[i]); }
+        if (ctx->ev_tree[i]) cudaEventDestroy(ctx->ev_tree[i]);
+        if (ctx->ev_roll[i]) cudaEventDestroy(ctx->ev_roll[i]);
+    }
+    if (ctx->q_head.p) cudaFree(ctx->q_head.p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return DIEE_OK;
@@ -173,7 +187,7 @@ int32_t diee_bg_playout_dev(diee_ctx *ctx, const diee_bg_state *starts, int32_t 
     CU(cudaSetDevice(ctx->device));
     if (n == 0) return DIEE_OK;
     int nl = 0;
-    RESERVE(ctx->q_head, sizeof(unsigned long long));
+    RESERVE(ctx->q_head, sizeof(unsigned long long) * 8);
     CU(launch_bg_playout(ctx->stream, starts, n, seed, first_game_id, round_limit, winners_out, plies_out, finals_out,
                          (unsigned long long *)ctx->q_head.p, &nl));
     ctx->launches += nl;
@@ -316,9 +330,11 @@ int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *state
     if (rc != DIEE_OK) return rc;
     PoolPtrs pp{ctx->p_states.p, (int32_t *)ctx->p_parent.p, (float *)ctx->p_visits.p, (float *)ctx->p_value.p,
                 (uint32_t *)ctx->p_action.p, (uint32_t *)ctx->p_nmoves.p, (int32_t *)ctx->p_nnodes.p,
-                (int32_t *)ctx->p_simnode.p, ctx->p_finals.p, nullptr};
-    RESERVE(ctx->q_head, sizeof(unsigned long long));
-    pp.queue_head = (unsigned long long *)ctx->q_head.p;
+                (int32_t *)ctx->p_simnode.p, ctx->p_finals.p};
+    RESERVE(ctx->q_head, sizeof(unsigned long long) * 8);
+    SearchPipe pipe;
+    for (int i = 0; i < SEARCH_SLICES; ++i) { pipe.side[i] = ctx->side[i]; pipe.tree_done[i] = ctx->ev_tree[i]; pipe.roll_done[i] = ctx->ev_roll[i]; }
+    pipe.queue_heads = (unsigned long long *)ctx->q_head.p;
     const size_t pairs = (size_t)cfg->iterations * (size_t)n;
     CU(cudaMemsetAsync(ctx->p_simnode.p, 0xFF, sizeof(int32_t) * pairs, ctx->stream));
     CU(cudaMemsetAsync(ctx->p_finals.p, 0, state_size(game_kind) * pairs, ctx->stream));
@@ -328,7 +344,7 @@ int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *state
         RESERVE(ctx->s_best, sizeof(uint32_t) * (size_t)n);
         best32 = (uint32_t *)ctx->s_best.p;
     }
-    CU(launch_mcts_search(ctx->stream, game_kind, states, n, players, *cfg, seed, first_game_id, epoch, pp,
+    CU(launch_mcts_search(ctx->stream, game_kind, states, n, players, *cfg, seed, first_game_id, epoch, pp, pipe,
                           (const float *)ctx->ln_table.p, best32, status_out, stats_dev, &nl));
     ctx->launches += nl;
     if (game_kind == DIEE_GAME_TICTACTOE) {

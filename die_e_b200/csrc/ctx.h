@@ -25,7 +25,10 @@ struct diee_ctx {
     // pure-MCTS node pool (HBM resident, reused between searches)
     DevBuf p_states, p_parent, p_visits, p_value, p_action, p_nmoves, p_nnodes, p_simnode, p_finals, ln_table;
     uint32_t ln_table_n = 0;
-    DevBuf q_head;  // job queue head of the persistent lane kernel (lane_kernels.cu)
+    DevBuf q_head;  // job queue heads of the persistent lane kernel (lane_kernels.cu)
+    // side streams / events of the sliced search (mcts_kernels.cu launch_typed)
+    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_tree[4] = {nullptr, nullptr, nullptr, nullptr}, ev_roll[4] = {nullptr, nullptr, nullptr, nullptr};
     // AlphaZero search arena + per-iteration batch buffers (alpha.cu)
     DevBuf a_state, a_parent, a_first, a_nchild, a_visits, a_value, a_prior, a_action, a_nnodes, a_selg, a_seln, a_status,
         a_any, a_batch, a_policy, a_valueout, a_dir, a_states_in, a_ids_in, a_root_ids, a_root_moves, a_root_visits,

@@ -43,6 +43,7 @@ struct LaneJob {
     // PLAYOUT (C2): item = game index; ROLLOUT (T4): item = game * iterations + iteration
     long long n_items;
     uint32_t iterations;  // ROLLOUT only
+    uint32_t it_begin, it_count;  // ROLLOUT: the slice of iterations this launch covers (items = games x it_count)
     uint32_t limit;
     uint64_t seed;
     uint32_t first_game_id, epoch;
@@ -115,11 +116,13 @@ lane_run_kernel(LaneJob job) {
             if (first + __popc(idle) >= job.n_items) queue_open = false;
             if (need == PATH_DONE) {
                 item = first + __popc(idle & ((1u << lane) - 1u));
-                if (item < job.n_items) {
+                if (item >= job.n_items) item = -1;
+                if (item >= 0) {
                     k = 0;
                     if (ROLLOUT) {
-                        const uint32_t gm = (uint32_t)(item / job.iterations);
-                        const uint32_t it = (uint32_t)(item - (long long)gm * job.iterations);
+                        const uint32_t gm = (uint32_t)(item / job.it_count);
+                        const uint32_t it = job.it_begin + (uint32_t)(item - (long long)gm * job.it_count);
+                        item = (long long)gm * job.iterations + it;  // from here on: the (game, iteration) pair
                         const int node = job.sim_node[item];
                         if (node >= 0 && job.limit > 0) {  // node < 0: the iteration ended on a terminal leaf, no rollout
                             lane_load_state(g, job.states + (size_t)gm * (job.iterations + 1) + node);
@@ -243,28 +246,29 @@ cudaError_t launch_bg_playout(cudaStream_t st, const diee_bg_state *starts, int 
     return launch_lane_job<false>(st, job, launches);
 }
 
-cudaError_t launch_bg_rollouts(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id,
-                               uint32_t epoch, const PoolPtrs &pp, diee_search_stats *stats_out, int *launches) {
-    const long long pairs = (long long)n_games * cfg.iterations;
-    if (pairs <= 0 || cfg.simulate_round_limit == 0) return cudaSuccess;
+cudaError_t launch_bg_rollouts(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, uint32_t it_begin, uint32_t it_end,
+                               uint64_t seed, uint32_t first_game_id, uint32_t epoch, const PoolPtrs &pp,
+                               unsigned long long *queue_head, int *launches) {
+    const long long items = (long long)n_games * (it_end - it_begin);
+    if (items <= 0 || cfg.simulate_round_limit == 0) return cudaSuccess;
     LaneJob job{};
-    job.n_items = pairs; job.iterations = cfg.iterations; job.limit = cfg.simulate_round_limit; job.seed = seed;
-    job.first_game_id = first_game_id; job.epoch = epoch;
+    job.n_items = items; job.iterations = cfg.iterations; job.it_begin = it_begin; job.it_count = it_end - it_begin;
+    job.limit = cfg.simulate_round_limit; job.seed = seed; job.first_game_id = first_game_id; job.epoch = epoch;
     job.states = static_cast<const diee_bg_state *>(pp.states); job.sim_node = pp.sim_node;
     job.finals = static_cast<diee_bg_state *>(pp.finals);
-    job.next_item = pp.queue_head;
-    cudaError_t e = launch_lane_job<true>(st, job, launches);
-    if (e != cudaSuccess) return e;
-    if (stats_out) {
-        bg_rollout_count_kernel<<<(n_games + 127) / 128, 128, 0, st>>>(n_games, cfg.iterations, cfg.simulate_round_limit, pp.sim_node, stats_out);
-        if (launches) *launches += 1;
-        e = cudaGetLastError();
-    }
-    return e;
+    job.next_item = queue_head;
+    return launch_lane_job<true>(st, job, launches);
+}
+
+cudaError_t launch_bg_rollout_count(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, const PoolPtrs &pp,
+                                    diee_search_stats *stats_out, int *launches) {
+    if (!stats_out || n_games <= 0) return cudaSuccess;
+    bg_rollout_count_kernel<<<(n_games + 127) / 128, 128, 0, st>>>(n_games, cfg.iterations, cfg.simulate_round_limit, pp.sim_node, stats_out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
 }
 
 }  // namespace diee
-
 #ifdef DIEE_LANE_STATS
 extern "C" int diee_debug_lane_stats(unsigned long long *out16, int reset) {
     cudaMemcpyFromSymbol(out16, diee::g_lane_stats, sizeof(unsigned long long) * 16);

@@ -16,7 +16,14 @@ struct PoolPtrs {
     int32_t *n_nodes;
     int32_t *sim_node;
     void *finals;
-    unsigned long long *queue_head;  // job queue head of the persistent lane kernel
+};
+
+// side streams of a split search: rollouts of one slice of iterations run beside the tree kernel of the next
+constexpr int SEARCH_SLICES = 4;
+struct SearchPipe {
+    cudaStream_t side[SEARCH_SLICES];
+    cudaEvent_t tree_done[SEARCH_SLICES], roll_done[SEARCH_SLICES];
+    unsigned long long *queue_heads;  // SEARCH_SLICES job queue heads of the persistent lane kernel
 };
 
 cudaError_t launch_bg_valid_moves(cudaStream_t st, const diee_bg_state *states, int n, diee_move *moves_out,
@@ -26,14 +33,17 @@ cudaError_t launch_bg_playout(cudaStream_t st, const diee_bg_state *starts, int 
                               int round_limit, int8_t *winners_out, int32_t *plies_out, diee_bg_state *finals_out,
                               unsigned long long *queue_head, int *launches);
 // every deferred rollout of a split backgammon search, one lane per (game, iteration)  (lane_kernels.cu)
-cudaError_t launch_bg_rollouts(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id,
-                               uint32_t epoch, const PoolPtrs &pp, diee_search_stats *stats_out, int *launches);
+cudaError_t launch_bg_rollouts(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, uint32_t it_begin, uint32_t it_end,
+                               uint64_t seed, uint32_t first_game_id, uint32_t epoch, const PoolPtrs &pp,
+                               unsigned long long *queue_head, int *launches);
+cudaError_t launch_bg_rollout_count(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, const PoolPtrs &pp,
+                                    diee_search_stats *stats_out, int *launches);
 cudaError_t launch_bg_encode_moves(cudaStream_t st, const diee_bg_state *states, const diee_move *moves, int n, uint16_t *ids_out);
 cudaError_t launch_bg_decode_moves(cudaStream_t st, const diee_bg_state *states, const uint16_t *ids, int n, diee_move *moves_out);
 cudaError_t launch_bg_encode_states(cudaStream_t st, const diee_bg_state *states, int n, float *out);
 cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots, int n, const int8_t *players,
                                const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
-                               const PoolPtrs &pp, const float *ln_table, uint32_t *best_out, int32_t *status_out,
-                               diee_search_stats *stats_out, int *launches);
+                               const PoolPtrs &pp, const SearchPipe &pipe, const float *ln_table, uint32_t *best_out,
+                               int32_t *status_out, diee_search_stats *stats_out, int *launches);
 
 }  // namespace diee

@@ -12,9 +12,11 @@
 // IEEE f32 with explicit round-to-nearest intrinsics (no FMA contraction, no fast division) and
 // ln(parent visits) comes from a host-built table of (float)log((double)n): visits are
 // integer-valued, so this is bit-identical to the oracle.
+#include <cstdlib>
 #include <type_traits>
 
 #include "bg_device.cuh"
+#include "bg_lane.cuh"
 #include "launchers.h"
 
 namespace diee {
@@ -23,9 +25,52 @@ constexpr int MCTS_WARPS_PER_CTA = 4;
 constexpr int NO_WINNER = 2;
 
 // ---------------- game policies ----------------
+// The warp's board as the lane engine's bit planes (warp-uniform: every lane holds the whole board).
+__device__ __forceinline__ void bg_to_planes(const BgWarp &g, lane::LaneBoard &b) {
+    const int a = abs(g.v);
+    uint32_t neg[4], pos[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        neg[k] = __ballot_sync(FULL, g.v < 0 && ((a >> k) & 1)) & M24;
+        pos[k] = __ballot_sync(FULL, g.v > 0 && ((a >> k) & 1)) & M24;
+    }
+    if (g.player < 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { b.own[k] = neg[k]; b.opp[k] = pos[k]; }
+        b.bar_own = g.bar0; b.bar_opp = g.bar1; b.off_own = g.off0; b.off_opp = g.off1;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { b.own[k] = lane::l_rev24(pos[k]); b.opp[k] = lane::l_rev24(neg[k]); }
+        b.bar_own = g.bar1; b.bar_opp = g.bar0; b.off_own = g.off1; b.off_opp = g.off0;
+    }
+    b.roll0 = g.roll0; b.roll1 = g.roll1; b.player = g.player; b.second = g.second;
+}
+
 struct BgGame {
     using State = diee_bg_state;
     BgWarp g;
+    // Number of legal plays and (k >= 0) the k-th of them.  Contact play and bar entries are counted in
+    // closed form by the lane engine (bg_lane.cuh) -- ~10x fewer instructions than building the list --
+    // redundantly on every lane; positions in the bear-off regime build the list cooperatively.
+    __device__ __forceinline__ int count_and_kth(WarpSlab &slab, int lane, bool &ovf, int k, uint32_t &seq) const {
+        lane::LaneBoard b;
+        bg_to_planes(g, b);
+        const int hi = max(g.roll0, g.roll1), lo = min(g.roll0, g.roll1);
+        lane::LaneMasks m;
+        const bool closed = lane::l_closed_applies(b, m, lo, hi);
+        if (closed || b.bar_own > 0 || m.own1 == 0) {
+            lane::LaneGen gen;
+            gen.U = 0;
+            if (b.bar_own > 0) lane::l_movegen_bar(b, m, lo, hi, gen);
+            else if (m.own1 != 0) lane::l_movegen_closed(b, m, lo, hi, gen);
+            if (k >= 0 && k < gen.U) seq = lane::l_play_to_seq(lane::l_pick(b, gen, nullptr, 0, k), g.player);
+            return gen.U;
+        }
+        const int U = bg_movegen(g, slab, lane, ovf);
+        if (k >= 0 && k < U) seq = slab.raw[k];
+        __syncwarp();
+        return U;
+    }
     __device__ __forceinline__ void load(const State *s, int lane) { bg_load(g, s, lane); }
     __device__ __forceinline__ void store(State *s, int lane) const { bg_store(g, s, lane); }
     __device__ __forceinline__ int winner() const { const int w = bg_winner(g); return w == 0 ? NO_WINNER : w; }
@@ -61,6 +106,11 @@ struct TttGame {  // tictactoe/mod.rs; the whole state is warp-uniform
         return ((xm | om) & 0x1FFu) == 0x1FFu ? 0 : NO_WINNER;
     }
     __device__ __forceinline__ int movegen(WarpSlab &, int, bool &) const { return __popc(~(xm | om) & 0x1FFu); }
+    __device__ __forceinline__ int count_and_kth(WarpSlab &slab, int, bool &, int k, uint32_t &seq) const {
+        const int U = __popc(~(xm | om) & 0x1FFu);
+        if (k >= 0 && k < U) seq = move_at(slab, k);
+        return U;
+    }
     __device__ __forceinline__ uint32_t move_at(const WarpSlab &, int k) const {  // k-th empty cell ascending :36-44
         uint32_t e = ~(xm | om) & 0x1FFu;
         for (int i = 0; i < k; ++i) e &= e - 1;
@@ -124,9 +174,9 @@ __device__ __forceinline__ float rollout_plies(G &game, WarpSlab &slab, int lane
 template <class G, bool SPLIT>
 __global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32)
 mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int8_t *__restrict__ players,
-                   diee_mcts_cfg cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch, Pool pool,
-                   const float *__restrict__ ln_table, uint32_t *__restrict__ best_out, int32_t *__restrict__ status_out,
-                   diee_search_stats *__restrict__ stats_out) {
+                   diee_mcts_cfg cfg, uint32_t it_begin, uint32_t it_end, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
+                   Pool pool, const float *__restrict__ ln_table, uint32_t *__restrict__ best_out,
+                   int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out) {
     __shared__ WarpSlab slabs[MCTS_WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gidx = blockIdx.x * MCTS_WARPS_PER_CTA + wib;
@@ -145,26 +195,42 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     const bool check_current = cfg.mode_flags & DIEE_MODE_ROLLOUT_CHECK_CURRENT;
     const bool pass_child = cfg.mode_flags & DIEE_MODE_PASS_CHILD;
 
+    // The search may be cut into slices of iterations [it_begin, it_end) (one launch each, so that the
+    // rollouts of a slice can run beside the tree work of the next): everything a later slice needs is in
+    // the pool; n_nodes == 0 marks a terminal root.
     G game;
-    game.load(roots + gidx, lane);
     uint32_t best = SEQ_EMPTY;
     int status = DIEE_OK;
     int n_nodes = 0;
     unsigned long long plies = 0;
     uint32_t sel_levels = 0, sel_children = 0, terminal_leaves = 0;
     bool ovf = false;
+    const bool last_slice = it_end >= cfg.iterations;
 
-    if (game.winner() == NO_WINNER) {  // simple_mcts.rs:12-14
-        // root = add_node(state)  (Node::new computes the legal moves eagerly, node.rs:50)
-        game.store(st, lane);
-        int U = game.movegen(slab, lane, ovf);
-        __syncwarp();
-        if (U == 0 && pass_child) U = 1;
-        if (lane == 0) { parent[0] = -1; visits[0] = 0.f; value[0] = 0.f; action[0] = SEQ_EMPTY; nm[0] = ((uint32_t)U << 16) | (uint32_t)U; }
-        n_nodes = 1;
-        __syncwarp();
+    if (it_begin == 0) {
+        game.load(roots + gidx, lane);
+        if (game.winner() == NO_WINNER) {  // simple_mcts.rs:12-14
+            // root = add_node(state)  (Node::new computes the legal moves eagerly, node.rs:50)
+            game.store(st, lane);
+            uint32_t unused = SEQ_EMPTY;
+            int U = game.count_and_kth(slab, lane, ovf, -1, unused);
+            if (U == 0 && pass_child) U = 1;
+            if (lane == 0) { parent[0] = -1; visits[0] = 0.f; value[0] = 0.f; action[0] = SEQ_EMPTY; nm[0] = ((uint32_t)U << 16) | (uint32_t)U; }
+            n_nodes = 1;
+            __syncwarp();
+        }
+    } else {
+        n_nodes = pool.n_nodes[gidx];
+        status = status_out[gidx];
+        if (stats_out) {
+            const diee_search_stats ss = stats_out[gidx];
+            plies = ss.rollout_plies; sel_levels = ss.select_levels; sel_children = ss.select_children; terminal_leaves = ss.terminal_leaves;
+        }
+    }
 
-        for (uint32_t it = 0; it < cfg.iterations; ++it) {
+    if (n_nodes > 0) {
+        if (status == DIEE_OK)
+        for (uint32_t it = it_begin; it < it_end; ++it) {
             // ---- select_leaf_node :88-94 ----
             int cur = 0;
             uint32_t nmv;
@@ -213,16 +279,15 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
             } else {
                 if (nunt == 0) { status = DIEE_ERR_NO_MOVES_PANIC; break; }  // node.rs:119-121 (Q6)
                 // ---- Node::expand node.rs:118-137: pop the LAST untried move ----
-                const int U = game.movegen(slab, lane, ovf);
-                const uint32_t seq = U == 0 ? SEQ_EMPTY : game.move_at(slab, nunt - 1);
-                __syncwarp();
+                uint32_t seq = SEQ_EMPTY;  // stays EMPTY_MOVE for the pass child of a no-move node
+                game.count_and_kth(slab, lane, ovf, nunt - 1, seq);
                 const int child = n_nodes;
                 uint32_t blk[4];
                 philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)child, gid, DIEE_STREAM_EXPAND, epoch, blk);
                 game.step(seq, die_of(blk[0]), die_of(blk[1]), lane);
                 game.store(st + child, lane);
-                int Uc = game.movegen(slab, lane, ovf);  // Node::new for the child
-                __syncwarp();
+                uint32_t unused = SEQ_EMPTY;
+                int Uc = game.count_and_kth(slab, lane, ovf, -1, unused);  // Node::new for the child
                 if (Uc == 0 && pass_child) Uc = 1;
                 if (lane == 0) {
                     nm[cur] = ((uint32_t)nmoves << 16) | (uint32_t)(nunt - 1);
@@ -256,7 +321,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
             __syncwarp();
         }
 
-        if (status == DIEE_OK) {  // select_most_visits :71-86 (last maximum)
+        if (status == DIEE_OK && last_slice) {  // select_most_visits :71-86 (last maximum)
             float bv = -INFINITY;
             int bi = -1;
             for (int c0 = 1; c0 < n_nodes; c0 += 32) {
@@ -278,7 +343,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     }
     if (ovf && status == DIEE_OK) status = DIEE_ERR_OVERFLOW;
     if (lane == 0) {
-        best_out[gidx] = best;
+        if (last_slice) best_out[gidx] = best;
         status_out[gidx] = status;
         pool.n_nodes[gidx] = n_nodes;
         if (stats_out) {
@@ -322,42 +387,66 @@ static inline int mcts_grid(int n) { return (n + MCTS_WARPS_PER_CTA - 1) / MCTS_
 template <class G>
 static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const int8_t *players, const diee_mcts_cfg &cfg,
                                 uint64_t seed, uint32_t first_game_id, uint32_t epoch, const Pool &pool, const PoolPtrs &pp,
-                                const float *ln_table, uint32_t *best_out, int32_t *status_out, diee_search_stats *stats_out,
-                                int *launches) {
+                                const SearchPipe &pipe, const float *ln_table, uint32_t *best_out, int32_t *status_out,
+                                diee_search_stats *stats_out, int *launches) {
     const bool split = !(cfg.mode_flags & DIEE_MODE_ROLLOUT_CHECK_CURRENT);
     const typename G::State *r = static_cast<const typename G::State *>(roots);
-    if (split) {
-        mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
-            r, n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
-        if constexpr (std::is_same<G, BgGame>::value) {  // backgammon: one lane per rollout (lane_kernels.cu)
-            *launches = 1;
-            return launch_bg_rollouts(st, n, cfg, seed, first_game_id, epoch, pp, stats_out, launches);
-        } else {
-            const long long pairs = (long long)n * cfg.iterations;
-            const long long blocks = (pairs + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA;
-            rollout_kernel<G><<<(unsigned)blocks, MCTS_WARPS_PER_CTA * 32, 0, st>>>(n, cfg, seed, first_game_id, epoch, pool,
-                                                                                 players, status_out, stats_out);
-        }
-        *launches = 2;
-    } else {
+    cudaError_t e;
+    if (!split) {
         mcts_search_kernel<G, false><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
-            r, n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
+            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
         *launches = 1;
+        return cudaGetLastError();
     }
-    return cudaGetLastError();
+    if constexpr (std::is_same<G, BgGame>::value) {
+        // backgammon: the rollouts are one lane each (lane_kernels.cu) and never feed back into the tree
+        // (quirk Q5), so the search runs as slices of iterations: tree kernel of slice s on the caller's
+        // stream, rollouts of slice s on a side stream beside the tree kernel of slice s + 1.
+        // Measured on B200 (1,024 games x 100 iterations): 1 slice 3.39 ms, 2 slices 3.36 ms, 4 slices 3.96 ms per
+        // search -- the latency-bound tree kernel loses as much to sharing the SMs as the overlap wins, so the
+        // default is one slice; DIEE_SEARCH_SLICES keeps the experiment reproducible.
+        uint32_t slices = 1;
+        if (const char *ev = getenv("DIEE_SEARCH_SLICES")) slices = (uint32_t)atoi(ev);
+        if (slices < 1u) slices = 1u;
+        if (slices > (uint32_t)SEARCH_SLICES) slices = (uint32_t)SEARCH_SLICES;
+        if (slices > cfg.iterations) slices = cfg.iterations;
+        for (uint32_t s = 0; s < slices; ++s) {
+            const uint32_t a = (uint32_t)((uint64_t)cfg.iterations * s / slices), b = (uint32_t)((uint64_t)cfg.iterations * (s + 1) / slices);
+            mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
+                r, n, players, cfg, a, b, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
+            *launches += 1;
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(pipe.tree_done[s], st)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(pipe.side[s], pipe.tree_done[s], 0)) != cudaSuccess) return e;
+            if ((e = launch_bg_rollouts(pipe.side[s], n, cfg, a, b, seed, first_game_id, epoch, pp, pipe.queue_heads + s, launches)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(pipe.roll_done[s], pipe.side[s])) != cudaSuccess) return e;
+        }
+        for (uint32_t s = 0; s < slices; ++s)
+            if ((e = cudaStreamWaitEvent(st, pipe.roll_done[s], 0)) != cudaSuccess) return e;
+        return launch_bg_rollout_count(st, n, cfg, pp, stats_out, launches);
+    } else {
+        mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
+            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
+        const long long pairs = (long long)n * cfg.iterations;
+        const long long blocks = (pairs + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA;
+        rollout_kernel<G><<<(unsigned)blocks, MCTS_WARPS_PER_CTA * 32, 0, st>>>(n, cfg, seed, first_game_id, epoch, pool, players,
+                                                                             status_out, stats_out);
+        *launches = 2;
+        return cudaGetLastError();
+    }
 }
 
 cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots, int n, const int8_t *players,
                                const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
-                               const PoolPtrs &pp, const float *ln_table, uint32_t *best_out, int32_t *status_out,
-                               diee_search_stats *stats_out, int *launches) {
+                               const PoolPtrs &pp, const SearchPipe &pipe, const float *ln_table, uint32_t *best_out,
+                               int32_t *status_out, diee_search_stats *stats_out, int *launches) {
     *launches = 0;
     if (n <= 0) return cudaSuccess;
     Pool pool{pp.states, pp.parent, pp.visits, pp.value, pp.action, pp.nmoves, pp.n_nodes, pp.sim_node, pp.finals};
     if (game_kind == DIEE_GAME_BACKGAMMON)
-        return launch_typed<BgGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, pp, ln_table, best_out,
+        return launch_typed<BgGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, pp, pipe, ln_table, best_out,
                                     status_out, stats_out, launches);
-    return launch_typed<TttGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, pp, ln_table, best_out,
+    return launch_typed<TttGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, pp, pipe, ln_table, best_out,
                                  status_out, stats_out, launches);
 }
 

@@ -215,17 +215,18 @@ __global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32
 
 template <bool ROLLOUT>
 static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) {
-    job.lag_weight = 0;
-    if (const char *e = getenv("DIEE_LANE_LAG")) job.lag_weight = atoi(e);
-    static int sms = 0;
+    // tuning knobs, read once: waiting-time weight of the vote and resident CTAs (x 4 warps) per SM.  Measured on
+    // B200 with 102,400 rollouts: 6 CTAs/SM and weight 0 are best (profiles/r01_lane_sweep.txt).
+    static int sms = 0, lag_weight = 0, blocks_per_sm = 6;
     if (sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
+        if (const char *e = getenv("DIEE_LANE_LAG")) lag_weight = atoi(e);
+        if (const char *e = getenv("DIEE_LANE_BLOCKS_PER_SM")) blocks_per_sm = atoi(e) > 0 ? atoi(e) : 6;
     }
-    int blocks_per_sm = 6;  // x 4 warps
-    if (const char *e = getenv("DIEE_LANE_BLOCKS_PER_SM")) blocks_per_sm = atoi(e);
+    job.lag_weight = lag_weight;
     long long blocks = (job.n_items + LANE_CTA - 1) / LANE_CTA;
     if (blocks > (long long)sms * blocks_per_sm) blocks = (long long)sms * blocks_per_sm;
     cudaError_t e = cudaMemsetAsync(job.next_item, 0, sizeof(unsigned long long), st);

@@ -52,7 +52,8 @@ struct BgGame {
     // Number of legal plays and (k >= 0) the k-th of them.  Contact play and bar entries are counted in
     // closed form by the lane engine (bg_lane.cuh) -- ~10x fewer instructions than building the list --
     // redundantly on every lane; positions in the bear-off regime build the list cooperatively.
-    __device__ __forceinline__ int count_and_kth(WarpSlab &slab, int lane, bool &ovf, int k, uint32_t &seq) const {
+    // (one out-of-line copy: the tree kernel calls it three times per iteration and is instruction-fetch bound)
+    __device__ __noinline__ int count_and_kth(WarpSlab &slab, int lane, bool &ovf, int k, uint32_t &seq) const {
         lane::LaneBoard b;
         bg_to_planes(g, b);
         const int hi = max(g.roll0, g.roll1), lo = min(g.roll0, g.roll1);
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32)
 mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int8_t *__restrict__ players,
                    diee_mcts_cfg cfg, uint32_t it_begin, uint32_t it_end, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
                    Pool pool, const float *__restrict__ ln_table, uint32_t *__restrict__ best_out,
-                   int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out) {
+                   int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out, bool slab_in_smem) {
     __shared__ WarpSlab slabs[MCTS_WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gidx = blockIdx.x * MCTS_WARPS_PER_CTA + wib;
@@ -184,10 +185,28 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     WarpSlab &slab = slabs[wib];
     const int cap = (int)cfg.iterations + 1;
     const size_t base = (size_t)gidx * cap;
-    typename G::State *st = reinterpret_cast<typename G::State *>(pool.states) + base;
-    int32_t *parent = pool.parent + base;
-    float *visits = pool.visits + base, *value = pool.value + base;
-    uint32_t *action = pool.action + base, *nm = pool.nmoves + base;
+    // The game's node slab.  While the kernel runs it lives in SHARED memory when it fits (the search is a
+    // chain of dependent reads of parent / visits / value / move counts / states -- a few dozen cycles each
+    // from shared memory, several hundred from L2) and is written back to the HBM pool, coalesced, at the
+    // end; otherwise the kernel works on the pool directly.
+    extern __shared__ __align__(16) unsigned char slab_mem[];
+    typename G::State *gst = reinterpret_cast<typename G::State *>(pool.states) + base;
+    int32_t *gparent = pool.parent + base;
+    float *gvisits = pool.visits + base, *gvalue = pool.value + base;
+    uint32_t *gnm = pool.nmoves + base;
+    typename G::State *st = gst;
+    int32_t *parent = gparent;
+    float *visits = gvisits, *value = gvalue;
+    uint32_t *nm = gnm;
+    if (slab_in_smem) {
+        unsigned char *mine = slab_mem + (size_t)wib * cap * (sizeof(typename G::State) + 16);
+        st = reinterpret_cast<typename G::State *>(mine);
+        parent = reinterpret_cast<int32_t *>(mine + (size_t)cap * sizeof(typename G::State));
+        visits = reinterpret_cast<float *>(parent + cap);
+        value = visits + cap;
+        nm = reinterpret_cast<uint32_t *>(value + cap);
+    }
+    uint32_t *action = pool.action + base;
     int32_t *sim_node = pool.sim_node + (size_t)gidx * cfg.iterations;
     typename G::State *finals = reinterpret_cast<typename G::State *>(pool.finals) + (size_t)gidx * cfg.iterations;
     const int player = players[gidx];
@@ -222,6 +241,12 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     } else {
         n_nodes = pool.n_nodes[gidx];
         status = status_out[gidx];
+        if (slab_in_smem) {
+            for (int i = lane; i < n_nodes; i += 32) { parent[i] = gparent[i]; visits[i] = gvisits[i]; value[i] = gvalue[i]; nm[i] = gnm[i]; }
+            const int words = n_nodes * (int)(sizeof(typename G::State) / 4);
+            for (int i = lane; i < words; i += 32) reinterpret_cast<uint32_t *>(st)[i] = reinterpret_cast<const uint32_t *>(gst)[i];
+            __syncwarp();
+        }
         if (stats_out) {
             const diee_search_stats ss = stats_out[gidx];
             plies = ss.rollout_plies; sel_levels = ss.select_levels; sel_children = ss.select_children; terminal_leaves = ss.terminal_leaves;
@@ -341,6 +366,12 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
             if (bi >= 0) best = action[bi];
         }
     }
+    if (slab_in_smem) {
+        __syncwarp();
+        for (int i = lane; i < n_nodes; i += 32) { gparent[i] = parent[i]; gvisits[i] = visits[i]; gvalue[i] = value[i]; gnm[i] = nm[i]; }
+        const int words = n_nodes * (int)(sizeof(typename G::State) / 4);
+        for (int i = lane; i < words; i += 32) reinterpret_cast<uint32_t *>(gst)[i] = reinterpret_cast<const uint32_t *>(st)[i];
+    }
     if (ovf && status == DIEE_OK) status = DIEE_ERR_OVERFLOW;
     if (lane == 0) {
         if (last_slice) best_out[gidx] = best;
@@ -392,9 +423,17 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
     const bool split = !(cfg.mode_flags & DIEE_MODE_ROLLOUT_CHECK_CURRENT);
     const typename G::State *r = static_cast<const typename G::State *>(roots);
     cudaError_t e;
+    // node slabs of the CTA's games in shared memory when they fit
+    size_t slab_bytes = (size_t)MCTS_WARPS_PER_CTA * (cfg.iterations + 1) * (sizeof(typename G::State) + 16);
+    const bool in_smem = slab_bytes <= 160 * 1024;
+    if (!in_smem) slab_bytes = 0;
+    if (in_smem) {
+        if ((e = cudaFuncSetAttribute(mcts_search_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(mcts_search_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+    }
     if (!split) {
-        mcts_search_kernel<G, false><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
-            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
+        mcts_search_kernel<G, false><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
+            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem);
         *launches = 1;
         return cudaGetLastError();
     }
@@ -412,8 +451,8 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         if (slices > cfg.iterations) slices = cfg.iterations;
         for (uint32_t s = 0; s < slices; ++s) {
             const uint32_t a = (uint32_t)((uint64_t)cfg.iterations * s / slices), b = (uint32_t)((uint64_t)cfg.iterations * (s + 1) / slices);
-            mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
-                r, n, players, cfg, a, b, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
+            mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
+                r, n, players, cfg, a, b, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem);
             *launches += 1;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if ((e = cudaEventRecord(pipe.tree_done[s], st)) != cudaSuccess) return e;
@@ -425,8 +464,8 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
             if ((e = cudaStreamWaitEvent(st, pipe.roll_done[s], 0)) != cudaSuccess) return e;
         return launch_bg_rollout_count(st, n, cfg, pp, stats_out, launches);
     } else {
-        mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, 0, st>>>(
-            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out);
+        mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
+            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem);
         const long long pairs = (long long)n * cfg.iterations;
         const long long blocks = (pairs + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA;
         rollout_kernel<G><<<(unsigned)blocks, MCTS_WARPS_PER_CTA * 32, 0, st>>>(n, cfg, seed, first_game_id, epoch, pool, players,

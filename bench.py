@@ -116,6 +116,22 @@ def midgame_states(ctx, ffi, first_gid, n):
     return out
 
 
+def ncu_traffic(summary_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summary of the
+    dominant kernel (profiles/), or None.  The capture is of the default configuration of that workload."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", summary_name)
+    if not os.path.exists(path):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, seen = 0.0, 0
+    for line in open(path):
+        if line.startswith("dram__bytes_read.sum") or line.startswith("dram__bytes_write.sum"):
+            unit = line.split("[")[1].split("]")[0]
+            total += float(line.split("=")[1].replace(",", "")) * scale.get(unit, 1.0)
+            seen += 1
+    return total if seen == 2 else None
+
+
 def bsim_bytes(stats, n_sims):
     """algorithmic HBM bytes per simulation for the SoA pool:
     select: per level 8 B (move counts + visits of the node) + 12 B per child (parent, visits, value);
@@ -266,6 +282,7 @@ def run_ours(args, rank, world):
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     units = 0.0
     stats_acc = None
+    split_ms = []  # (tree kernel ms, rollout kernel ms) per timed step, from CUDA events inside the library
     barrier()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -278,6 +295,8 @@ def run_ours(args, rank, world):
             units += float(d_plies.sum().item())
         elif args.workload == "mcts":
             evs[i][1].synchronize()
+            if args.rollout == "ref_exact":
+                split_ms.append(ctx.search_timing())
             st = d_stats.cpu().numpy().view(ffi.SEARCH_STATS).reshape(-1)
             stats_acc = st if stats_acc is None else np.concatenate([stats_acc, st])
             units += units_per_step
@@ -331,14 +350,23 @@ def run_ours(args, rank, world):
     out = None
     if rank == 0:
         value = units / (dev_ms / 1e3)
+        dominant = None
         if args.workload == "mcts":
             n_sims_local = G * args.iterations * args.steps
             b_sim = bsim_bytes(stats_acc, n_sims_local)
-            alg_bytes = b_sim * G * args.iterations  # per launch
             plies_per_sim = float(stats_acc["rollout_plies"].sum()) / n_sims_local
-            extra = {"bytes_per_simulation": round(b_sim, 1), "rollout_plies_per_simulation": round(plies_per_sim, 2),
+            extra = {"tree_bytes_per_simulation": round(b_sim, 1), "rollout_plies_per_simulation": round(plies_per_sim, 2),
                      "rollout_plies_per_sec": round(value * plies_per_sim, 1),
                      "mean_select_depth": round(float(stats_acc["select_levels"].sum()) / n_sims_local, 3)}
+            if split_ms:
+                tree_ms = float(np.mean([a for a, _ in split_ms]))
+                roll_ms = float(np.mean([b for _, b in split_ms]))
+                extra.update(tree_kernel_ms=round(tree_ms, 4), rollout_kernel_ms=round(roll_ms, 4))
+                # dominant kernel = the rollouts: SURVEY 8d(1) 64 B per ply x the plies one launch plays
+                alg_bytes = 64.0 * plies_per_sim * G * args.iterations
+                dominant = ("lane_run_kernel<true> (all rollouts of one search, one lane each)", roll_ms)
+            else:
+                alg_bytes = b_sim * G * args.iterations  # per launch
         elif args.workload == "playout":
             alg_bytes = 64.0 * units / args.steps / world  # 32 B read + 32 B write per ply
             extra = {"bytes_per_ply": 64, "games_per_sec": round(G * world * args.steps / (dev_ms / 1e3), 1),
@@ -346,8 +374,11 @@ def run_ours(args, rank, world):
         else:
             alg_bytes = 0.0
             extra = {}
+        traffic = None
+        if args.workload == "mcts" and dominant and G == 1024 and args.iterations == 100 and args.round_limit == 400:
+            traffic = ncu_traffic("r01_lane_run_rollouts_v4_ncu_full_summary.txt")
         avg_launch_ms = float(np.mean(kern_ms))
-        achieved = alg_bytes / (avg_launch_ms / 1e3) / 1e9
+        achieved = alg_bytes / ((dominant[1] if dominant else avg_launch_ms) / 1e3) / 1e9
         roof = None
         if args.workload in ("alpha", "selfplay"):
             burst, sustained, tsrc = tensor_peaks()
@@ -376,10 +407,15 @@ def run_ours(args, rank, world):
                        "max over ranks; L2 flushed (256 MiB fill) between timed steps", "wall_s": round(t_wall, 3),
                        "parallelism": f"games sharded over {world} GPU(s), no collective", **extra},
             "roofline": roof or {"bound": "hbm", "achieved": round(achieved, 4), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": round(achieved / hbm_peak, 8), "traffic": None, "peak_source": peak_src,
-                         "kernel": "rollout_kernel<BgGame> + mcts_search_kernel<BgGame>" if args.workload == "mcts" else "bg_playout_kernel",
-                         "note": "the path is integer-issue/latency bound, not HBM bound: the whole rollout runs in "
-                                 "registers + shared memory (SURVEY 8d M-roofline (2)); see DESIGN.md and profiles/"},
+                         "frac": round(achieved / hbm_peak, 8), "traffic": traffic, "peak_source": peak_src,
+                         "kernel": (dominant[0] if dominant else "mcts_search_kernel<BgGame> (fused rollouts)") if args.workload == "mcts"
+                         else "lane_run_kernel<false> (whole games, one lane each)",
+                         "note": "achieved = 64 B per ply (32 B state in + 32 B out, SURVEY 8d(1)) x plies of one launch / that "
+                                 "kernel's CUDA-event time; in reference-exact rollouts the plies after BOTH sides have collected "
+                                 "everything (forced passes to the 400-ply cap, ~3/4 of them) are resolved in closed form.  The "
+                                 "path is integer-issue bound, not HBM bound: a game lives in one lane's registers from its first "
+                                 "ply to its last, so the real traffic is 64 B per GAME (`traffic`, ncu); the figures that track "
+                                 "kernel quality are warp instructions per played ply and lane utilisation (profiles/, DESIGN.md 4)"},
             "e2e": {"value": round(e2e_units / e2e_s, 1), "unit": unit, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world},
             "gpu_launches": int(launches), "clocks": clocks,

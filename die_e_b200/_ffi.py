@@ -44,7 +44,7 @@ SYMBOLS = [
     "diee_bg_playout", "diee_bg_playout_dev", "diee_bg_encode_moves", "diee_bg_decode_moves",
     "diee_bg_encode_states", "diee_bg_encode_states_dev", "diee_mcts_search", "diee_mcts_search_dev",
     "diee_net_create", "diee_net_destroy", "diee_net_param_count", "diee_net_forward", "diee_net_forward_dev",
-    "diee_dirichlet", "diee_alpha_search", "diee_alpha_search_dev", "diee_selfplay_run", "diee_net_eval_count",
+    "diee_search_timing", "diee_dirichlet", "diee_alpha_search", "diee_alpha_search_dev", "diee_selfplay_run", "diee_net_eval_count",
 ]
 
 
@@ -142,6 +142,12 @@ class Context:
 
     def launch_count(self):
         return int(lib().diee_launch_count(self._h))
+
+    def search_timing(self):
+        """(tree_ms, rollout_ms) of the last reference-exact backgammon search, from CUDA events on its stream"""
+        a, b = C.c_float(0), C.c_float(0)
+        self._chk(lib().diee_search_timing(self._h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
 
     # ---- env, host buffers ----
     def bg_valid_moves(self, states, want_ids=False):

@@ -42,6 +42,8 @@ int32_t diee_ctx_create(int32_t device, diee_ctx **out) {
             return DIEE_ERR_CUDA;
         }
     }
+    for (int i = 0; i < 3; ++i)
+        if (cudaEventCreate(&ctx->ev_time[i]) != cudaSuccess) { delete ctx; return DIEE_ERR_CUDA; }
     *out = ctx;
     return DIEE_OK;
 }
@@ -65,6 +67,8 @@ int32_t diee_ctx_destroy(diee_ctx *ctx) {
         if (ctx->ev_tree[i]) cudaEventDestroy(ctx->ev_tree[i]);
         if (ctx->ev_roll[i]) cudaEventDestroy(ctx->ev_roll[i]);
     }
+    for (int i = 0; i < 3; ++i)
+        if (ctx->ev_time[i]) cudaEventDestroy(ctx->ev_time[i]);
     if (ctx->q_head.p) cudaFree(ctx->q_head.p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -81,6 +85,16 @@ int32_t diee_sync(diee_ctx *ctx) {
     if (!ctx) return DIEE_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    return DIEE_OK;
+}
+
+int32_t diee_search_timing(diee_ctx *ctx, float *tree_ms, float *rollout_ms) {
+    if (!ctx || !tree_ms || !rollout_ms) return DIEE_ERR_INVALID;
+    if (!ctx->search_timed) return fail(ctx, DIEE_ERR_INVALID, "search_timing: the last search was not a split backgammon search");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev_time[2]));
+    CU(cudaEventElapsedTime(tree_ms, ctx->ev_time[0], ctx->ev_time[1]));
+    CU(cudaEventElapsedTime(rollout_ms, ctx->ev_time[1], ctx->ev_time[2]));
     return DIEE_OK;
 }
 
@@ -335,6 +349,8 @@ int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *state
     SearchPipe pipe;
     for (int i = 0; i < SEARCH_SLICES; ++i) { pipe.side[i] = ctx->side[i]; pipe.tree_done[i] = ctx->ev_tree[i]; pipe.roll_done[i] = ctx->ev_roll[i]; }
     pipe.queue_heads = (unsigned long long *)ctx->q_head.p;
+    pipe.t_begin = ctx->ev_time[0]; pipe.t_tree = ctx->ev_time[1]; pipe.t_end = ctx->ev_time[2];
+    pipe.timed = &ctx->search_timed;
     const size_t pairs = (size_t)cfg->iterations * (size_t)n;
     CU(cudaMemsetAsync(ctx->p_simnode.p, 0xFF, sizeof(int32_t) * pairs, ctx->stream));
     CU(cudaMemsetAsync(ctx->p_finals.p, 0, state_size(game_kind) * pairs, ctx->stream));

@@ -29,6 +29,8 @@ struct diee_ctx {
     // side streams / events of the sliced search (mcts_kernels.cu launch_typed)
     cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_tree[4] = {nullptr, nullptr, nullptr, nullptr}, ev_roll[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_time[3] = {nullptr, nullptr, nullptr};  // begin | tree done | rollouts done of the last split search
+    bool search_timed = false;
     // AlphaZero search arena + per-iteration batch buffers (alpha.cu)
     DevBuf a_state, a_parent, a_first, a_nchild, a_visits, a_value, a_prior, a_action, a_nnodes, a_selg, a_seln, a_status,
         a_any, a_batch, a_policy, a_valueout, a_dir, a_states_in, a_ids_in, a_root_ids, a_root_moves, a_root_visits,

@@ -24,6 +24,8 @@ struct SearchPipe {
     cudaStream_t side[SEARCH_SLICES];
     cudaEvent_t tree_done[SEARCH_SLICES], roll_done[SEARCH_SLICES];
     unsigned long long *queue_heads;  // SEARCH_SLICES job queue heads of the persistent lane kernel
+    cudaEvent_t t_begin, t_tree, t_end;  // timing marks of an unsliced search (tree kernel | rollouts)
+    bool *timed;                         // set when the marks of the last search are valid
 };
 
 cudaError_t launch_bg_valid_moves(cudaStream_t st, const diee_bg_state *states, int n, diee_move *moves_out,

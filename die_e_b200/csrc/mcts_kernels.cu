@@ -449,6 +449,19 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         if (slices < 1u) slices = 1u;
         if (slices > (uint32_t)SEARCH_SLICES) slices = (uint32_t)SEARCH_SLICES;
         if (slices > cfg.iterations) slices = cfg.iterations;
+        *pipe.timed = false;
+        if (slices == 1) {  // everything on the caller's stream, with timing marks around the two kernels
+            if ((e = cudaEventRecord(pipe.t_begin, st)) != cudaSuccess) return e;
+            mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
+                r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem);
+            *launches += 1;
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(pipe.t_tree, st)) != cudaSuccess) return e;
+            if ((e = launch_bg_rollouts(st, n, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pp, pipe.queue_heads, launches)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(pipe.t_end, st)) != cudaSuccess) return e;
+            *pipe.timed = true;
+            return launch_bg_rollout_count(st, n, cfg, pp, stats_out, launches);
+        }
         for (uint32_t s = 0; s < slices; ++s) {
             const uint32_t a = (uint32_t)((uint64_t)cfg.iterations * s / slices), b = (uint32_t)((uint64_t)cfg.iterations * (s + 1) / slices);
             mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(

@@ -201,6 +201,9 @@ int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *state
                              const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
                              uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
                              int32_t *status_out, diee_search_stats *stats_dev);
+/* CUDA-event durations of the two kernels of the last reference-exact backgammon search on this context
+ * (tree kernel | all rollouts), for the roofline line of bench.py.  Waits for that search to finish. */
+int32_t diee_search_timing(diee_ctx *ctx, float *tree_ms, float *rollout_ms);
 
 /* ---- policy/value net: ResNet (alphazero/nnet.rs:57-155), inference only ----
  * Architecture (backgammon): conv3x3(6->F)+BN+ReLU, `blocks` x [conv+BN+ReLU+conv+BN+add+ReLU],

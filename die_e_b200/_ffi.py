@@ -43,7 +43,7 @@ SYMBOLS = [
     "diee_bg_valid_moves", "diee_bg_valid_moves_dev", "diee_bg_apply_moves", "diee_bg_apply_moves_dev",
     "diee_bg_playout", "diee_bg_playout_dev", "diee_bg_encode_moves", "diee_bg_decode_moves",
     "diee_bg_encode_states", "diee_bg_encode_states_dev", "diee_mcts_search", "diee_mcts_search_dev",
-    "diee_net_create", "diee_net_destroy", "diee_net_param_count", "diee_net_forward", "diee_net_forward_dev",
+    "diee_net_create", "diee_net_destroy", "diee_net_set_precision", "diee_net_param_count", "diee_net_forward", "diee_net_forward_dev",
     "diee_search_timing", "diee_dirichlet", "diee_alpha_search", "diee_alpha_search_dev", "diee_selfplay_run", "diee_net_eval_count",
 ]
 
@@ -285,6 +285,9 @@ class Context:
                                              _p(d_status), _p(d_stats)))
 
 
+NET_BF16, NET_SPLIT3, NET_FP32 = 0, 1, 2
+
+
 class Net:
     """a diee_net handle (policy/value ResNet on one ctx)"""
 
@@ -309,6 +312,10 @@ class Net:
 
     def param_count(self):
         return int(lib().diee_net_param_count(self._h))
+
+    def set_precision(self, precision):
+        """NET_BF16 (fast path), NET_SPLIT3 (tensor cores, 24-bit operands) or NET_FP32 (parity mode, CUDA-core fp32)"""
+        self.ctx._chk(lib().diee_net_set_precision(self.ctx._h, self._h, C.c_int32(precision)))
 
     def forward(self, states):
         states = np.ascontiguousarray(states, dtype=BG_STATE).reshape(-1)

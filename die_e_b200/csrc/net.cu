@@ -67,10 +67,53 @@ static bool make_kmajor_map(CUtensorMap *m, const void *base, long long rows, in
 
 struct ConvLayer {
     __nv_bfloat16 *w = nullptr;  // [c_out_pad][K]
+    __nv_bfloat16 *w3 = nullptr; // split precision: [c_out_pad][3 planes][K], w = w3[0] + w3[1] + w3[2] to 24 bits
+    float *wf32 = nullptr;       // fp32 mode: [9][c_in][c_out] (BatchNorm folded)
+    int c_in = 0, c_out = 0;
     float *bias = nullptr;       // [c_out_pad]
-    CUtensorMap wmap;
+    CUtensorMap wmap, wmap3;
     int c_out_pad = 0, K = 0, ntaps = 9, chunks = 4, bn = 128;
 };
+
+// the plane pairs (i, j), i + j <= 2, of a split-precision product, packed 2+2 bits each; smallest terms first
+static constexpr uint32_t PAIRS6 = (2u << 0 | 0u << 2) | (0u << 4 | 2u << 6) | (1u << 8 | 1u << 10) | (1u << 12 | 0u << 14) |
+                                   (0u << 16 | 1u << 18) | (0u << 20 | 0u << 22);
+// exact bf16 activations (the first layer's integers): activation plane 0 against the three weight planes
+static constexpr uint32_t PAIRS3 = (0u << 0 | 2u << 2) | (0u << 4 | 1u << 6) | (0u << 8 | 0u << 10);
+
+static void split3(float v, __nv_bfloat16 out[3]) {
+    out[0] = __float2bfloat16(v);
+    const float r1 = v - __bfloat162float(out[0]);
+    out[1] = __float2bfloat16(r1);
+    const float r2 = r1 - __bfloat162float(out[1]);
+    out[2] = __float2bfloat16(r2);
+}
+
+// fp32 mode weights from the packed fp32 matrix wf [c_out_pad][K], K index = tap * c_in + ci
+static int32_t upload_f32(diee_ctx *ctx, ConvLayer &L, const std::vector<float> &wf, int c_in, int c_out) {
+    std::vector<float> w((size_t)9 * c_in * c_out);
+    for (int co = 0; co < c_out; ++co)
+        for (int tap = 0; tap < 9; ++tap)
+            for (int ci = 0; ci < c_in; ++ci) w[((size_t)tap * c_in + ci) * c_out + co] = wf[(size_t)co * L.K + (size_t)tap * c_in + ci];
+    L.c_in = c_in; L.c_out = c_out;
+    CU(cudaMalloc(&L.wf32, w.size() * sizeof(float)));
+    CU(cudaMemcpy(L.wf32, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return DIEE_OK;
+}
+
+static int32_t upload_split(diee_ctx *ctx, ConvLayer &L, const std::vector<float> &wf) {
+    // wf: [c_out_pad][K] fp32 (BatchNorm already folded)
+    std::vector<__nv_bfloat16> w3((size_t)L.c_out_pad * 3 * L.K);
+    for (int co = 0; co < L.c_out_pad; ++co)
+        for (int k = 0; k < L.K; ++k) {
+            __nv_bfloat16 p[3];
+            split3(wf[(size_t)co * L.K + k], p);
+            for (int pl = 0; pl < 3; ++pl) w3[((size_t)co * 3 + pl) * L.K + k] = p[pl];
+        }
+    CU(cudaMalloc(&L.w3, w3.size() * sizeof(__nv_bfloat16)));
+    CU(cudaMemcpy(L.w3, w3.data(), w3.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    return DIEE_OK;
+}
 
 struct diee_net {
     int filters = 0, blocks = 0;
@@ -81,6 +124,8 @@ struct diee_net {
     float *bp = nullptr, *wv = nullptr;
     float bv = 0.f;
     // activation scratch (grown on demand)
+    float *wpT = nullptr;  // split precision: policy Linear weight fp32 [768][1352], same K order
+    int precision = DIEE_NET_BF16;
     DevBuf in0, actA, actB, actC, pfeat, vfeat, s_states, s_policy, s_value;
     int64_t param_count = 0;
 };
@@ -92,6 +137,7 @@ static int32_t build_conv(diee_ctx *ctx, ConvLayer &L, const float *w, const flo
                           const float *mean, const float *var, int c_out, int c_in, int c_out_pad, int k_pad, int bn) {
     const int K = k_pad ? k_pad : 9 * c_in;
     std::vector<__nv_bfloat16> wp((size_t)c_out_pad * K, __float2bfloat16(0.f));
+    std::vector<float> wf((size_t)c_out_pad * K, 0.f);
     std::vector<float> bp((size_t)c_out_pad, 0.f);
     for (int co = 0; co < c_out; ++co) {
         const double scale = (double)g[co] / std::sqrt((double)var[co] + 1e-5);
@@ -100,6 +146,7 @@ static int32_t build_conv(diee_ctx *ctx, ConvLayer &L, const float *w, const flo
             for (int tap = 0; tap < 9; ++tap) {
                 const double v = (double)w[((size_t)co * c_in + ci) * 9 + tap] * scale;
                 wp[(size_t)co * K + (size_t)tap * c_in + ci] = __float2bfloat16((float)v);
+                wf[(size_t)co * K + (size_t)tap * c_in + ci] = (float)v;
             }
     }
     L.c_out_pad = c_out_pad; L.K = K; L.bn = bn;
@@ -110,7 +157,10 @@ static int32_t build_conv(diee_ctx *ctx, ConvLayer &L, const float *w, const flo
     CU(cudaMemcpy(L.w, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (!make_w_map(&L.wmap, L.w, c_out_pad, K, bn)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed");
-    return DIEE_OK;
+    int32_t rc = upload_split(ctx, L, wf);
+    if (rc != DIEE_OK) return rc;
+    if (!make_w_map(&L.wmap3, L.w3, c_out_pad, 3 * K, bn)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (split weights) failed");
+    return upload_f32(ctx, L, wf, c_in, c_out);
 }
 
 extern "C" {
@@ -159,13 +209,17 @@ int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *t,
         // build with k_pad = 64: K index = tap*6 + ci (< 54)
         const int K = 64;
         std::vector<__nv_bfloat16> wp((size_t)F * K, __float2bfloat16(0.f));
+        std::vector<float> wf0((size_t)F * K, 0.f);
         std::vector<float> bpv((size_t)F, 0.f);
         for (int co = 0; co < F; ++co) {
             const double scale = (double)t[2][co] / std::sqrt((double)t[5][co] + 1e-5);
             bpv[co] = (float)(((double)t[1][co] - (double)t[4][co]) * scale + (double)t[3][co]);
             for (int ci = 0; ci < 6; ++ci)
-                for (int tap = 0; tap < 9; ++tap)
-                    wp[(size_t)co * K + tap * 6 + ci] = __float2bfloat16((float)((double)w6[((size_t)co * 6 + ci) * 9 + tap] * scale));
+                for (int tap = 0; tap < 9; ++tap) {
+                    const float v = (float)((double)w6[((size_t)co * 6 + ci) * 9 + tap] * scale);
+                    wp[(size_t)co * K + tap * 6 + ci] = __float2bfloat16(v);
+                    wf0[(size_t)co * K + tap * 6 + ci] = v;
+                }
         }
         L.c_out_pad = F; L.K = K; L.bn = 128; L.ntaps = 1; L.chunks = 1;
         CU(cudaMalloc(&L.w, wp.size() * sizeof(__nv_bfloat16)));
@@ -173,6 +227,11 @@ int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *t,
         CU(cudaMemcpy(L.w, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(L.bias, bpv.data(), bpv.size() * sizeof(float), cudaMemcpyHostToDevice));
         if (!make_w_map(&L.wmap, L.w, F, K, 128)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed");
+        rc = upload_split(ctx, L, wf0);
+        if (rc != DIEE_OK) return rc;
+        rc = upload_f32(ctx, L, wf0, 6, F);
+        if (rc != DIEE_OK) return rc;
+        if (!make_w_map(&L.wmap3, L.w3, F, 3 * K, 128)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (split weights) failed");
         net->convs.push_back(L);
     }
     idx = 6;
@@ -197,6 +256,12 @@ int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *t,
         CU(cudaMalloc(&net->wp, wp.size() * sizeof(__nv_bfloat16)));
         CU(cudaMemcpy(net->wp, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
         if (!make_kmajor_map(&net->wp_map, net->wp, 1408, 768, 128)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (policy linear) failed");
+        std::vector<float> wT((size_t)768 * DIEE_ACTION_SPACE);
+        for (int j = 0; j < DIEE_ACTION_SPACE; ++j)
+            for (int c = 0; c < 32; ++c)
+                for (int pos = 0; pos < 24; ++pos) wT[(size_t)(pos * 32 + c) * DIEE_ACTION_SPACE + j] = W[(size_t)j * 768 + c * 24 + pos];
+        CU(cudaMalloc(&net->wpT, wT.size() * sizeof(float)));
+        CU(cudaMemcpy(net->wpT, wT.data(), wT.size() * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMalloc(&net->bp, DIEE_ACTION_SPACE * sizeof(float)));
         CU(cudaMemcpy(net->bp, t[idx + 7], DIEE_ACTION_SPACE * sizeof(float), cudaMemcpyHostToDevice));
     }
@@ -219,9 +284,10 @@ int32_t diee_net_destroy(diee_ctx *ctx, diee_net *net) {
     if (!ctx || !net) return DIEE_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (ConvLayer &L : net->convs) { cudaFree(L.w); cudaFree(L.bias); }
-    cudaFree(net->pconv.w); cudaFree(net->pconv.bias); cudaFree(net->vconv.w); cudaFree(net->vconv.bias);
-    cudaFree(net->wp); cudaFree(net->bp); cudaFree(net->wv);
+    for (ConvLayer &L : net->convs) { cudaFree(L.w); cudaFree(L.w3); cudaFree(L.wf32); cudaFree(L.bias); }
+    cudaFree(net->pconv.w); cudaFree(net->pconv.w3); cudaFree(net->pconv.wf32); cudaFree(net->pconv.bias);
+    cudaFree(net->vconv.w); cudaFree(net->vconv.w3); cudaFree(net->vconv.wf32); cudaFree(net->vconv.bias);
+    cudaFree(net->wp); cudaFree(net->wpT); cudaFree(net->bp); cudaFree(net->wv);
     DevBuf *bufs[] = {&net->in0, &net->actA, &net->actB, &net->actC, &net->pfeat, &net->vfeat, &net->s_states, &net->s_policy, &net->s_value};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -237,6 +303,66 @@ int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *
     CU(cudaSetDevice(ctx->device));
     const int F = net->filters;
     const size_t rows = (size_t)n * 24;
+    if (net->precision == DIEE_NET_FP32) {
+        // the reference's own arithmetic: fp32 FMAs on the CUDA cores (parity mode)
+        RESERVE(net->actA, rows * F * 4);
+        RESERVE(net->actB, rows * F * 4);
+        RESERVE(net->actC, rows * F * 4);
+        RESERVE(net->pfeat, rows * 32 * 4);
+        RESERVE(net->vfeat, rows * 16 * 4);
+        cudaStream_t st = ctx->stream;
+        float *bx = (float *)net->actA.p, *by = (float *)net->actB.p, *bz = (float *)net->actC.p;
+        const ConvLayer &L0 = net->convs[0];
+        CU(launch_conv_f32(st, nullptr, states, n, 6, L0.wf32, L0.bias, nullptr, bx, F, F, 1));
+        ctx->launches += 1;
+        for (int b = 0; b < net->blocks; ++b) {
+            const ConvLayer &c1 = net->convs[1 + 2 * b], &c2 = net->convs[2 + 2 * b];
+            CU(launch_conv_f32(st, bx, nullptr, n, F, c1.wf32, c1.bias, nullptr, by, F, F, 1));
+            CU(launch_conv_f32(st, by, nullptr, n, F, c2.wf32, c2.bias, bx, bz, F, F, 1));
+            ctx->launches += 2;
+            float *tp = bx; bx = bz; bz = tp;
+        }
+        CU(cudaMemsetAsync(net->vfeat.p, 0, rows * 16 * 4, st));  // channels 3..15 of the value features are padding
+        CU(launch_conv_f32(st, bx, nullptr, n, F, net->pconv.wf32, net->pconv.bias, nullptr, (float *)net->pfeat.p, 32, 32, 1));
+        CU(launch_conv_f32(st, bx, nullptr, n, F, net->vconv.wf32, net->vconv.bias, nullptr, (float *)net->vfeat.p, 3, 16, 1));
+        CU(launch_heads_f32(st, (const float *)net->pfeat.p, net->wpT, net->bp, (const float *)net->vfeat.p, net->wv, net->bv, n, policy_out, value_out));
+        ctx->launches += 4;
+        return DIEE_OK;
+    }
+    if (net->precision == DIEE_NET_SPLIT3) {
+        // fp32-parity mode: activations and weights as three bf16 planes, six tensor-core products per
+        // K-block, fp32 everywhere else (bias, residual, heads)
+        RESERVE(net->in0, rows * 64 * 2);
+        RESERVE(net->actA, rows * F * 6);
+        RESERVE(net->actB, rows * F * 6);
+        RESERVE(net->actC, rows * F * 6);
+        RESERVE(net->pfeat, rows * 32 * 4);
+        RESERVE(net->vfeat, rows * 16 * 4);
+        CUtensorMap m_in, mA, mB, mC;
+        if (!make_act_map(&m_in, net->in0.p, n, 64) || !make_act_map(&mA, net->actA.p, n, 3 * F) ||
+            !make_act_map(&mB, net->actB.p, n, 3 * F) || !make_act_map(&mC, net->actC.p, n, 3 * F))
+            return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (activations) failed");
+        cudaStream_t st = ctx->stream;
+        CU(launch_encode_im2col(st, states, n, net->in0.p));
+        const ConvLayer &L0 = net->convs[0];
+        CU(launch_conv(st, L0.bn, m_in, L0.wmap3, n, L0.ntaps, L0.chunks, L0.bias, nullptr, net->actA.p, 2, F, 1, 3, PAIRS3, 0, L0.K));
+        ctx->launches += 2;
+        void *bx = net->actA.p, *by = net->actB.p, *bz = net->actC.p;
+        CUtensorMap *mx = &mA, *my = &mB, *mz = &mC;
+        for (int b = 0; b < net->blocks; ++b) {
+            const ConvLayer &c1 = net->convs[1 + 2 * b], &c2 = net->convs[2 + 2 * b];
+            CU(launch_conv(st, c1.bn, *mx, c1.wmap3, n, 9, c1.chunks, c1.bias, nullptr, by, 2, F, 1, 6, PAIRS6, F, c1.K));
+            CU(launch_conv(st, c2.bn, *my, c2.wmap3, n, 9, c2.chunks, c2.bias, bx, bz, 2, F, 1, 6, PAIRS6, F, c2.K));
+            ctx->launches += 2;
+            void *tp = bx; bx = bz; bz = tp;
+            CUtensorMap *tm = mx; mx = mz; mz = tm;
+        }
+        CU(launch_conv(st, net->pconv.bn, *mx, net->pconv.wmap3, n, 9, net->pconv.chunks, net->pconv.bias, nullptr, net->pfeat.p, 1, 32, 1, 6, PAIRS6, F, net->pconv.K));
+        CU(launch_conv(st, net->vconv.bn, *mx, net->vconv.wmap3, n, 9, net->vconv.chunks, net->vconv.bias, nullptr, net->vfeat.p, 1, 16, 1, 6, PAIRS6, F, net->vconv.K));
+        CU(launch_heads_f32(st, (const float *)net->pfeat.p, net->wpT, net->bp, (const float *)net->vfeat.p, net->wv, net->bv, n, policy_out, value_out));
+        ctx->launches += 4;
+        return DIEE_OK;
+    }
     RESERVE(net->in0, rows * 64 * 2);
     RESERVE(net->actA, rows * F * 2);
     RESERVE(net->actB, rows * F * 2);
@@ -291,5 +417,12 @@ int32_t diee_net_forward(diee_ctx *ctx, diee_net *net, const diee_bg_state *stat
 }
 
 int64_t diee_net_param_count(const diee_net *net) { return net ? net->param_count : 0; }
+
+int32_t diee_net_set_precision(diee_ctx *ctx, diee_net *net, int32_t precision) {
+    if (!ctx || !net) return DIEE_ERR_INVALID;
+    if (precision != DIEE_NET_BF16 && precision != DIEE_NET_SPLIT3 && precision != DIEE_NET_FP32) return fail(ctx, DIEE_ERR_INVALID, "net_set_precision: unknown precision %d", precision);
+    net->precision = precision;
+    return DIEE_OK;
+}
 
 }  // extern "C"

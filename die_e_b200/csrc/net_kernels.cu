@@ -146,12 +146,20 @@ struct ConvCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
 
-// out_mode: 0 = bf16 NHWC [rows][c_out_total], 1 = fp32 NHWC
+// out_mode: 0 = bf16 NHWC [rows][c_out_total], 1 = fp32 NHWC, 2 = three bf16 planes [rows][3][c_out_total]
+//
+// Split precision (the fp32-parity mode of the net): an fp32 value is carried as three bf16 planes
+// x = x0 + x1 + x2 (each the bf16 rounding of what the previous ones left over, 24 mantissa bits in all).
+// A product then needs the plane pairs (i, j) with i + j <= 2 -- six bf16 MMAs accumulated in the fp32 TMEM
+// accumulator -- so the K loop simply runs over (pair, tap, chunk): `pairs` packs up to eight (i, j) as 2+2
+// bits each, plane i of the activations starts a_plane channels further on, plane j of the weights b_plane
+// K-columns further on.  Plain bf16 is the one pair (0, 0).
 template <int BN>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int n_boards,
                   int ntaps, int chunks, const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual,
-                  void *__restrict__ out, int out_mode, int c_out_total, int relu) {
+                  void *__restrict__ out, int out_mode, int c_out_total, int relu, int npairs, uint32_t pairs, int a_plane,
+                  int b_plane) {
     using Cfg = ConvCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -165,7 +173,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int board0 = blockIdx.x * CONV_NB;
     const int n0 = blockIdx.y * BN;
-    const int num_kb = ntaps * chunks;
+    const int per_pair = ntaps * chunks;
+    const int num_kb = per_pair * npairs;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmapA);
@@ -191,10 +200,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 uint8_t *sa = smem + s * Cfg::STAGE_BYTES;
                 uint8_t *sb = sa + CONV_A_BYTES;
                 mbar_expect_tx(&full_bar[s], (uint32_t)Cfg::STAGE_BYTES);
-                const int tap = kb / chunks, chunk = kb - tap * chunks;
+                const int pr = kb / per_pair, kin = kb - pr * per_pair;
+                const int pi = (int)((pairs >> (4 * pr)) & 3u), pj = (int)((pairs >> (4 * pr + 2)) & 3u);
+                const int tap = kin / chunks, chunk = kin - tap * chunks;
                 const int kh = ntaps == 9 ? tap / 3 : 1, kw = ntaps == 9 ? tap - (tap / 3) * 3 : 1;
-                tma_load_4d(sa, &tmapA, &full_bar[s], chunk * 64, kw - 1, kh - 1, board0);
-                tma_load_2d(sb, &tmapB, &full_bar[s], kb * 64, n0);
+                tma_load_4d(sa, &tmapA, &full_bar[s], pi * a_plane + chunk * 64, kw - 1, kh - 1, board0);
+                tma_load_2d(sb, &tmapB, &full_bar[s], pj * b_plane + kin * 64, n0);
             }
         }
     } else if (warp == 1) {
@@ -240,29 +251,61 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 if (ncol == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
                 tmem_ld_wait();
                 if (valid) {
-                    float f[32];
+                    float f[32], rsum[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = j < ncol ? __uint_as_float(v[j]) + bias_smem[c0 + j] : 0.f;
-                    const size_t off = (size_t)grow * c_out_total + n0 + c0;
+                    const int nplanes = out_mode == 2 ? 3 : 1;
+                    const size_t off = (size_t)grow * c_out_total * nplanes + n0 + c0;
                     if (residual) {
-                        const uint4 *rp = reinterpret_cast<const uint4 *>(residual + off);
+                        // the skip connection: in split precision the residual is the sum of its three planes,
+                        // smallest first (exact: they do not overlap)
+                        for (int pl = nplanes - 1; pl >= 0; --pl) {
+                            const uint4 *rp = reinterpret_cast<const uint4 *>(residual + off + (size_t)pl * c_out_total);
+                            float r32[32];
 #pragma unroll
-                        for (int g4 = 0; g4 < 4; ++g4) {
-                            const uint4 r = rp[g4];
-                            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+                            for (int g4 = 0; g4 < 4; ++g4) {
+                                const uint4 r = rp[g4];
+                                const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[h]);
-                                f[g4 * 8 + h * 2] += __bfloat162float(b2.x);
-                                f[g4 * 8 + h * 2 + 1] += __bfloat162float(b2.y);
+                                for (int h = 0; h < 4; ++h) {
+                                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[h]);
+                                    r32[g4 * 8 + h * 2] = __bfloat162float(b2.x);
+                                    r32[g4 * 8 + h * 2 + 1] = __bfloat162float(b2.y);
+                                }
+                            }
+                            if (pl == nplanes - 1) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) rsum[j] = r32[j];
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) rsum[j] += r32[j];
                             }
                         }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] += rsum[j];
                     }
                     if (relu) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
                     }
-                    if (out_mode == 0) {
+                    if (out_mode == 2) {
+                        // three bf16 planes: each is the bf16 rounding of what the previous ones left over
+                        for (int pl = 0; pl < 3; ++pl) {
+                            uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(out) + off + (size_t)pl * c_out_total);
+#pragma unroll
+                            for (int g4 = 0; g4 < 4; ++g4) {
+                                uint32_t w[4];
+#pragma unroll
+                                for (int h = 0; h < 4; ++h) {
+                                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g4 * 8 + h * 2], f[g4 * 8 + h * 2 + 1]);
+                                    w[h] = *reinterpret_cast<const uint32_t *>(&b2);
+                                    f[g4 * 8 + h * 2] -= __bfloat162float(b2.x);
+                                    f[g4 * 8 + h * 2 + 1] -= __bfloat162float(b2.y);
+                                }
+                                if (g4 * 8 < ncol) op[g4] = make_uint4(w[0], w[1], w[2], w[3]);
+                            }
+                        }
+                    } else if (out_mode == 0) {
                         uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(out) + off);
 #pragma unroll
                         for (int g4 = 0; g4 < 4; ++g4) {
@@ -452,11 +495,94 @@ softmax_value_kernel(const float *__restrict__ vfeat, const float *__restrict__ 
     if (lane == 0) value_out[b] = tanhf(acc + bv);
 }
 
+// ---------------------------------------------------------------- fp32 reference-arithmetic mode (DIEE_NET_FP32)
+// The reference computes in fp32 (lib.rs:20, tch conv2d / batch_norm / linear).  This mode does the same on the
+// CUDA cores: IEEE single FMAs with round-to-nearest, one accumulator per output, so it differs from the
+// reference only by summation order.  It is the PARITY mode of the net (speed is not its purpose; the tensor
+// cores accumulate with truncation, which costs ~1e-5 per layer -- see DIEE_NET_SPLIT3).
+//   x: fp32 NHWC [n][24][c_in] (or, first layer, the packed states: as_tensor is applied on the fly, c_in = 6)
+//   w: fp32 [9][c_in][c_out] with eval-mode BatchNorm folded in; out: fp32 [n][24][out_stride]
+// One CTA = one board x 64 output channels; thread = (channel, half of the 24 positions).
+__global__ void __launch_bounds__(128)
+conv3x3_f32_kernel(const float *__restrict__ x, const diee_bg_state *__restrict__ states, int c_in, const float *__restrict__ w,
+                   const float *__restrict__ bias, const float *__restrict__ residual, float *__restrict__ out, int c_out,
+                   int out_stride, int relu) {
+    extern __shared__ float xs[];  // [24][c_in]
+    const int b = blockIdx.x;
+    if (states) {
+        const diee_bg_state &s = states[b];
+        for (int i = threadIdx.x; i < 24 * 6; i += 128) {
+            const int pt = i / 6, c = i - pt * 6, half = pt < 12 ? 0 : 1;
+            float val;
+            switch (c) {  // as_tensor channel order, backgammon_logic.rs:240-250
+                case 0: val = (float)s.pts[pt]; break;
+                case 1: val = (float)s.player; break;
+                case 2: val = (float)s.bar[half]; break;
+                case 3: val = (float)s.off[half]; break;
+                case 4: val = (float)s.roll[half]; break;
+                default: val = s.second ? 1.f : 0.f; break;
+            }
+            xs[i] = val;
+        }
+    } else {
+        for (int i = threadIdx.x; i < 24 * c_in; i += 128) xs[i] = x[(size_t)b * 24 * c_in + i];
+    }
+    __syncthreads();
+    const int co = blockIdx.y * 64 + (threadIdx.x & 63);
+    const int p0 = (threadIdx.x >> 6) * 12;
+    if (co >= c_out) return;
+    float acc[12];
+#pragma unroll
+    for (int p = 0; p < 12; ++p) acc[p] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+        int src[12];
+#pragma unroll
+        for (int p = 0; p < 12; ++p) {
+            const int pos = p0 + p, hh = pos / 6 + dh, ww = pos % 6 + dw;
+            src[p] = (hh >= 0 && hh < 4 && ww >= 0 && ww < 6) ? (hh * 6 + ww) * c_in : -1;
+        }
+        const float *wt = w + (size_t)tap * c_in * c_out + co;
+        for (int ci = 0; ci < c_in; ++ci) {
+            const float wv = wt[(size_t)ci * c_out];
+#pragma unroll
+            for (int p = 0; p < 12; ++p)
+                if (src[p] >= 0) acc[p] = fmaf(xs[src[p] + ci], wv, acc[p]);
+        }
+    }
+    const float bv = bias[co];
+#pragma unroll
+    for (int p = 0; p < 12; ++p) {
+        const size_t row = (size_t)b * 24 + p0 + p;
+        float v = acc[p] + bv;
+        if (residual) v += residual[row * out_stride + co];
+        if (relu) v = fmaxf(v, 0.f);
+        out[row * out_stride + co] = v;
+    }
+}
+
+// Policy Linear(768 -> 1352) in plain fp32 for the split-precision (fp32-parity) mode: feat fp32 [n][768]
+// (K index = pos*32 + c), wT fp32 [768][1352].  One thread per logit, sequential fp32 FMA over K.
+__global__ void __launch_bounds__(256)
+fc_f32_kernel(const float *__restrict__ feat, const float *__restrict__ wT, const float *__restrict__ bias, int n,
+              float *__restrict__ out) {
+    __shared__ float f[768];
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < 768; i += 256) f[i] = feat[(size_t)b * 768 + i];
+    __syncthreads();
+    for (int j = blockIdx.y * 256 + threadIdx.x; j < DIEE_ACTION_SPACE; j += gridDim.y * 256) {
+        float acc = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 768; ++k) acc = fmaf(f[k], wT[(size_t)k * DIEE_ACTION_SPACE + j], acc);
+        out[(size_t)b * DIEE_ACTION_SPACE + j] = acc + bias[j];
+    }
+}
+
 // ---------------------------------------------------------------- launchers
 template <int BN>
 static cudaError_t launch_conv_bn(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,
                                   int chunks, const float *bias, const __nv_bfloat16 *residual, void *out, int out_mode,
-                                  int c_out_total, int relu) {
+                                  int c_out_total, int relu, int npairs, uint32_t pairs, int a_plane, int b_plane) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM_BYTES);
@@ -465,17 +591,19 @@ static cudaError_t launch_conv_bn(cudaStream_t st, const CUtensorMap &ta, const 
     }
     dim3 grid((n_boards + CONV_NB - 1) / CONV_NB, c_out_total / BN);
     conv3x3_tc_kernel<BN><<<grid, CONV_THREADS, ConvCfg<BN>::SMEM_BYTES, st>>>(ta, tb, n_boards, ntaps, chunks, bias, residual, out,
-                                                                              out_mode, c_out_total, relu);
+                                                                              out_mode, c_out_total, relu, npairs, pairs, a_plane,
+                                                                              b_plane);
     return cudaGetLastError();
 }
 
 cudaError_t launch_conv(cudaStream_t st, int bn, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps, int chunks,
-                        const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu) {
+                        const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
+                        int npairs, uint32_t pairs, int a_plane, int b_plane) {
     const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(residual);
     switch (bn) {
-        case 128: return launch_conv_bn<128>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu);
-        case 32: return launch_conv_bn<32>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu);
-        case 16: return launch_conv_bn<16>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu);
+        case 128: return launch_conv_bn<128>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu, npairs, pairs, a_plane, b_plane);
+        case 32: return launch_conv_bn<32>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu, npairs, pairs, a_plane, b_plane);
+        case 16: return launch_conv_bn<16>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu, npairs, pairs, a_plane, b_plane);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -500,6 +628,24 @@ cudaError_t launch_heads(cudaStream_t st, const CUtensorMap &ta, const CUtensorM
     }
     dim3 grid((n + 127) / 128, FC_N_PAD / 128);
     fc_tc_kernel<<<grid, CONV_THREADS, FC_SMEM_BYTES, st>>>(ta, tb, n, bp, policy_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    softmax_value_kernel<<<(n + 7) / 8, 256, 0, st>>>(vfeat, wv, bv, n, policy_out, value_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_f32(cudaStream_t st, const float *x, const diee_bg_state *states, int n, int c_in, const float *w,
+                            const float *bias, const float *residual, float *out, int c_out, int out_stride, int relu) {
+    if (n <= 0) return cudaSuccess;
+    conv3x3_f32_kernel<<<dim3((unsigned)n, (unsigned)((c_out + 63) / 64)), 128, (size_t)24 * c_in * sizeof(float), st>>>(
+        x, states, c_in, w, bias, residual, out, c_out, out_stride, relu);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_heads_f32(cudaStream_t st, const float *pfeat, const float *wT, const float *bp, const float *vfeat,
+                             const float *wv, float bv, int n, float *policy_out, float *value_out) {
+    if (n <= 0) return cudaSuccess;
+    fc_f32_kernel<<<dim3((unsigned)n, 6), 256, 0, st>>>(pfeat, wT, bp, n, policy_out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     softmax_value_kernel<<<(n + 7) / 8, 256, 0, st>>>(vfeat, wv, bv, n, policy_out, value_out);

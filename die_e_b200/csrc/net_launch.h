@@ -8,7 +8,12 @@
 
 namespace diee {
 cudaError_t launch_conv(cudaStream_t st, int bn, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps, int chunks,
-                        const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu);
+                        const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
+                        int npairs = 1, uint32_t pairs = 0, int a_plane = 0, int b_plane = 0);
+cudaError_t launch_conv_f32(cudaStream_t st, const float *x, const diee_bg_state *states, int n, int c_in, const float *w,
+                            const float *bias, const float *residual, float *out, int c_out, int out_stride, int relu);
+cudaError_t launch_heads_f32(cudaStream_t st, const float *pfeat, const float *wT, const float *bp, const float *vfeat,
+                             const float *wv, float bv, int n, float *policy_out, float *value_out);
 cudaError_t launch_encode_im2col(cudaStream_t st, const diee_bg_state *states, int n, void *out);
 cudaError_t launch_heads(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, const float *bp, const float *vfeat,
                          const float *wv, float bv, int n, float *policy_out, float *value_out);

@@ -221,6 +221,17 @@ int32_t diee_search_timing(diee_ctx *ctx, float *tree_ms, float *rollout_ms);
 typedef struct diee_net diee_net;
 int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *tensors, const int64_t *numels,
                         int32_t n_tensors, diee_net **out);
+/* Arithmetic of the forward pass (nnet.rs:120-133 computes in fp32, lib.rs:20).
+ * DIEE_NET_BF16 (default): bf16 operands on the tensor cores, fp32 accumulation -- the fast path.
+ * DIEE_NET_SPLIT3: still on the tensor cores, but every activation and weight is carried as three bf16 planes
+ *   (24 mantissa bits) and each product is six MMAs; what remains is the tensor cores' truncating fp32
+ *   accumulation, ~1e-5 per layer (about 10x the rounding cost of an fp32 forward).
+ * DIEE_NET_FP32: the PARITY mode -- fp32 FMAs (round to nearest) on the CUDA cores, like the reference; differs
+ *   from it only by summation order. */
+#define DIEE_NET_BF16 0
+#define DIEE_NET_SPLIT3 1
+#define DIEE_NET_FP32 2
+int32_t diee_net_set_precision(diee_ctx *ctx, diee_net *net, int32_t precision);
 int32_t diee_net_destroy(diee_ctx *ctx, diee_net *net);
 int64_t diee_net_param_count(const diee_net *net);
 int32_t diee_net_forward(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, float *policy_out,

@@ -8,7 +8,10 @@ Floating point: the product computes in bf16 with fp32 accumulation.  Two bars a
       the 19-block bar is the bf16 noise floor itself (|dv| <= 6e-2, |dp| <= 10 % of the row maximum);
   (2) against the fp64 oracle of the reference architecture the bf16 error itself is bounded
       (value |dv| <= 0.1, policy total-variation distance <= 0.05) and printed.
-north_star's 1e-5 (relative, vs the fp32 reference) is NOT met by the bf16 path and is not claimed."""
+north_star's 1e-5 (relative, vs the fp32 reference) is NOT met by the bf16 path and is not claimed for it.
+The parity mode is DIEE_NET_FP32 (fp32 FMAs on the CUDA cores, the reference's own arithmetic):
+test_fp32_mode_matches_fp32_reference asserts it against the fp64 oracle next to the reference's own fp32
+rounding cost, and bounds the 24-bit tensor-core mode DIEE_NET_SPLIT3 the same way."""
 import numpy as np
 import pytest
 
@@ -53,6 +56,43 @@ def test_forward_matches_oracles(ctx, oracle, filters, blocks, n, bn):
         assert d_emul_v <= 6e-2 and d_emul_p <= 1e-1
     assert d64_v <= 0.1 and tv64 <= 0.05
     assert (p.argmax(1) == pe.argmax(1)).mean() >= 0.9
+    net.close()
+
+
+@pytest.mark.parametrize("filters,blocks,n,bn", [(128, 1, 20, "identity"), (256, 2, 37, "random"), (256, 19, 48, "random")])
+def test_fp32_mode_matches_fp32_reference(ctx, oracle, filters, blocks, n, bn):
+    """N1 in the parity mode (DIEE_NET_FP32) and in the 24-bit tensor-core mode (DIEE_NET_SPLIT3).
+
+    Tolerance.  north_star asks for 1e-5 relative on the value estimate against the fp32 reference.  Two correct
+    fp32 forwards differ by their summation order, so the bar is written against the fp64 oracle and next to
+    the reference's OWN fp32 rounding cost (torch fp32 vs fp64, printed): the fp32 mode must be within
+    max(1e-5, 4 x that cost) on the value (relative to max(|v|, 1e-2)) and on the policy (fraction of the row
+    maximum -- a softmax row reaches down to 1e-9, a per-entry relative bar means nothing there).  With these
+    synthetic weights the reference's own cost is 3e-7 at 2 blocks and 1.6e-5 at 19 blocks.
+    SPLIT3 is bounded by 20 x the same figure (truncating accumulation in TMEM, ~1e-5 per layer)."""
+    import torch
+    from die_e_b200 import _ffi, nnet
+    tens = nnet.synthetic_tensors(seed=7, filters=filters, blocks=blocks, bn_stats=bn)
+    net = _ffi.Net(ctx, tens)
+    states, x = _inputs(oracle, n)
+    p64, v64 = net_oracle.forward(tens, x, blocks)
+    p32, v32 = net_oracle.forward(tens, x, blocks, dtype=torch.float32)   # what the reference (tch, fp32) computes
+
+    def err(p, v):
+        return ((np.abs(v - v64) / np.maximum(np.abs(v64), 1e-2)).max(), (np.abs(p - p64).max(1) / p64.max(1)).max())
+    ref_v, ref_p = err(p32, v32)
+    out = {}
+    for name, mode in (("fp32", _ffi.NET_FP32), ("split3", _ffi.NET_SPLIT3), ("bf16", _ffi.NET_BF16)):
+        net.set_precision(mode)
+        p, v = net.forward(states)
+        assert np.isfinite(p).all() and np.isfinite(v).all() and np.allclose(p.sum(1), 1.0, atol=1e-4)
+        out[name] = err(p, v) + (p,)
+    print(f"\n[net F={filters} B={blocks} n={n}] error vs fp64 (value rel, policy/rowmax): "
+          f"torch fp32 {ref_v:.2e} {ref_p:.2e} | ours fp32 {out['fp32'][0]:.2e} {out['fp32'][1]:.2e} | "
+          f"split3 {out['split3'][0]:.2e} {out['split3'][1]:.2e} | bf16 {out['bf16'][0]:.2e} {out['bf16'][1]:.2e}")
+    assert out["fp32"][0] <= max(1e-5, 4 * ref_v) and out["fp32"][1] <= max(1e-5, 4 * ref_p)
+    assert out["split3"][0] <= max(1e-5, 20 * ref_v) and out["split3"][1] <= max(1e-5, 20 * ref_p)
+    assert (out["fp32"][2].argmax(1) == p64.argmax(1)).all()
     net.close()
 
 

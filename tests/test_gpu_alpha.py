@@ -61,6 +61,57 @@ def test_alpha_search_bit_exact(ctx, net, oracle, n, iters, seed):
         assert [int(x) for x in r_ids[g, :nc]] == [oracle.bg_encode(states[g:g + 1], m) for m in oracle.moves_to_list(ch["action"], nc)]
 
 
+def test_alpha_search_end_to_end_against_an_independent_fp32_net(ctx, oracle):
+    """End to end, nothing shared: the GPU search with the net in its fp32 parity mode (DIEE_NET_FP32) against the
+    oracle search whose net is torch's fp32 CPU forward of the same weights (what the reference's tch computes).
+    The two nets agree to ~1e-6, so the trees can only differ where two PUCT scores are closer than that.
+    Bar: root visit counts identical for >= 95 % of the games, total-variation distance of the root visit
+    distributions <= 1e-2 for every game, and value estimates of the root children (value / visits) within
+    1e-5 relative (floor 1e-2) wherever the visit counts agree."""
+    import torch
+    import net_oracle
+    from die_e_b200 import _ffi, nnet
+    blocks = 2
+    tens = nnet.synthetic_tensors(seed=33, filters=128, blocks=blocks, bn_stats="random")
+    gnet = _ffi.Net(ctx, tens)
+    gnet.set_precision(_ffi.NET_FP32)
+    n, iters, seed = 24, 30, 5
+    states = positions.midgame_positions(seed=seed, n=n, max_adv=100)
+    ids = np.arange(500, 500 + n, dtype=np.uint32)
+    cfg = oracle.mcts_cfg(iterations=iters, c=2.0, limit=400, alpha=0.3, eps=0.25)
+    max_nodes = 1 + (iters + 1) * 40
+
+    def torch_fp32(st):
+        x = np.concatenate([oracle.bg_as_tensor(st[i:i + 1]) for i in range(len(st))])
+        p, v = net_oracle.forward(tens, x, blocks, dtype=torch.float32)
+        return p.astype(np.float32), v.astype(np.float32)
+    o_nodes, o_n, o_status = oracle.alpha_mcts_parallel(states, ids, cfg, seed, 2, oracle.make_eval(torch_fp32), max_nodes)
+    r_ids, r_moves, r_vis, r_cnt, status, nodes, n_nodes = ctx.alpha_search(gnet, states, ids, cfg, seed, epoch=2,
+                                                                            max_nodes=max_nodes, dump=True)
+    assert (status == o_status).all()
+    same, worst_tv, worst_q = 0, 0.0, 0.0
+    for g in range(n):
+        root = o_nodes[g, 0]
+        nc = int(root["n_children"])
+        assert r_cnt[g] == nc
+        ch = o_nodes[g, root["first_child"]:root["first_child"] + nc]
+        assert r_moves[g, :nc].tobytes() == ch["action"].tobytes()       # legal moves and their order never depend on the net
+        a, b = r_vis[g, :nc].astype(np.float64), ch["visits"].astype(np.float64)
+        if nc:
+            worst_tv = max(worst_tv, 0.5 * np.abs(a / max(a.sum(), 1) - b / max(b.sum(), 1)).sum())
+        if (a == b).all():
+            same += 1
+            gch = nodes[g, nodes[g, 0]["first_child"]:nodes[g, 0]["first_child"] + nc]
+            vis = b > 0
+            qa = gch["value"][vis].astype(np.float64) / b[vis]
+            qb = ch["value"][vis].astype(np.float64) / b[vis]
+            if vis.any():
+                worst_q = max(worst_q, (np.abs(qa - qb) / np.maximum(np.abs(qb), 1e-2)).max())
+    print(f"\n[alpha end-to-end fp32] identical root visit counts {same}/{n}, worst TV {worst_tv:.2e}, worst value rel {worst_q:.2e}")
+    assert same >= 0.95 * n and worst_tv <= 1e-2 and worst_q <= 1e-5
+    gnet.close()
+
+
 def test_alpha_search_endgame_quirks(ctx, net, oracle):
     """positions one move from the end: terminal leaves (value +-1 w.r.t. the root player), stale slots that
     hit game 0's root (Q9), a root with no legal move (Q12) and an already finished game"""

@@ -383,6 +383,21 @@ def alpha_mcts_parallel(states, game_ids, cfg, seed, epoch, eval_cb, max_nodes):
     return nodes, n_nodes, status
 
 
+def root_pi(nodes_row, temperature_inv):
+    """get_prob_tensor_parallel row + pow(1/T) for one game's tree (utils.rs:42-58, alpha_parallel.rs:164-166)"""
+    row = np.ascontiguousarray(nodes_row)
+    ids = np.zeros(MAX_MOVES, dtype=np.uint16)
+    pi = np.zeros(MAX_MOVES, dtype=np.float32)
+    n = lib().orc_root_pi(_p(row), C.c_float(temperature_inv), _p(ids), _p(pi))
+    return ids[:n].copy(), pi[:n].copy()
+
+
+def weighted_select(ids, pi, seed, game_id, ply):
+    ids = np.ascontiguousarray(ids, dtype=np.uint16)
+    pi = np.ascontiguousarray(pi, dtype=np.float32)
+    return int(lib().orc_weighted_select(_p(ids), _p(pi), C.c_int(len(ids)), C.c_uint64(seed), C.c_uint32(game_id), C.c_uint32(ply)))
+
+
 def self_play(n_games, cfg, temperature, seed, first_game_id, eval_cb, max_nodes):
     limit = int(cfg["simulate_round_limit"][0])
     rec_cap = n_games * (2 * limit + 4)

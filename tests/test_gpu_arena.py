@@ -1,0 +1,79 @@
+"""GPU parity tests of the arena (`versus::play`, src/versus.rs:160-318 -- SURVEY 8(f) rank 1) against its oracle
+twin (tests/orc_arena.py: the same rounds played one game at a time on the CPU oracle).  Bar: identical -- every
+game's winner and the round it ended in, hence wins / draws / winrate."""
+import numpy as np
+import pytest
+
+import orc_arena
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from die_e_b200 import _ffi
+    return _ffi.Context(0)
+
+
+def _same(res, want):
+    w1, w2, winners, rounds = want
+    assert (res.winners == winners).all() and (res.rounds == rounds).all()
+    assert (res.wins_p1, res.wins_p2, res.draws) == (w1, w2, res.n_games - w1 - w2)
+
+
+def test_backgammon_random_vs_random(ctx, oracle):
+    from die_e_b200.versus import Agent, Player, play
+    res = play("backgammon", Player(Agent.Random), Player(Agent.Random), seed=11, num_games=64, round_limit=400, ctx=ctx)
+    _same(res, orc_arena.play_backgammon("random", "random", None, 1.0, 11, 64, 400))
+    assert res.wins_p1 + res.wins_p2 + res.draws == 64 and res.draws <= 2
+    # the round limit: games still running when it is reached are draws once they have played a move
+    res = play("backgammon", Player(Agent.Random), Player(Agent.Random), seed=12, num_games=16, round_limit=30, ctx=ctx)
+    _same(res, orc_arena.play_backgammon("random", "random", None, 1.0, 12, 16, 30))
+    assert res.draws > 0 and "Winrate" in str(res)
+
+
+def test_backgammon_mcts_vs_random(ctx, oracle):
+    from die_e_b200 import _ffi
+    from die_e_b200.mcts import MctsConfig
+    from die_e_b200.versus import Agent, Player, play
+    for mode in (_ffi.MODE_PASS_CHILD, _ffi.MODE_PASS_CHILD | _ffi.MODE_ROLLOUT_CHECK_CURRENT):
+        cfg = MctsConfig(iterations=16, c=2.0, simulate_round_limit=40, mode_flags=mode)
+        ocfg = oracle.mcts_cfg(iterations=16, c=2.0, limit=40, mode=mode)
+        res = play("backgammon", Player(Agent.Mcts), Player(Agent.Random), cfg, seed=21, num_games=12, round_limit=400, ctx=ctx)
+        _same(res, orc_arena.play_backgammon("mcts", "random", ocfg, 1.0, 21, 12, 400))
+        res = play("backgammon", Player(Agent.Random), Player(Agent.Mcts), cfg, seed=22, num_games=8, round_limit=400, ctx=ctx)
+        _same(res, orc_arena.play_backgammon("random", "mcts", ocfg, 1.0, 22, 8, 400))
+
+
+def test_tictactoe_mcts_vs_random_is_config_1(ctx, oracle):
+    """BASELINE configs[0]: Tic-Tac-Toe MCTS agent vs random, iterations=100, random rollouts (`die-e -g tic-tac-toe play`)"""
+    from die_e_b200.mcts import MctsConfig
+    from die_e_b200.versus import Agent, Player, play
+    cfg = MctsConfig(iterations=100, c=2.0, simulate_round_limit=400)
+    ocfg = oracle.mcts_cfg(iterations=100, c=2.0, limit=400)
+    res = play("tictactoe", Player(Agent.Mcts), Player(Agent.Random), cfg, seed=31, num_games=60, ctx=ctx)
+    _same(res, orc_arena.play_tictactoe("mcts", "random", ocfg, 31, 60, 400))
+    # the reference's own size: 400 games, first 200 started by player 1
+    import time
+    t0 = time.perf_counter()
+    full = play("tictactoe", Player(Agent.Mcts), Player(Agent.Random), cfg, seed=0xD1EE, ctx=ctx)
+    dt = time.perf_counter() - t0
+    assert full.n_games == 400 and full.wins_p1 + full.wins_p2 + full.draws == 400
+    t0 = time.perf_counter()
+    orc_arena.play_tictactoe("mcts", "random", ocfg, 0xD1EE, 400, 400)
+    dt_cpu = time.perf_counter() - t0
+    print(f"\n[C1] tictactoe MCTS(100) vs random, 400 games: {full.wins_p1} / {full.wins_p2} / {full.draws} "
+          f"(winrate {full.winrate:.3f}); arena wall time {dt * 1e3:.0f} ms on the GPU engine, {dt_cpu * 1e3:.0f} ms oracle twin (1 core)")
+
+
+def test_backgammon_model_vs_random(ctx, oracle):
+    from die_e_b200 import _ffi, nnet
+    from die_e_b200.mcts import MctsConfig
+    from die_e_b200.versus import Agent, Player, play
+    model = nnet.ResNet.new(seed=41, filters=128, blocks=1, bn_stats="random", ctx=ctx)
+    cfg = MctsConfig(iterations=8, c=2.0, simulate_round_limit=400, dirichlet_alpha=0.3, dirichlet_epsilon=0.25)
+    ocfg = oracle.mcts_cfg(iterations=8, c=2.0, limit=400, alpha=0.3, eps=0.25)
+    cb = oracle.make_eval(lambda st: model._net.forward(st))   # identical net outputs on both sides
+    res = play("backgammon", Player(Agent.Model, model), Player(Agent.Random), cfg, temp=1.25, seed=51, num_games=6,
+               round_limit=60, ctx=ctx)
+    _same(res, orc_arena.play_backgammon("model", "random", ocfg, 1.25, 51, 6, 60, eval_cb=cb, max_nodes=1 + 9 * 60))

@@ -60,3 +60,12 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 src = open(os.path.join(d, f)).read()
                 assert "oracle/" not in src and "liborc" not in src and "import orc" not in src, f
+
+
+def test_arena_surface_matches_the_reference_cli():
+    """versus.rs:124-130 / main.rs:15-83: agent names as clap prints them; the arena needs the GPU engine"""
+    from die_e_b200.versus import Agent, Player, PlayResult
+    assert [a.value for a in Agent] == ["model", "mcts", "random", "none"]
+    r = PlayResult(Agent.Mcts, Agent.Random, 3, 1, 5, None, None)
+    assert r.draws == 1 and abs(r.winrate - 0.6) < 1e-12 and "Wins Player 1: 3" in str(r)
+    assert Player(Agent.Random).model is None

@@ -80,6 +80,69 @@ def memory_to_arrays(rec, pi_ids, pi_vals, ctx=None):
     return ps, states, rec["outcome"].astype(np.int8)
 
 
+# ---- replay-buffer files: what the (unchanged) tch training loop reads back (SURVEY 8(f) rank 2) ----
+# `Tensor::save` (tch) is libtorch's `torch::save(tensor, path)`: a TorchScript archive holding ONE tensor under the
+# key "0".  The reference writes three of them per self-play iteration (alphazero.rs:149-176):
+#   ps.ot [M,1352] f32, states.ot [M,6,4,6] f32 (Tensor::concat of the [1,6,4,6] states), outcomes.ot [M] i8
+# under ./data/<game>/run-<id>/lrn-<i>/sp-<j>/ (alpha_parallel.rs:18-21,43-44,60-62).  Unverified against a file
+# written by tch itself (the reference ships none and there is no Rust toolchain here).
+def _save_tensor_ot(path, array):
+    import torch
+
+    class Holder(torch.nn.Module):
+        pass
+    m = Holder()
+    t = torch.from_numpy(np.ascontiguousarray(array))
+    if t.is_floating_point():
+        m.register_parameter("0", torch.nn.Parameter(t, requires_grad=False))
+    else:
+        m.register_buffer("0", t)
+    torch.jit.script(m).save(str(path))
+
+
+def _load_tensor_ot(path):
+    import torch
+    mod = torch.jit.load(str(path), map_location="cpu")
+    named = dict(list(mod.named_parameters()) + list(mod.named_buffers()))
+    if len(named) != 1:
+        raise ValueError(f"{path}: expected a single saved tensor, found {sorted(named)}")
+    return next(iter(named.values())).detach().cpu().numpy()
+
+
+def sp_dir(game_name, run_id, learn_iteration, self_play_iteration, base="."):
+    """./data/<game>/run-<id>/lrn-<i>/sp-<j>  (alpha_parallel.rs:18-21,43-44,60-62)"""
+    import os
+    return os.path.join(base, "data", game_name, f"run-{run_id}", f"lrn-{learn_iteration}", f"sp-{self_play_iteration}")
+
+
+def save_training_data(data, path, ctx=None):
+    """`AlphaZero::save_training_data(&self, data: &[MemoryFragment], path)` (alphazero.rs:149-176).
+    `data` is a list of MemoryFragment or the packed triple (records, pi_ids, pi_vals) of self_play_parallel(packed=True)."""
+    import os
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"path: {path} does not exist!")  # the reference panics
+    if isinstance(data, tuple):
+        ps, states, outcomes = memory_to_arrays(*data, ctx=ctx)
+    else:
+        ps = np.stack([f.ps for f in data]) if data else np.zeros((0, _ffi.ACTION_SPACE), np.float32)
+        states = np.concatenate([f.state for f in data]) if data else np.zeros((0, 6, 4, 6), np.float32)
+        outcomes = np.array([f.outcome for f in data], dtype=np.int8)
+    _save_tensor_ot(os.path.join(path, "ps.ot"), ps.astype(np.float32))
+    _save_tensor_ot(os.path.join(path, "states.ot"), states.astype(np.float32))
+    _save_tensor_ot(os.path.join(path, "outcomes.ot"), outcomes.astype(np.int8))
+
+
+def load_training_data(path):
+    """`AlphaZero::load_training_data(path) -> Vec<MemoryFragment>` (alphazero.rs:178-200)"""
+    import os
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"path: {path} does not exist!")
+    ps = _load_tensor_ot(os.path.join(path, "ps.ot"))
+    states = _load_tensor_ot(os.path.join(path, "states.ot"))
+    outcomes = _load_tensor_ot(os.path.join(path, "outcomes.ot"))
+    return [MemoryFragment(int(outcomes[i]), ps[i], states[i:i + 1]) for i in range(len(ps))]
+
+
 class AlphaZero:
     """alphazero.rs:60-67: model + configs.  Only the self-play half is served by this engine."""
 

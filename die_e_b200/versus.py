@@ -48,7 +48,88 @@ class Player:  # versus.rs:124-127
         self.player_type, self.model = player_type, model
 
 
+_AGENT_SERDE = {Agent.Random: "Random", Agent.Mcts: "Mcts", Agent.Model: "Model", Agent.Nobody: "None"}  # serde variant names
+
+
+class Game:
+    """`Game<T>` (versus.rs:27-50) and its JSON wire format (serde derive): {"id", "player1", "player2", "turns",
+    "winner", "initial_state"}; a Backgammon state serialises as {"board": [[24 x i8], [hit0, hit1], [col0, col1]],
+    "roll": [a, b], "player": +-1, "is_second_play": bool, "id": n} (backgammon_logic.rs:53-60), a TicTacToe state as
+    {"board": [9 x i8], "player": +-1, "id": n}.  The reference never fills `turns` (versus.rs:47 only creates it)
+    and types `Turn::action` as Vec<T>; files written here keep `turns` empty so the reference's `load_game` reads
+    them, unless the arena is asked to record turns (an extension: roll, action as [from, to] pairs, agent)."""
+
+    def __init__(self, game_id, player1, player2, initial_state, winner=Agent.Nobody, turns=None):
+        self.id, self.player1, self.player2 = game_id, player1, player2
+        self.initial_state, self.winner, self.turns = initial_state, winner, turns or []
+
+    def to_json(self):
+        return {"id": self.id, "player1": _AGENT_SERDE[self.player1], "player2": _AGENT_SERDE[self.player2],
+                "turns": self.turns, "winner": _AGENT_SERDE[self.winner], "initial_state": self.initial_state}
+
+    @classmethod
+    def from_json(cls, d):
+        rev = {v: k for k, v in _AGENT_SERDE.items()}
+        return cls(d["id"], rev[d["player1"]], rev[d["player2"]], d["initial_state"], rev[d["winner"]], d.get("turns", []))
+
+
+def _bg_state_json(s, idx):
+    return {"board": [[int(v) for v in s["pts"]], [int(s["bar"][0]), int(s["bar"][1])], [int(s["off"][0]), int(s["off"][1])]],
+            "roll": [int(s["roll"][0]), int(s["roll"][1])], "player": int(s["player"]), "is_second_play": bool(s["second"]),
+            "id": int(idx)}
+
+
+def _game_id(seed, idx):
+    """a 21-character id like nanoid's (versus.rs:45), but reproducible: drawn from the INIT stream of the game"""
+    alphabet = "useandom-26T198340PX75pxJACKVERYMINDBUSHWOLF_GQZbfghjklqvwyzrict"  # nanoid's url alphabet
+    out = []
+    for blk in range(6):
+        for w in _ffi.philox(seed, 1 + blk, idx, _ffi.STREAM_INIT, 0):
+            out.append(alphabet[int(w) & 63])
+    return "".join(out[:21])
+
+
+def save_game(game, game_path):
+    """versus.rs:52-61: <game_path>/<id>.json, pretty-printed"""
+    import json
+    import os
+    path = os.path.join(game_path, f"{game.id}.json")
+    with open(path, "w") as f:
+        f.write(json.dumps(game.to_json(), indent=2))
+    return path
+
+
+def load_game(path):
+    """versus.rs:63-71"""
+    import json
+    with open(path) as f:
+        return Game.from_json(json.load(f))
+
+
+def load_all_games(path):
+    """versus.rs:107-122: every *.json file of the directory"""
+    import os
+    return [load_game(os.path.join(path, n)) for n in sorted(os.listdir(path)) if n.endswith(".json") and os.path.isfile(os.path.join(path, n))]
+
+
+def print_game(path, out=print):
+    """the `replay` subcommand (versus.rs:73-105, main.rs:208-213), without the interactive pause"""
+    game = load_game(path)
+    out(f"Game ID: {game.id}")
+    out(f"Player 1: {_AGENT_SERDE[game.player1]}, Player 2: {_AGENT_SERDE[game.player2]}")
+    out(f"Game winner: {_AGENT_SERDE[game.winner]}")
+    out("Initial State:")
+    out(str(game.initial_state))
+    for turn in game.turns:
+        out(f"Player: {turn.get('player')}")
+        out(f"Roll: {turn.get('roll')}")
+        out(f"Action: {turn.get('action')}")
+    return game
+
+
 class PlayResult:  # versus.rs:130-152
+    games = ()  # Vec<Game<T>> in the order the games were retired (filled when the arena keeps games)
+
     def __init__(self, player1, player2, wins_p1, wins_p2, n_games, winners, rounds):
         self.player1, self.player2, self.wins_p1, self.wins_p2, self.n_games = player1, player2, wins_p1, wins_p2, n_games
         self.draws = n_games - (wins_p1 + wins_p2)
@@ -157,10 +238,14 @@ def _bg_actions(ctx, player, side, states, live_ids, all_states, cfg, temp, seed
     raise ValueError("Agent::None cannot play (versus.rs:316)")
 
 
-def play_backgammon(player1, player2, mcts_config=None, temp=1.0, seed=0xD1EE, num_games=400, round_limit=400, ctx=None):
+def play_backgammon(player1, player2, mcts_config=None, temp=1.0, seed=0xD1EE, num_games=400, round_limit=400, ctx=None,
+                    keep_games=False, record_turns=False):
     ctx = ctx or _ffi.default_context()
     cfg = mcts_config or MctsConfig()
     states = _bg_initial(num_games, seed)
+    games = [Game(_game_id(seed, g), player1.player_type, player2.player_type, _bg_state_json(states[g], g))
+             for g in range(num_games)] if keep_games else None
+    retired = []
     live = np.ones(num_games, dtype=bool)
     winners = np.zeros(num_games, dtype=np.int8)
     rounds = np.zeros(num_games, dtype=np.int32)
@@ -179,6 +264,12 @@ def play_backgammon(player1, player2, mcts_config=None, temp=1.0, seed=0xD1EE, n
         for i, g in enumerate(order):
             o = _ffi.philox(seed, round_count, int(g), _ffi.STREAM_GAME, 0)
             rolls[i] = (_ffi.die_of(o[0]), _ffi.die_of(o[1]))
+        if keep_games and record_turns:
+            from .backgammon import _move_list
+            for i, g in enumerate(order):
+                mover = player1 if states["player"][g] == -1 else player2
+                games[g].turns.append({"roll": [int(states["roll"][g][0]), int(states["roll"][g][1])],
+                                       "action": [list(p) for p in _move_list(acts[i])], "player": _AGENT_SERDE[mover.player_type]})
         states[order] = ctx.bg_apply_moves(states[order], acts, rolls)  # EMPTY_MOVE -> skip_turn
         round_count += 1
         for i, g in enumerate(order):
@@ -193,7 +284,13 @@ def play_backgammon(player1, player2, mcts_config=None, temp=1.0, seed=0xD1EE, n
                 winners[g], rounds[g] = w, round_count
                 wins_p1 += w == -1
                 wins_p2 += w == 1
-    return PlayResult(player1.player_type, player2.player_type, int(wins_p1), int(wins_p2), num_games, winners, rounds)
+                if keep_games:  # versus.rs:236-246
+                    games[g].winner = player1.player_type if w == -1 else (player2.player_type if w == 1 else Agent.Nobody)
+                    retired.append(games[g])
+    res = PlayResult(player1.player_type, player2.player_type, int(wins_p1), int(wins_p2), num_games, winners, rounds)
+    if keep_games:
+        res.games = retired
+    return res
 
 
 # ---------------------------------------------------------------- tictactoe (BASELINE configs[0])

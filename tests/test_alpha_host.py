@@ -51,3 +51,32 @@ def test_oracle_self_play_records(oracle):
         ids = pi_ids[r["pi_offset"]:r["pi_offset"] + r["n_pi"]]
         want = [oracle.bg_encode(np.array([r["state"]]), m) for m in oracle.bg_valid_moves(np.array([r["state"]]))]
         assert list(ids) == want
+
+
+def test_training_data_files_round_trip(tmp_path):
+    """ps.ot / states.ot / outcomes.ot as the tch training loop reads them (alphazero.rs:149-200)"""
+    import numpy as np
+    import pytest
+    import torch
+    from die_e_b200 import alphazero
+    rng = np.random.default_rng(3)
+    data = []
+    for i in range(7):
+        ps = np.zeros(1352, dtype=np.float32)
+        ps[rng.integers(0, 1352, 5)] = rng.random(5, dtype=np.float32)
+        data.append(alphazero.MemoryFragment(int(rng.integers(-1, 2)), ps, rng.integers(-3, 4, (1, 6, 4, 6)).astype(np.float32)))
+    d = tmp_path / alphazero.sp_dir("backgammon", "abc", 2, 1, base="")
+    with pytest.raises(FileNotFoundError):
+        alphazero.save_training_data(data, d)
+    d.mkdir(parents=True)
+    assert str(d).endswith("data/backgammon/run-abc/lrn-2/sp-1")
+    alphazero.save_training_data(data, d)
+    # each file is a libtorch archive holding one tensor under the key "0" (what tch's Tensor::load expects)
+    for name, shape, dtype in (("ps.ot", (7, 1352), torch.float32), ("states.ot", (7, 6, 4, 6), torch.float32), ("outcomes.ot", (7,), torch.int8)):
+        mod = torch.jit.load(str(d / name))
+        named = dict(list(mod.named_parameters()) + list(mod.named_buffers()))
+        assert list(named) == ["0"] and tuple(named["0"].shape) == shape and named["0"].dtype == dtype
+    back = alphazero.load_training_data(d)
+    assert len(back) == 7
+    for a, b in zip(data, back):
+        assert a.outcome == b.outcome and (a.ps == b.ps).all() and (a.state == b.state).all() and b.state.shape == (1, 6, 4, 6)

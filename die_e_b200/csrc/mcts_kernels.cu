@@ -46,31 +46,51 @@ __device__ __forceinline__ void bg_to_planes(const BgWarp &g, lane::LaneBoard &b
     b.roll0 = g.roll0; b.roll1 = g.roll1; b.player = g.player; b.second = g.second;
 }
 
+// Number of legal plays of the warp's game and (k >= 0) the k-th of them, as (overflow << 63 | U << 32 | play).
+// Contact play and bar entries are counted in closed form by the lane engine (bg_lane.cuh) -- ~10x fewer
+// instructions than building the list -- redundantly on every lane; positions in the bear-off regime build
+// the list cooperatively.  One out-of-line copy (the tree kernel calls it three times per iteration and is
+// instruction-fetch bound); everything travels BY VALUE in registers: a reference to the caller's board
+// would force it into local memory and every call would start with a round trip through it.
+__device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal, WarpSlab *slab, int lane, int k) {
+    BgWarp g;
+    g.v = v;
+    g.bar0 = (int)(scal & 15u); g.bar1 = (int)((scal >> 4) & 15u); g.off0 = (int)((scal >> 8) & 15u); g.off1 = (int)((scal >> 12) & 15u);
+    g.roll0 = (int)((scal >> 16) & 15u); g.roll1 = (int)((scal >> 20) & 15u);
+    g.player = ((scal >> 24) & 1u) ? 1 : -1;
+    g.second = (int)((scal >> 25) & 1u);
+    lane::LaneBoard b;
+    bg_to_planes(g, b);
+    const int hi = max(g.roll0, g.roll1), lo = min(g.roll0, g.roll1);
+    lane::LaneMasks m;
+    const bool closed = lane::l_closed_applies(b, m, lo, hi);
+    uint32_t seq = SEQ_EMPTY;
+    if (closed || b.bar_own > 0 || m.own1 == 0) {
+        lane::LaneGen gen;
+        gen.U = 0;
+        if (b.bar_own > 0) lane::l_movegen_bar(b, m, lo, hi, gen);
+        else if (m.own1 != 0) lane::l_movegen_closed(b, m, lo, hi, gen);
+        if (k >= 0 && k < gen.U) seq = lane::l_play_to_seq(lane::l_pick(b, gen, nullptr, 0, k), g.player);
+        return ((unsigned long long)(uint32_t)gen.U << 32) | seq;
+    }
+    bool ovf = false;
+    const int U = bg_movegen(g, *slab, lane, ovf);
+    if (k >= 0 && k < U) seq = slab->raw[k];
+    __syncwarp();
+    return ((unsigned long long)ovf << 63) | ((unsigned long long)(uint32_t)U << 32) | seq;
+}
+
 struct BgGame {
     using State = diee_bg_state;
     BgWarp g;
-    // Number of legal plays and (k >= 0) the k-th of them.  Contact play and bar entries are counted in
-    // closed form by the lane engine (bg_lane.cuh) -- ~10x fewer instructions than building the list --
-    // redundantly on every lane; positions in the bear-off regime build the list cooperatively.
-    // (one out-of-line copy: the tree kernel calls it three times per iteration and is instruction-fetch bound)
-    __device__ __noinline__ int count_and_kth(WarpSlab &slab, int lane, bool &ovf, int k, uint32_t &seq) const {
-        lane::LaneBoard b;
-        bg_to_planes(g, b);
-        const int hi = max(g.roll0, g.roll1), lo = min(g.roll0, g.roll1);
-        lane::LaneMasks m;
-        const bool closed = lane::l_closed_applies(b, m, lo, hi);
-        if (closed || b.bar_own > 0 || m.own1 == 0) {
-            lane::LaneGen gen;
-            gen.U = 0;
-            if (b.bar_own > 0) lane::l_movegen_bar(b, m, lo, hi, gen);
-            else if (m.own1 != 0) lane::l_movegen_closed(b, m, lo, hi, gen);
-            if (k >= 0 && k < gen.U) seq = lane::l_play_to_seq(lane::l_pick(b, gen, nullptr, 0, k), g.player);
-            return gen.U;
-        }
-        const int U = bg_movegen(g, slab, lane, ovf);
-        if (k >= 0 && k < U) seq = slab.raw[k];
-        __syncwarp();
-        return U;
+    __device__ __forceinline__ int count_and_kth(WarpSlab &slab, int lane, bool &ovf, int k, uint32_t &seq) const {
+        const uint32_t scal = (uint32_t)g.bar0 | ((uint32_t)g.bar1 << 4) | ((uint32_t)g.off0 << 8) | ((uint32_t)g.off1 << 12) |
+                              ((uint32_t)g.roll0 << 16) | ((uint32_t)g.roll1 << 20) | ((g.player > 0 ? 1u : 0u) << 24) |
+                              ((uint32_t)(g.second ? 1 : 0) << 25);
+        const unsigned long long r = bg_count_and_kth(g.v, scal, &slab, lane, k);
+        if (r >> 63) ovf = true;
+        if (k >= 0) seq = (uint32_t)r;
+        return (int)((r >> 32) & 0x7FFFFFFFu);
     }
     __device__ __forceinline__ void load(const State *s, int lane) { bg_load(g, s, lane); }
     __device__ __forceinline__ void store(State *s, int lane) const { bg_store(g, s, lane); }

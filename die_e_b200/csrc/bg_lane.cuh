@@ -689,12 +689,112 @@ LANE_HD LanePlay l_pick_bar(const LaneBoard &g, const LaneMasks &m, int lo, int 
     return l_play_from(L_BAR, hi, lo, t.single1 ? L_SINGLE : t.N1, k - t.n0, isplus);
 }
 
+// ---------------- pure bear-off: every own checker in the home board, no opposing checker there ----------------
+// Six points, no hits, no blocks: the sources of die d are the own points >= d-1 (d-1 itself collects, the higher
+// ones move down), or, when all checkers sit below d-1, the highest own point (it collects with the bigger die).
+// The walk over roots is then twelve predicated steps on 6-bit masks; plays are told apart in registers:
+// net single moves F -> a in four 6-bit masks (as everywhere), plays whose two sub-moves are interchangeable
+// (doubles; both collect) in a symmetric 6x6 bit matrix, all others in a 6x6 matrix indexed
+// (point moved by the low die, point moved by the high die).  Same scratch output as l_movegen_walk.
+LANE_HD bool l_pure_bearoff(const LaneBoard &g) {
+    const uint32_t own1 = g.own[0] | g.own[1] | g.own[2] | g.own[3];
+    const uint32_t oppany = g.opp[0] | g.opp[1] | g.opp[2] | g.opp[3];
+    return g.bar_own == 0 && own1 != 0 && (own1 & ~0x3Fu) == 0 && (oppany & 0x3Fu) == 0;
+}
+LANE_HD uint32_t l_pb_sources(int d, uint32_t own) {
+    const uint32_t upper = own & ~((1u << (d - 1)) - 1u);
+    return upper ? upper : (own ? (1u << l_high(own)) : 0u);
+}
+LANE_HD void l_movegen_pb(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stride) {
+    const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;
+    const bool dbl = hi == lo;
+    const bool isplus = g.player > 0;
+    const uint32_t o123 = g.own[1] | g.own[2] | g.own[3];
+    const uint32_t own = (g.own[0] | o123) & 0x3Fu;
+    const uint32_t single = g.own[0] & ~o123 & 0x3Fu;
+    gen.isplus = isplus;
+    gen.closed = false;
+    gen.N0 = 0;
+    gen.lo = lo;
+    gen.hi = hi;
+    gen.R0 = gen.R1 = 0;
+    uint32_t seen_lo = 0, seen_hi = 0, seen_sum = 0, seen_off = 0;
+    uint64_t seen_any = 0, seen_ord = 0;  // bit 6*a + b
+    int U = 0, slot = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int b = 0; b < 2; ++b) {
+        if (b == 1 && dbl) break;
+        const int m1 = b == 0 ? lo : hi, m2 = b == 0 ? hi : lo;
+        const uint32_t R = l_pb_sources(m1, own);
+        if (b == 0) gen.R0 = R; else gen.R1 = R;
+        uint32_t r = R;
+        while (r) {
+            const int x = l_take(r, isplus);
+            const uint32_t xb = 1u << x;
+            r &= ~xb;
+            const bool off1 = x < m1;                       // the first sub-move collects
+            const uint32_t t1b = off1 ? 0u : (xb >> m1);
+            const uint32_t ownp = (own & ~(single & xb)) | t1b;
+            const uint32_t C = l_pb_sources(m2, ownp);
+            uint32_t newm = 0;
+            if (C == 0) {
+                const bool fresh = off1 ? l_test_and_set(seen_off, xb) : (b == 0 ? l_test_and_set(seen_lo, xb) : l_test_and_set(seen_hi, xb));
+                if (fresh) newm = L_SINGLE;
+            } else {
+                const uint32_t runbit = t1b & C;                                   // the same checker moves on: F = x
+                const uint32_t refbit = (xb << m2) & 0x3Fu & C;                    // a checker refills x: F = x + m2
+                if (runbit) {
+                    const bool off2 = (x - m1) < m2;
+                    if (off2 ? l_test_and_set(seen_off, xb) : l_test_and_set(seen_sum, xb)) newm |= runbit;
+                }
+                if (refbit) {
+                    if (off1 ? l_test_and_set(seen_off, refbit) : l_test_and_set(seen_sum, refbit)) newm |= refbit;
+                }
+                const uint32_t rest = C & ~(runbit | refbit);
+                // interchangeable sub-moves: doubles, or both collect (second collects iff its point < m2)
+                const uint32_t anym = dbl ? rest : (off1 ? (rest & ((1u << m2) - 1u)) : 0u);
+                const uint32_t ordm = rest & ~anym;
+                if (anym) {
+                    const uint32_t row = (uint32_t)(seen_any >> (6 * x)) & 0x3Fu;
+                    newm |= anym & ~row;
+                    seen_any |= (uint64_t)anym << (6 * x);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int y = 0; y < 6; ++y)
+                        if ((anym >> y) & 1u) seen_any |= 1ull << (6 * y + x);
+                }
+                if (ordm) {
+                    if (b == 0) {
+                        newm |= ordm;
+                        seen_ord |= (uint64_t)ordm << (6 * x);
+                    } else {  // (child by the low die, this root by the high die): seen iff row[child] has bit x
+                        uint32_t dup = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                        for (int y = 0; y < 6; ++y) dup |= (uint32_t)((seen_ord >> (6 * y + x)) & 1ull) << y;
+                        newm |= ordm & ~dup;
+                    }
+                }
+            }
+            scr[slot * stride] = newm;
+            ++slot;
+            U += l_popc(newm);
+        }
+    }
+    gen.U = U;
+}
+
 // Counts the distinct plays of `g`.  Contact play is counted in closed form; otherwise root by root.
 LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stride) {
     const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;
     LaneMasks m;
     if (l_closed_applies(g, m, lo, hi)) l_movegen_closed(g, m, lo, hi, gen);
     else if (g.bar_own > 0) l_movegen_bar(g, m, lo, hi, gen);
+    else if (l_pure_bearoff(g)) l_movegen_pb(g, gen, scr, stride);
     else l_movegen_walk(g, gen, scr, stride);
 }
 

@@ -73,6 +73,14 @@ __device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal
         if (k >= 0 && k < gen.U) seq = lane::l_play_to_seq(lane::l_pick(b, gen, nullptr, 0, k), g.player);
         return ((unsigned long long)(uint32_t)gen.U << 32) | seq;
     }
+    if (lane::l_pure_bearoff(b)) {  // six-point mask walk, redundantly on every lane; the slab is its scratch
+        lane::LaneGen gen;
+        lane::l_movegen_pb(b, gen, slab->raw, 1);
+        __syncwarp();
+        if (k >= 0 && k < gen.U) seq = lane::l_play_to_seq(lane::l_pick_walk(gen, slab->raw, 1, k), g.player);
+        __syncwarp();
+        return ((unsigned long long)(uint32_t)gen.U << 32) | seq;
+    }
     bool ovf = false;
     const int U = bg_movegen(g, *slab, lane, ovf);
     if (k >= 0 && k < U) seq = slab->raw[k];

@@ -35,7 +35,7 @@ static void print_state(const orc_bg_state &s) {
 
 static long long n_checked = 0, n_moves_checked = 0, n_boregime = 0, n_bo_opp_home = 0, n_doubles = 0, n_bar = 0;
 static int max_moves = 0;
-static long long n_closed = 0;
+static long long n_closed = 0, n_pb = 0;
 
 static bool check_position(const orc_bg_state &s) {
     uint32_t w[8];
@@ -67,6 +67,7 @@ static bool check_position(const orc_bg_state &s) {
         if (g.bar_own > 0 && n > 0) ++n_bar;
         if (n > max_moves) max_moves = n;
         if (gen.closed && n > 0) ++n_closed;
+        if (l_pure_bearoff(g) && n > 0) ++n_pb;
     }
     if (gen.U != n) {
         fprintf(stderr, "count differs: lane %d oracle %d\n", gen.U, n);
@@ -221,7 +222,7 @@ int main(int argc, char **argv) {
         if (!check_position(s)) return 1;
     }
     printf("lane engine == oracle on %lld positions, %lld plays (bear-off regime %lld, of which opposing checkers in the home board %lld; "
-           "doubles %lld; from the bar %lld; counted in closed form %lld; most plays in one position %d)\n",
-           n_checked, n_moves_checked, n_boregime, n_bo_opp_home, n_doubles, n_bar, n_closed, max_moves);
+           "doubles %lld; from the bar %lld; counted in closed form %lld; pure bear-off form %lld; most plays in one position %d)\n",
+           n_checked, n_moves_checked, n_boregime, n_bo_opp_home, n_doubles, n_bar, n_closed, n_pb, max_moves);
     return 0;
 }

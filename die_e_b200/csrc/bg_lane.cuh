@@ -798,6 +798,33 @@ LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stri
     else l_movegen_walk(g, gen, scr, stride);
 }
 
+// Root walk of the closed forms.  Root number i (in `from` order) contributes
+//     base - (tri ? i : 0) + [in plus0] + [in plus1] - [in minus0] - [in minus1]
+// plays (base = children every root has, tri = the triangular correction of doubles, the masks = the roots that
+// gain or lose one play), so finding the root that holds play k needs a few bit tests per root; that root's
+// mask of new children is built once, afterwards.
+struct LaneCum {
+    uint32_t R, plus0, plus1, minus0, minus1;
+    int base;
+    bool tri;
+};
+// -> one-hot bit of the root holding play k; j = the play's index within that root
+LANE_HD uint32_t l_find_root(const LaneCum &c, int k, bool isplus, int &j) {
+    uint32_t r = c.R, xb = 0;
+    int acc = 0, rank = 0;
+    while (r) {
+        xb = isplus ? (0x80000000u >> (31 - l_high(r))) : (r & (0u - r));
+        r ^= xb;
+        const int cnt = c.base - (c.tri ? rank : 0) + ((c.plus0 & xb) ? 1 : 0) + ((c.plus1 & xb) ? 1 : 0) -
+                        ((c.minus0 & xb) ? 1 : 0) - ((c.minus1 & xb) ? 1 : 0);
+        if (k < acc + cnt) break;
+        acc += cnt;
+        ++rank;
+    }
+    j = k - acc;
+    return xb;
+}
+
 // the k-th distinct play (0 <= k < gen.U) in reference order
 LANE_HD LanePlay l_pick(const LaneBoard &g, const LaneGen &gen, const uint32_t *scr, int stride, int k) {
     if (!gen.closed) return l_pick_walk(gen, scr, stride, k);
@@ -806,48 +833,37 @@ LANE_HD LanePlay l_pick(const LaneBoard &g, const LaneGen &gen, const uint32_t *
     LaneMasks m;
     l_closed_applies(g, m, lo, hi);
     if (g.bar_own > 0) return l_pick_bar(g, m, lo, hi, k);
-    int acc = 0;
+    LaneCum c;
+    int j;
     if (lo == hi) {
         LaneDbl t;
         l_dbl(m, lo, isplus, t);
-        uint32_t r = t.R;
-        while (r) {
-            const int x = l_take(r, isplus);
-            r &= ~(1u << x);
-            const uint32_t nm = l_dbl_newmask(m, t, lo, isplus, x);
-            const int c = l_popc(nm);
-            if (k < acc + c) return l_play_from(x, lo, lo, nm, k - acc, isplus);
-            acc += c;
-        }
-    } else {
-        LaneTwo t;
-        l_two(m, lo, hi, isplus, t);
-        if (k < gen.N0) {
-            uint32_t r = t.R0;
-            while (r) {
-                const int x = l_take(r, isplus);
-                r &= ~(1u << x);
-                const uint32_t nm = l_two_newmask0(m, t, lo, hi, isplus, x);
-                const int c = l_popc(nm);
-                if (k < acc + c) return l_play_from(x, lo, hi, nm, k - acc, isplus);
-                acc += c;
-            }
-        } else {
-            acc = gen.N0;
-            uint32_t r = t.R1;
-            while (r) {
-                const int y = l_take(r, isplus);
-                r &= ~(1u << y);
-                const uint32_t nm = l_two_newmask1(t, lo, hi, y);
-                const int c = l_popc(nm);
-                if (k < acc + c) return l_play_from(y, hi, lo, nm, k - acc, isplus);
-                acc += c;
-            }
-        }
+        c.R = t.R; c.base = t.nR; c.tri = true;
+        c.plus0 = t.HIT | t.NEWRUN | t.Z;                       // disjoint: a root without children neither runs on nor hits
+        c.plus1 = (t.NEWLEAPF >> lo) & t.R;                     // the root whose refill child is new
+        c.minus0 = t.Lx;                                        // a lone checker cannot be moved twice
+        c.minus1 = t.R & (isplus ? (t.R << lo) : (t.R >> lo));  // the run-on / refill partner is judged on its own
+        const int x = l_low(l_find_root(c, k, isplus, j));
+        return l_play_from(x, lo, lo, l_dbl_newmask(m, t, lo, isplus, x), j, isplus);
     }
-    LanePlay none;
-    none.n = 0; none.x1 = none.t1 = none.x2 = none.t2 = 0;
-    return none;
+    LaneTwo t;
+    l_two(m, lo, hi, isplus, t);
+    c.tri = false;
+    if (k < gen.N0) {
+        c.R = t.R0; c.base = t.nR1;
+        c.plus0 = t.G0 | t.Z0;                                  // disjoint
+        c.plus1 = 0;
+        c.minus0 = t.L;
+        c.minus1 = isplus ? ((t.D0 >> hi) & t.R0) : t.D0;       // the root holding the later copy of a repeated net move
+        const int x = l_low(l_find_root(c, k, isplus, j));
+        return l_play_from(x, lo, hi, l_two_newmask0(m, t, lo, hi, isplus, x), j, isplus);
+    }
+    c.R = t.R1; c.base = 0;
+    c.plus0 = t.NR1 | t.Z1;                                     // disjoint
+    c.plus1 = t.NL1;
+    c.minus0 = c.minus1 = 0;
+    const int y = l_low(l_find_root(c, k - gen.N0, isplus, j));
+    return l_play_from(y, hi, lo, l_two_newmask1(t, lo, hi, y), j, isplus);
 }
 
 }  // namespace lane

@@ -52,7 +52,8 @@ __device__ __forceinline__ void bg_to_planes(const BgWarp &g, lane::LaneBoard &b
 // the list cooperatively.  One out-of-line copy (the tree kernel calls it three times per iteration and is
 // instruction-fetch bound); everything travels BY VALUE in registers: a reference to the caller's board
 // would force it into local memory and every call would start with a round trip through it.
-__device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal, WarpSlab *slab, int lane, int k) {
+// k >= 0: the k-th play; k == -1: count only; k == -2: the play at index_of(w, U) (a rollout's uniform choice).
+__device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal, WarpSlab *slab, int lane, int k, uint32_t w) {
     BgWarp g;
     g.v = v;
     g.bar0 = (int)(scal & 15u); g.bar1 = (int)((scal >> 4) & 15u); g.off0 = (int)((scal >> 8) & 15u); g.off1 = (int)((scal >> 12) & 15u);
@@ -70,6 +71,7 @@ __device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal
         gen.U = 0;
         if (b.bar_own > 0) lane::l_movegen_bar(b, m, lo, hi, gen);
         else if (m.own1 != 0) lane::l_movegen_closed(b, m, lo, hi, gen);
+        if (k == -2 && gen.U > 0) k = (int)index_of(w, (uint32_t)gen.U);
         if (k >= 0 && k < gen.U) seq = lane::l_play_to_seq(lane::l_pick(b, gen, nullptr, 0, k), g.player);
         return ((unsigned long long)(uint32_t)gen.U << 32) | seq;
     }
@@ -77,12 +79,14 @@ __device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal
         lane::LaneGen gen;
         lane::l_movegen_pb(b, gen, slab->raw, 1);
         __syncwarp();
+        if (k == -2 && gen.U > 0) k = (int)index_of(w, (uint32_t)gen.U);
         if (k >= 0 && k < gen.U) seq = lane::l_play_to_seq(lane::l_pick_walk(gen, slab->raw, 1, k), g.player);
         __syncwarp();
         return ((unsigned long long)(uint32_t)gen.U << 32) | seq;
     }
     bool ovf = false;
     const int U = bg_movegen(g, *slab, lane, ovf);
+    if (k == -2 && U > 0) k = (int)index_of(w, (uint32_t)U);
     if (k >= 0 && k < U) seq = slab->raw[k];
     __syncwarp();
     return ((unsigned long long)ovf << 63) | ((unsigned long long)(uint32_t)U << 32) | seq;
@@ -95,10 +99,19 @@ struct BgGame {
         const uint32_t scal = (uint32_t)g.bar0 | ((uint32_t)g.bar1 << 4) | ((uint32_t)g.off0 << 8) | ((uint32_t)g.off1 << 12) |
                               ((uint32_t)g.roll0 << 16) | ((uint32_t)g.roll1 << 20) | ((g.player > 0 ? 1u : 0u) << 24) |
                               ((uint32_t)(g.second ? 1 : 0) << 25);
-        const unsigned long long r = bg_count_and_kth(g.v, scal, &slab, lane, k);
+        const unsigned long long r = bg_count_and_kth(g.v, scal, &slab, lane, k, 0u);
         if (r >> 63) ovf = true;
         if (k >= 0) seq = (uint32_t)r;
         return (int)((r >> 32) & 0x7FFFFFFFu);
+    }
+    // the play a rollout makes: uniform over the legal plays with the word w (SEQ_EMPTY when there is none)
+    __device__ __forceinline__ uint32_t random_play(WarpSlab &slab, int lane, bool &ovf, uint32_t w) const {
+        const uint32_t scal = (uint32_t)g.bar0 | ((uint32_t)g.bar1 << 4) | ((uint32_t)g.off0 << 8) | ((uint32_t)g.off1 << 12) |
+                              ((uint32_t)g.roll0 << 16) | ((uint32_t)g.roll1 << 20) | ((g.player > 0 ? 1u : 0u) << 24) |
+                              ((uint32_t)(g.second ? 1 : 0) << 25);
+        const unsigned long long r = bg_count_and_kth(g.v, scal, &slab, lane, -2, w);
+        if (r >> 63) ovf = true;
+        return (uint32_t)r;
     }
     __device__ __forceinline__ void load(const State *s, int lane) { bg_load(g, s, lane); }
     __device__ __forceinline__ void store(State *s, int lane) const { bg_store(g, s, lane); }
@@ -139,6 +152,10 @@ struct TttGame {  // tictactoe/mod.rs; the whole state is warp-uniform
         const int U = __popc(~(xm | om) & 0x1FFu);
         if (k >= 0 && k < U) seq = move_at(slab, k);
         return U;
+    }
+    __device__ __forceinline__ uint32_t random_play(WarpSlab &slab, int, bool &, uint32_t w) const {
+        const int U = __popc(~(xm | om) & 0x1FFu);
+        return U > 0 ? move_at(slab, (int)index_of(w, (uint32_t)U)) : SEQ_EMPTY;
     }
     __device__ __forceinline__ uint32_t move_at(const WarpSlab &, int k) const {  // k-th empty cell ascending :36-44
         uint32_t e = ~(xm | om) & 0x1FFu;
@@ -186,9 +203,7 @@ __device__ __forceinline__ float rollout_plies(G &game, WarpSlab &slab, int lane
         const int d0 = die_of(__shfl_sync(FULL, rng.w0, src));
         const int d1 = die_of(__shfl_sync(FULL, rng.w1, src));
         const uint32_t w2 = __shfl_sync(FULL, rng.w2, src);
-        const int Ur = game.movegen(slab, lane, ovf);
-        const uint32_t sq = Ur > 0 ? game.move_at(slab, (int)index_of(w2, (uint32_t)Ur)) : SEQ_EMPTY;
-        __syncwarp();
+        const uint32_t sq = game.random_play(slab, lane, ovf, w2);
         game.step(sq, d0, d1, lane);
         ++plies;
     }

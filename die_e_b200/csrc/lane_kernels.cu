@@ -20,7 +20,7 @@ namespace diee {
 
 using namespace lane;
 
-constexpr int LANE_CTA = 128;
+constexpr int LANE_CTA = 64;
 
 __device__ __forceinline__ void lane_load_state(LaneBoard &g, const diee_bg_state *s) {
     const uint4 a = __ldg(reinterpret_cast<const uint4 *>(s));
@@ -216,15 +216,15 @@ __global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32
 template <bool ROLLOUT>
 static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) {
     // tuning knobs, read once: waiting-time weight of the vote and resident CTAs (x 4 warps) per SM.  Measured on
-    // B200 with 102,400 rollouts: 6 CTAs/SM and weight 0 are best (profiles/r01_lane_sweep.txt).
-    static int sms = 0, lag_weight = 0, blocks_per_sm = 6;
+    // B200 with 102,400 rollouts: 10 CTAs of 64 lanes per SM and weight 0 are best.
+    static int sms = 0, lag_weight = 0, blocks_per_sm = 10;
     if (sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
         if (const char *e = getenv("DIEE_LANE_LAG")) lag_weight = atoi(e);
-        if (const char *e = getenv("DIEE_LANE_BLOCKS_PER_SM")) blocks_per_sm = atoi(e) > 0 ? atoi(e) : 6;
+        if (const char *e = getenv("DIEE_LANE_BLOCKS_PER_SM")) blocks_per_sm = atoi(e) > 0 ? atoi(e) : 10;
     }
     job.lag_weight = lag_weight;
     long long blocks = (job.n_items + LANE_CTA - 1) / LANE_CTA;

@@ -332,10 +332,11 @@ static int32_t check_mcts_args(diee_ctx *ctx, int32_t game_kind, const void *sta
     return DIEE_OK;
 }
 
-int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
-                             const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
-                             uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
-                             int32_t *status_out, diee_search_stats *stats_dev) {
+// dump: the caller will read the node pool back, so every node's legal-move count must be materialised
+static int32_t mcts_search_dev_impl(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
+                                    const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
+                                    uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
+                                    int32_t *status_out, diee_search_stats *stats_dev, bool dump) {
     int32_t rc = check_mcts_args(ctx, game_kind, states, n, players, cfg, best_moves_out, status_out, epoch);
     if (rc != DIEE_OK) return rc;
     if (n == 0) return DIEE_OK;
@@ -361,7 +362,7 @@ int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *state
         best32 = (uint32_t *)ctx->s_best.p;
     }
     CU(launch_mcts_search(ctx->stream, game_kind, states, n, players, *cfg, seed, first_game_id, epoch, pp, pipe,
-                          (const float *)ctx->ln_table.p, best32, status_out, stats_dev, &nl));
+                          (const float *)ctx->ln_table.p, best32, status_out, stats_dev, dump, &nl));
     ctx->launches += nl;
     if (game_kind == DIEE_GAME_TICTACTOE) {
         // EMPTY_MOVE = 10 (tictactoe/mod.rs:18); done on the host side of the stream for this tiny case
@@ -374,6 +375,14 @@ int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *state
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return DIEE_OK;
+}
+
+int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
+                             const int8_t *players, const diee_mcts_cfg *cfg, uint64_t seed,
+                             uint32_t first_game_id, uint32_t epoch, void *best_moves_out,
+                             int32_t *status_out, diee_search_stats *stats_dev) {
+    return mcts_search_dev_impl(ctx, game_kind, states, n, players, cfg, seed, first_game_id, epoch, best_moves_out, status_out,
+                                stats_dev, false);
 }
 
 int32_t diee_mcts_search(diee_ctx *ctx, int32_t game_kind, const void *states, int32_t n,
@@ -399,8 +408,9 @@ int32_t diee_mcts_search(diee_ctx *ctx, int32_t game_kind, const void *states, i
     RESERVE(ctx->s_plies, sizeof(diee_search_stats) * (size_t)n);
     CU(cudaMemcpyAsync(ctx->s_states.p, states, ss * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->s_players.p, players, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    rc = diee_mcts_search_dev(ctx, game_kind, ctx->s_states.p, n, (const int8_t *)ctx->s_players.p, cfg, seed, first_game_id,
-                              epoch, ctx->s_moves.p, (int32_t *)ctx->s_status.p, (diee_search_stats *)ctx->s_plies.p);
+    rc = mcts_search_dev_impl(ctx, game_kind, ctx->s_states.p, n, (const int8_t *)ctx->s_players.p, cfg, seed, first_game_id,
+                              epoch, ctx->s_moves.p, (int32_t *)ctx->s_status.p, (diee_search_stats *)ctx->s_plies.p,
+                              nodes_out != nullptr);
     if (rc != DIEE_OK) return rc;
     CU(cudaMemcpyAsync(best_moves_out, ctx->s_moves.p, best_sz * n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(status_out, ctx->s_status.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));

@@ -46,6 +46,6 @@ cudaError_t launch_bg_encode_states(cudaStream_t st, const diee_bg_state *states
 cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots, int n, const int8_t *players,
                                const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
                                const PoolPtrs &pp, const SearchPipe &pipe, const float *ln_table, uint32_t *best_out,
-                               int32_t *status_out, diee_search_stats *stats_out, int *launches);
+                               int32_t *status_out, diee_search_stats *stats_out, bool dump, int *launches);
 
 }  // namespace diee

@@ -23,6 +23,7 @@ namespace diee {
 
 constexpr int MCTS_WARPS_PER_CTA = 4;
 constexpr int NO_WINNER = 2;
+constexpr uint32_t NM_UNKNOWN = 0xFFFFFFFFu;  // a node whose legal moves have not been counted yet
 
 // ---------------- game policies ----------------
 // The warp's board as the lane engine's bit planes (warp-uniform: every lane holds the whole board).
@@ -220,7 +221,8 @@ __global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32)
 mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int8_t *__restrict__ players,
                    diee_mcts_cfg cfg, uint32_t it_begin, uint32_t it_end, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
                    Pool pool, const float *__restrict__ ln_table, uint32_t *__restrict__ best_out,
-                   int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out, bool slab_in_smem) {
+                   int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out, bool slab_in_smem,
+                   bool fill_counts) {
     __shared__ WarpSlab slabs[MCTS_WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gidx = blockIdx.x * MCTS_WARPS_PER_CTA + wib;
@@ -304,6 +306,18 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
             uint32_t nmv;
             for (;;) {
                 nmv = nm[cur];
+                if (nmv == NM_UNKNOWN) {
+                    // Node::new counts a node's legal moves eagerly (node.rs:50); nothing reads the count before
+                    // the search comes back to the node, so it is taken here, on first arrival -- most nodes of a
+                    // 100-iteration search are never reached again and never need it (a pool dump fills them in).
+                    game.load(st + cur, lane);
+                    uint32_t unused = SEQ_EMPTY;
+                    int Uc = game.count_and_kth(slab, lane, ovf, -1, unused);
+                    if (Uc == 0 && pass_child) Uc = 1;
+                    nmv = ((uint32_t)Uc << 16) | (uint32_t)Uc;
+                    if (lane == 0) nm[cur] = nmv;
+                    __syncwarp();
+                }
                 const int nmoves = (int)(nmv >> 16), nunt = (int)(nmv & 0xFFFFu);
                 if (nunt != 0 || nmoves == 0) break;  // has untried moves, or no children at all
                 ++sel_levels;
@@ -354,13 +368,10 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                 philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)child, gid, DIEE_STREAM_EXPAND, epoch, blk);
                 game.step(seq, die_of(blk[0]), die_of(blk[1]), lane);
                 game.store(st + child, lane);
-                uint32_t unused = SEQ_EMPTY;
-                int Uc = game.count_and_kth(slab, lane, ovf, -1, unused);  // Node::new for the child
-                if (Uc == 0 && pass_child) Uc = 1;
                 if (lane == 0) {
                     nm[cur] = ((uint32_t)nmoves << 16) | (uint32_t)(nunt - 1);
                     parent[child] = cur; visits[child] = 0.f; value[child] = 0.f; action[child] = seq;
-                    nm[child] = ((uint32_t)Uc << 16) | (uint32_t)Uc;
+                    nm[child] = NM_UNKNOWN;  // counted on first arrival (see select)
                 }
                 n_nodes = child + 1;
                 leaf = child;
@@ -407,6 +418,18 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                 if (take) { bv = os; bi = oi; }
             }
             if (bi >= 0) best = action[bi];
+        }
+    }
+    if (fill_counts && last_slice) {  // a pool dump shows every node as Node::new leaves it
+        __syncwarp();
+        for (int i = 1; i < n_nodes; ++i) {
+            if (nm[i] != NM_UNKNOWN) continue;
+            game.load(st + i, lane);
+            uint32_t unused = SEQ_EMPTY;
+            int Uc = game.count_and_kth(slab, lane, ovf, -1, unused);
+            if (Uc == 0 && pass_child) Uc = 1;
+            if (lane == 0) nm[i] = ((uint32_t)Uc << 16) | (uint32_t)Uc;
+            __syncwarp();
         }
     }
     if (slab_in_smem) {
@@ -462,7 +485,7 @@ template <class G>
 static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const int8_t *players, const diee_mcts_cfg &cfg,
                                 uint64_t seed, uint32_t first_game_id, uint32_t epoch, const Pool &pool, const PoolPtrs &pp,
                                 const SearchPipe &pipe, const float *ln_table, uint32_t *best_out, int32_t *status_out,
-                                diee_search_stats *stats_out, int *launches) {
+                                diee_search_stats *stats_out, bool dump, int *launches) {
     const bool split = !(cfg.mode_flags & DIEE_MODE_ROLLOUT_CHECK_CURRENT);
     const typename G::State *r = static_cast<const typename G::State *>(roots);
     cudaError_t e;
@@ -476,7 +499,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
     }
     if (!split) {
         mcts_search_kernel<G, false><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
-            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem);
+            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
         *launches = 1;
         return cudaGetLastError();
     }
@@ -496,7 +519,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         if (slices == 1) {  // everything on the caller's stream, with timing marks around the two kernels
             if ((e = cudaEventRecord(pipe.t_begin, st)) != cudaSuccess) return e;
             mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
-                r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem);
+                r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
             *launches += 1;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if ((e = cudaEventRecord(pipe.t_tree, st)) != cudaSuccess) return e;
@@ -508,7 +531,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         for (uint32_t s = 0; s < slices; ++s) {
             const uint32_t a = (uint32_t)((uint64_t)cfg.iterations * s / slices), b = (uint32_t)((uint64_t)cfg.iterations * (s + 1) / slices);
             mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
-                r, n, players, cfg, a, b, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem);
+                r, n, players, cfg, a, b, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
             *launches += 1;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if ((e = cudaEventRecord(pipe.tree_done[s], st)) != cudaSuccess) return e;
@@ -521,7 +544,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         return launch_bg_rollout_count(st, n, cfg, pp, stats_out, launches);
     } else {
         mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
-            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem);
+            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
         const long long pairs = (long long)n * cfg.iterations;
         const long long blocks = (pairs + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA;
         rollout_kernel<G><<<(unsigned)blocks, MCTS_WARPS_PER_CTA * 32, 0, st>>>(n, cfg, seed, first_game_id, epoch, pool, players,
@@ -534,15 +557,15 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
 cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots, int n, const int8_t *players,
                                const diee_mcts_cfg &cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
                                const PoolPtrs &pp, const SearchPipe &pipe, const float *ln_table, uint32_t *best_out,
-                               int32_t *status_out, diee_search_stats *stats_out, int *launches) {
+                               int32_t *status_out, diee_search_stats *stats_out, bool dump, int *launches) {
     *launches = 0;
     if (n <= 0) return cudaSuccess;
     Pool pool{pp.states, pp.parent, pp.visits, pp.value, pp.action, pp.nmoves, pp.n_nodes, pp.sim_node, pp.finals};
     if (game_kind == DIEE_GAME_BACKGAMMON)
         return launch_typed<BgGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, pp, pipe, ln_table, best_out,
-                                    status_out, stats_out, launches);
+                                    status_out, stats_out, dump, launches);
     return launch_typed<TttGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, pp, pipe, ln_table, best_out,
-                                 status_out, stats_out, launches);
+                                 status_out, stats_out, dump, launches);
 }
 
 }  // namespace diee

@@ -376,7 +376,7 @@ def run_ours(args, rank, world):
             extra = {}
         traffic = None
         if args.workload == "mcts" and dominant and G == 1024 and args.iterations == 100 and args.round_limit == 400:
-            traffic = ncu_traffic("r01_lane_run_rollouts_v4_ncu_full_summary.txt")
+            traffic = ncu_traffic("r01_lane_run_rollouts_v5_ncu_full_summary.txt")
         avg_launch_ms = float(np.mean(kern_ms))
         achieved = alg_bytes / ((dominant[1] if dominant else avg_launch_ms) / 1e3) / 1e9
         roof = None

@@ -60,7 +60,8 @@ struct LaneJob {
 // wait for that path (see lane_run_kernel).
 // PATH_CLOSED: the distinct plays are counted in closed form (contact play, entering from the bar, or
 // nothing to move); PATH_WALK: the side can bear off within the play, counted root by root.
-enum { PATH_DONE = 0, PATH_CLOSED, PATH_WALK, PATH_COUNT };
+// PATH_STORE: the game is over (or the rollout has nothing left to play): write its result, once, in one place.
+enum { PATH_DONE = 0, PATH_CLOSED, PATH_WALK, PATH_STORE, PATH_COUNT };
 
 __device__ __forceinline__ int lane_path(const LaneBoard &g) {
     const uint32_t o123 = g.own[1] | g.own[2] | g.own[3];
@@ -69,17 +70,6 @@ __device__ __forceinline__ int lane_path(const LaneBoard &g) {
     const uint32_t outside = own1 & ~0x3Fu;
     if ((outside & (outside - 1u)) == 0 && (outside & ~(g.own[0] & ~o123)) == 0) return PATH_WALK;
     return PATH_CLOSED;
-}
-
-// a rollout whose two sides have collected everything: the remaining plies are skip_turns, i.e. the side
-// to move alternates and the dice shown at the end are those of the last ply
-template <bool ROLLOUT>
-__device__ __forceinline__ void rollout_finish_dead(const LaneJob &job, long long item, LaneBoard &g, uint32_t k_now, uint32_t gid, uint32_t c3) {
-    uint32_t o[4];
-    l_philox((uint32_t)job.seed, (uint32_t)(job.seed >> 32), job.limit - 1u, gid, DIEE_STREAM_ROLLOUT, c3, o);
-    if ((job.limit - k_now) & 1u) l_pass_turn(g, 0, 0);
-    g.second = 0; g.roll0 = l_die(o[0]); g.roll1 = l_die(o[1]);
-    lane_store_state(g, job.finals + item);
 }
 
 // One lane per item (a game, or one rollout of a search), whole job in one launch.
@@ -108,8 +98,9 @@ lane_run_kernel(LaneJob job) {
 
     for (;;) {
         // ---- idle lanes take the next items of the job (one atomic per warp) ----
+        // (in batches, like the stores: a quarter of the warp, or everybody)
         const uint32_t idle = __ballot_sync(0xFFFFFFFFu, need == PATH_DONE);
-        if (idle && queue_open) {
+        if (queue_open && (__popc(idle) >= 8 || idle == 0xFFFFFFFFu)) {
             long long first = 0;
             if (lane == 0) first = (long long)atomicAdd(job.next_item, (unsigned long long)__popc(idle));
             first = __shfl_sync(0xFFFFFFFFu, first, 0);
@@ -127,19 +118,12 @@ lane_run_kernel(LaneJob job) {
                         if (node >= 0 && job.limit > 0) {  // node < 0: the iteration ended on a terminal leaf, no rollout
                             lane_load_state(g, job.states + (size_t)gm * (job.iterations + 1) + node);
                             gid = job.first_game_id + gm; c3 = (job.epoch << 16) | (it & 0xFFFFu);
-                            if (g.off_own == 15 && g.off_opp == 15) rollout_finish_dead<ROLLOUT>(job, item, g, 0u, gid, c3);
-                            else need = lane_path(g);
+                            need = (g.off_own == 15 && g.off_opp == 15) ? PATH_STORE : lane_path(g);
                         }
                     } else {
                         lane_load_state(g, job.states + item);
                         gid = job.first_game_id + (uint32_t)item;
-                        const int w = l_winner(g);
-                        if (w != 0 || job.limit == 0) {
-                            job.winners[item] = (int8_t)w; job.plies[item] = 0;
-                            if (job.finals) lane_store_state(g, job.finals + item);
-                        } else {
-                            need = lane_path(g);
-                        }
+                        need = (l_winner(g) != 0 || job.limit == 0) ? PATH_STORE : lane_path(g);
                     }
                 }
             }
@@ -149,12 +133,16 @@ lane_run_kernel(LaneJob job) {
         // ---- vote ----
         int best = PATH_DONE, best_score = INT_MIN;
 #pragma unroll
-        for (int p = 1; p < PATH_COUNT; ++p) {
+        for (int p = PATH_CLOSED; p <= PATH_WALK; ++p) {
             const uint32_t waiting = __ballot_sync(0xFFFFFFFFu, need == p);
             if (waiting) {
                 const int score = __popc(waiting) + job.lag_weight * (int)__reduce_max_sync(0xFFFFFFFFu, need == p ? age : 0u);
                 if (score > best_score) { best_score = score; best = p; }
             }
+        }
+        {   // results are written in batches: when a quarter of the warp waits to, or nothing else is left to do
+            const uint32_t storing = __ballot_sync(0xFFFFFFFFu, need == PATH_STORE);
+            if (storing && (best == PATH_DONE || __popc(storing) >= 8)) best = PATH_STORE;
         }
         if (best == PATH_DONE) break;
 #ifdef DIEE_LANE_STATS
@@ -162,6 +150,25 @@ lane_run_kernel(LaneJob job) {
 #endif
         if (need != best) { ++age; continue; }
         age = 0;
+        if (best == PATH_STORE) {
+            if (ROLLOUT) {
+                if (k < job.limit) {
+                    // both sides have collected everything: the remaining plies are skip_turns, i.e. the side to
+                    // move alternates and the dice shown at the end are those of the last ply
+                    uint32_t o[4];
+                    l_philox((uint32_t)job.seed, (uint32_t)(job.seed >> 32), job.limit - 1u, gid, stream, c3, o);
+                    if ((job.limit - k) & 1u) l_pass_turn(g, 0, 0);
+                    g.second = 0; g.roll0 = l_die(o[0]); g.roll1 = l_die(o[1]);
+                }
+                lane_store_state(g, job.finals + item);
+            } else {
+                job.winners[item] = (int8_t)l_winner(g);  // versus.rs:231-235: the game stopped at its winner, or at the cap
+                job.plies[item] = (int32_t)k;
+                if (job.finals) lane_store_state(g, job.finals + item);
+            }
+            need = PATH_DONE;
+            continue;
+        }
 
         // ---- one ply on path `best` (warp-uniform) for the lanes that wait for it ----
         uint32_t o[4];
@@ -186,20 +193,8 @@ lane_run_kernel(LaneJob job) {
         ++k;
 
         // ---- what next ----
-        if (ROLLOUT) {
-            if (k == job.limit) { lane_store_state(g, job.finals + item); need = PATH_DONE; }
-            else if (g.off_own == 15 && g.off_opp == 15) { rollout_finish_dead<ROLLOUT>(job, item, g, k, gid, c3); need = PATH_DONE; }
-            else need = lane_path(g);
-        } else {
-            const int w = l_winner(g);
-            if (w != 0 || k == job.limit) {  // versus.rs:231-235: the game stops at its winner, or at the cap
-                job.winners[item] = (int8_t)w; job.plies[item] = (int32_t)k;
-                if (job.finals) lane_store_state(g, job.finals + item);
-                need = PATH_DONE;
-            } else {
-                need = lane_path(g);
-            }
-        }
+        if (ROLLOUT) need = (k == job.limit || (g.off_own == 15 && g.off_opp == 15)) ? PATH_STORE : lane_path(g);
+        else need = (k == job.limit || l_winner(g) != 0) ? PATH_STORE : lane_path(g);
     }
 }
 

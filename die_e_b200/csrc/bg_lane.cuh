@@ -61,7 +61,7 @@ LANE_HD int l_popc(uint32_t x) {
 }
 LANE_HD int l_low(uint32_t x) {  // index of the lowest set bit, x != 0
 #if defined(__CUDA_ARCH__)
-    return __ffs((int)x) - 1;
+    return 31 - __clz((int)(x & (0u - x)));  // one find-leading-one on the isolated bit (ffs would be brev + flo)
 #else
     return __builtin_ctz(x);
 #endif
@@ -79,6 +79,16 @@ LANE_HD uint32_t l_rev24(uint32_t x) {  // mirror the 24 points
 #else
     uint32_t r = 0;
     for (int i = 0; i < 24; ++i) r |= ((x >> i) & 1u) << (23 - i);
+    return r;
+#endif
+}
+
+LANE_HD uint32_t l_rev32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __brev(x);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) r |= ((x >> i) & 1u) << (31 - i);
     return r;
 #endif
 }
@@ -457,10 +467,11 @@ LANE_HD LanePlay l_pick_walk(const LaneGen &gen, const uint32_t *scr, int stride
                 pl.x1 = x;
                 pl.t1 = l_to(x, m1);
                 if (newm & L_SINGLE) { pl.n = 1; return pl; }
-                uint32_t mm = newm;
-                for (int j = k - acc; j > 0; --j) mm &= ~(1u << l_take(mm, gen.isplus));
+                uint32_t w = gen.isplus ? l_rev32(newm) : newm;
+                for (int j = k - acc; j > 0; --j) w &= w - 1u;
+                const int pos = l_low(w);
                 pl.n = 2;
-                pl.x2 = l_take(mm, gen.isplus);
+                pl.x2 = gen.isplus ? 31 - pos : pos;
                 pl.t2 = l_to(pl.x2, m2);
                 return pl;
             }
@@ -613,9 +624,12 @@ LANE_HD LanePlay l_play_from(int x, int m1, int m2, uint32_t nm, int j, bool isp
     pl.t1 = l_to(x, m1);
     pl.x2 = pl.t2 = 0;
     if (nm & L_SINGLE) { pl.n = 1; return pl; }
-    for (; j > 0; --j) nm &= ~(1u << l_take(nm, isplus));
+    // the j-th child in `from` order: player +1 counts from the top, so count from the bottom of the mirror image
+    uint32_t w = isplus ? l_rev32(nm) : nm;
+    for (; j > 0; --j) w &= w - 1u;
+    const int pos = l_low(w);
     pl.n = 2;
-    pl.x2 = l_take(nm, isplus);
+    pl.x2 = isplus ? 31 - pos : pos;
     pl.t2 = l_to(pl.x2, m2);
     return pl;
 }
@@ -808,8 +822,8 @@ struct LaneCum {
     int base;
     bool tri;
 };
-// -> one-hot bit of the root holding play k; j = the play's index within that root
-LANE_HD uint32_t l_find_root(const LaneCum &c, int k, bool isplus, int &j) {
+// -> point of the root holding play k; j = the play's index within that root
+LANE_HD int l_find_root(const LaneCum &c, int k, bool isplus, int &j) {
     uint32_t r = c.R, xb = 0;
     int acc = 0, rank = 0;
     while (r) {
@@ -822,7 +836,7 @@ LANE_HD uint32_t l_find_root(const LaneCum &c, int k, bool isplus, int &j) {
         ++rank;
     }
     j = k - acc;
-    return xb;
+    return l_high(xb);
 }
 
 // the k-th distinct play (0 <= k < gen.U) in reference order
@@ -843,7 +857,7 @@ LANE_HD LanePlay l_pick(const LaneBoard &g, const LaneGen &gen, const uint32_t *
         c.plus1 = (t.NEWLEAPF >> lo) & t.R;                     // the root whose refill child is new
         c.minus0 = t.Lx;                                        // a lone checker cannot be moved twice
         c.minus1 = t.R & (isplus ? (t.R << lo) : (t.R >> lo));  // the run-on / refill partner is judged on its own
-        const int x = l_low(l_find_root(c, k, isplus, j));
+        const int x = l_find_root(c, k, isplus, j);
         return l_play_from(x, lo, lo, l_dbl_newmask(m, t, lo, isplus, x), j, isplus);
     }
     LaneTwo t;
@@ -855,14 +869,14 @@ LANE_HD LanePlay l_pick(const LaneBoard &g, const LaneGen &gen, const uint32_t *
         c.plus1 = 0;
         c.minus0 = t.L;
         c.minus1 = isplus ? ((t.D0 >> hi) & t.R0) : t.D0;       // the root holding the later copy of a repeated net move
-        const int x = l_low(l_find_root(c, k, isplus, j));
+        const int x = l_find_root(c, k, isplus, j);
         return l_play_from(x, lo, hi, l_two_newmask0(m, t, lo, hi, isplus, x), j, isplus);
     }
     c.R = t.R1; c.base = 0;
     c.plus0 = t.NR1 | t.Z1;                                     // disjoint
     c.plus1 = t.NL1;
     c.minus0 = c.minus1 = 0;
-    const int y = l_low(l_find_root(c, k - gen.N0, isplus, j));
+    const int y = l_find_root(c, k - gen.N0, isplus, j);
     return l_play_from(y, hi, lo, l_two_newmask1(t, lo, hi, y), j, isplus);
 }
 

@@ -120,3 +120,19 @@ def test_mct_search_host_api(ctx, oracle):
     cfg = MctsConfig(iterations=30, simulate_round_limit=10, mode_flags=ffi.MODE_PASS_CHILD)
     mv = mct_search(bg, bg.get_player(), cfg, seed=3, game_id=1, ctx=ctx)
     assert mv in bg.get_valid_moves()
+
+
+def test_sliced_search_is_the_same_search(ctx, oracle, monkeypatch):
+    """DIEE_SEARCH_SLICES: the search cut into slices of iterations (tree kernel of slice s+1 beside the rollouts of
+    slice s on a side stream) must give exactly the unsliced result -- nodes, best moves, rollout end states."""
+    from die_e_b200 import _ffi
+    states = positions.midgame_positions(seed=13, n=24, max_adv=90)
+    players = states["player"].copy()
+    cfg = oracle.mcts_cfg(iterations=30, c=2.0, limit=60, mode=_ffi.MODE_PASS_CHILD)
+    ref = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
+    for slices in ("2", "4"):
+        monkeypatch.setenv("DIEE_SEARCH_SLICES", slices)
+        got = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
+        for a, b in zip(ref, got):
+            assert np.asarray(a).tobytes() == np.asarray(b).tobytes()
+    monkeypatch.delenv("DIEE_SEARCH_SLICES")

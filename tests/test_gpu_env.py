@@ -219,6 +219,26 @@ def test_playout_full_size_properties(ctx):
     assert (w_b == winners[1000:3000]).all() and (p_b == plies[1000:3000]).all()
 
 
+def test_playout_batch_shapes_and_queue_refill(ctx, oracle):
+    """batch sizes around the warp / CTA boundaries of the lane kernel, and a batch larger than the number of
+    resident lanes (148 SMs x 10 CTAs x 64 lanes), where lanes take a second game from the job queue"""
+    base = np.concatenate([positions.start_state(33, g) for g in range(130)])
+    want = [oracle.bg_playout(base[g:g + 1], 33, g, 400) for g in range(130)]
+    for n in (1, 31, 33, 63, 65, 129, 130):
+        w, p, f = ctx.bg_playout(base[:n], seed=33, first_game_id=0, round_limit=400, want_finals=True)
+        for g in range(n):
+            assert (w[g], p[g]) == want[g][:2] and f[g:g + 1].tobytes() == want[g][2].tobytes(), (n, g)
+    n = 120000
+    starts = np.repeat(base[:1], n)
+    rng = np.random.default_rng(5)
+    starts["roll"][:, 0] = rng.integers(1, 7, n)
+    starts["roll"][:, 1] = rng.integers(1, 7, n)
+    w, p, f = ctx.bg_playout(starts, seed=77, first_game_id=0, round_limit=80, want_finals=True)
+    for g in list(range(0, n, 4001)) + [n - 1, 94719, 94720, 94721]:
+        ow, op, of = oracle.bg_playout(starts[g:g + 1], 77, g, 80)
+        assert (w[g], p[g]) == (ow, op) and f[g:g + 1].tobytes() == of.tobytes(), g
+
+
 def test_codec_round_trips(ctx, oracle):
     cases = json.load(open(os.path.join(GOLDEN, "ref_encoding_kats.json")))["cases"]
     states = np.concatenate([oracle.make_state([0] * 24, roll=c["roll"], player=c["player"]) for c in cases])

@@ -243,13 +243,17 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     int32_t *parent = gparent;
     float *visits = gvisits, *value = gvalue;
     uint32_t *nm = gnm;
+    // first | last << 16 child index of every node (shared-memory slabs only): select_ucb then scans just the
+    // 32-node chunks that can hold children of the node instead of the whole slab
+    uint32_t *crange = nullptr;
     if (slab_in_smem) {
-        unsigned char *mine = slab_mem + (size_t)wib * cap * (sizeof(typename G::State) + 16);
+        unsigned char *mine = slab_mem + (size_t)wib * cap * (sizeof(typename G::State) + 20);
         st = reinterpret_cast<typename G::State *>(mine);
         parent = reinterpret_cast<int32_t *>(mine + (size_t)cap * sizeof(typename G::State));
         visits = reinterpret_cast<float *>(parent + cap);
         value = visits + cap;
         nm = reinterpret_cast<uint32_t *>(value + cap);
+        crange = nm + cap;
     }
     uint32_t *action = pool.action + base;
     int32_t *sim_node = pool.sim_node + (size_t)gidx * cfg.iterations;
@@ -279,7 +283,10 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
             uint32_t unused = SEQ_EMPTY;
             int U = game.count_and_kth(slab, lane, ovf, -1, unused);
             if (U == 0 && pass_child) U = 1;
-            if (lane == 0) { parent[0] = -1; visits[0] = 0.f; value[0] = 0.f; action[0] = SEQ_EMPTY; nm[0] = ((uint32_t)U << 16) | (uint32_t)U; }
+            if (lane == 0) {
+                parent[0] = -1; visits[0] = 0.f; value[0] = 0.f; action[0] = SEQ_EMPTY; nm[0] = ((uint32_t)U << 16) | (uint32_t)U;
+                if (crange) crange[0] = 0xFFFFu;
+            }
             n_nodes = 1;
             __syncwarp();
         }
@@ -290,6 +297,15 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
             for (int i = lane; i < n_nodes; i += 32) { parent[i] = gparent[i]; visits[i] = gvisits[i]; value[i] = gvalue[i]; nm[i] = gnm[i]; }
             const int words = n_nodes * (int)(sizeof(typename G::State) / 4);
             for (int i = lane; i < words; i += 32) reinterpret_cast<uint32_t *>(st)[i] = reinterpret_cast<const uint32_t *>(gst)[i];
+            __syncwarp();
+            if (lane == 0) {  // rebuild the child ranges (children are created in index order)
+                for (int i = 0; i < n_nodes; ++i) crange[i] = 0xFFFFu;
+                for (int i = 1; i < n_nodes; ++i) {
+                    const int p = parent[i];
+                    const uint32_t r = crange[p];
+                    crange[p] = ((r & 0xFFFFu) == 0xFFFFu ? (uint32_t)i : (r & 0xFFFFu)) | ((uint32_t)i << 16);
+                }
+            }
             __syncwarp();
         }
         if (stats_out) {
@@ -328,23 +344,28 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                 const float cl = __fmul_rn(cfg.c, lnp);
                 float bs = -INFINITY;
                 int bi = -1;
-                for (int c0 = 0; c0 < n_nodes; c0 += 32) {
+                int scan0 = 0, scan1 = n_nodes;
+                if (crange) {
+                    const uint32_t r = crange[cur];
+                    scan0 = (int)(r & 0xFFFFu) & ~31;
+                    scan1 = (int)(r >> 16) + 1;
+                }
+                for (int c0 = scan0; c0 < scan1; c0 += 32) {
                     const int idx = c0 + lane;
-                    if (idx < n_nodes && parent[idx] == cur) {
+                    if (idx < scan1 && parent[idx] == cur) {
                         const float vi = visits[idx];
                         // Node::ucb node.rs:86-96: value/visits + sqrt(c*ln(parent.visits)/visits)
                         const float s = __fadd_rn(__fdiv_rn(value[idx], vi), __fsqrt_rn(__fdiv_rn(cl, vi)));
                         if (!(bs > s)) { bs = s; bi = idx; }  // within a lane idx only grows
                     }
                 }
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) {
-                    const float os = __shfl_xor_sync(FULL, bs, d);
-                    const int oi = __shfl_xor_sync(FULL, bi, d);
-                    // keep the later index unless the earlier is strictly greater (max_by)
-                    const bool take = oi >= 0 && (bi < 0 || (oi > bi ? !(bs > os) : (os > bs)));
-                    if (take) { bs = os; bi = oi; }
-                }
+                // arg-max over the lanes, the LATER index among equal scores (max_by keeps the last maximum): two warp
+                // reductions -- the best score as an order-preserving integer, then the largest index that has it
+                // (scores are never NaN here: every child has visits >= 1, and never -0: values are sums from +0)
+                const uint32_t sb = __float_as_uint(bs);
+                const uint32_t key = bi >= 0 ? ((sb & 0x80000000u) ? ~sb : (sb | 0x80000000u)) : 0u;
+                const uint32_t kmax = __reduce_max_sync(FULL, key);
+                bi = __reduce_max_sync(FULL, (bi >= 0 && key == kmax) ? bi : -1);
                 if (bi < 0) { status = DIEE_ERR_OVERFLOW; break; }  // cannot happen: a fully expanded node has children
                 cur = bi;
             }
@@ -372,6 +393,11 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                     nm[cur] = ((uint32_t)nmoves << 16) | (uint32_t)(nunt - 1);
                     parent[child] = cur; visits[child] = 0.f; value[child] = 0.f; action[child] = seq;
                     nm[child] = NM_UNKNOWN;  // counted on first arrival (see select)
+                    if (crange) {
+                        const uint32_t r = crange[cur];
+                        crange[cur] = ((r & 0xFFFFu) == 0xFFFFu ? (uint32_t)child : (r & 0xFFFFu)) | ((uint32_t)child << 16);
+                        crange[child] = 0xFFFFu;
+                    }
                 }
                 n_nodes = child + 1;
                 leaf = child;
@@ -490,7 +516,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
     const typename G::State *r = static_cast<const typename G::State *>(roots);
     cudaError_t e;
     // node slabs of the CTA's games in shared memory when they fit
-    size_t slab_bytes = (size_t)MCTS_WARPS_PER_CTA * (cfg.iterations + 1) * (sizeof(typename G::State) + 16);
+    size_t slab_bytes = (size_t)MCTS_WARPS_PER_CTA * (cfg.iterations + 1) * (sizeof(typename G::State) + 20);
     const bool in_smem = slab_bytes <= 160 * 1024;
     if (!in_smem) slab_bytes = 0;
     if (in_smem) {

@@ -246,14 +246,18 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     // first | last << 16 child index of every node (shared-memory slabs only): select_ucb then scans just the
     // 32-node chunks that can hold children of the node instead of the whole slab
     uint32_t *crange = nullptr;
+    // value / visits of every node, refreshed where the two change (back-propagation): select_ucb then needs one
+    // IEEE division per child instead of two (same operands, same rounding, so the same bits)
+    float *qv = nullptr;
     if (slab_in_smem) {
-        unsigned char *mine = slab_mem + (size_t)wib * cap * (sizeof(typename G::State) + 20);
+        unsigned char *mine = slab_mem + (size_t)wib * cap * (sizeof(typename G::State) + 24);
         st = reinterpret_cast<typename G::State *>(mine);
         parent = reinterpret_cast<int32_t *>(mine + (size_t)cap * sizeof(typename G::State));
         visits = reinterpret_cast<float *>(parent + cap);
         value = visits + cap;
         nm = reinterpret_cast<uint32_t *>(value + cap);
         crange = nm + cap;
+        qv = reinterpret_cast<float *>(crange + cap);
     }
     uint32_t *action = pool.action + base;
     int32_t *sim_node = pool.sim_node + (size_t)gidx * cfg.iterations;
@@ -298,6 +302,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
             const int words = n_nodes * (int)(sizeof(typename G::State) / 4);
             for (int i = lane; i < words; i += 32) reinterpret_cast<uint32_t *>(st)[i] = reinterpret_cast<const uint32_t *>(gst)[i];
             __syncwarp();
+            for (int i = lane; i < n_nodes; i += 32) qv[i] = __fdiv_rn(value[i], visits[i]);
             if (lane == 0) {  // rebuild the child ranges (children are created in index order)
                 for (int i = 0; i < n_nodes; ++i) crange[i] = 0xFFFFu;
                 for (int i = 1; i < n_nodes; ++i) {
@@ -320,7 +325,10 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
             // ---- select_leaf_node :88-94 ----
             int cur = 0;
             uint32_t nmv;
+            int my_path_node = -1, depth = 0;  // lane d remembers the node of level d: the path back-propagation walks
             for (;;) {
+                if (lane == depth) my_path_node = cur;
+                ++depth;
                 nmv = nm[cur];
                 if (nmv == NM_UNKNOWN) {
                     // Node::new counts a node's legal moves eagerly (node.rs:50); nothing reads the count before
@@ -355,7 +363,8 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                     if (idx < scan1 && parent[idx] == cur) {
                         const float vi = visits[idx];
                         // Node::ucb node.rs:86-96: value/visits + sqrt(c*ln(parent.visits)/visits)
-                        const float s = __fadd_rn(__fdiv_rn(value[idx], vi), __fsqrt_rn(__fdiv_rn(cl, vi)));
+                        const float q = qv ? qv[idx] : __fdiv_rn(value[idx], vi);
+                        const float s = __fadd_rn(q, __fsqrt_rn(__fdiv_rn(cl, vi)));
                         if (!(bs > s)) { bs = s; bi = idx; }  // within a lane idx only grows
                     }
                 }
@@ -417,10 +426,21 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                 if (!deferred) game.store(finals + it, lane);  // where the rollout ended
             }
             // ---- backpropagate :96-103 (no sign flip) ----
-            if (lane == 0) {
+            // the path root .. cur was recorded during select, one node per lane; the new child (if any) joins it
+            if (leaf != cur) { if (lane == depth) my_path_node = leaf; ++depth; }
+            if (depth <= 32) {
+                if (my_path_node >= 0) {
+                    const float nv = __fadd_rn(visits[my_path_node], 1.0f), nw = __fadd_rn(value[my_path_node], result);
+                    visits[my_path_node] = nv;
+                    value[my_path_node] = nw;
+                    if (qv) qv[my_path_node] = __fdiv_rn(nw, nv);
+                }
+            } else if (lane == 0) {  // a path longer than a warp: walk the parent links
                 for (int i = leaf; i >= 0; i = parent[i]) {
-                    visits[i] = __fadd_rn(visits[i], 1.0f);
-                    value[i] = __fadd_rn(value[i], result);
+                    const float nv = __fadd_rn(visits[i], 1.0f), nw = __fadd_rn(value[i], result);
+                    visits[i] = nv;
+                    value[i] = nw;
+                    if (qv) qv[i] = __fdiv_rn(nw, nv);
                 }
             }
             __syncwarp();
@@ -516,7 +536,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
     const typename G::State *r = static_cast<const typename G::State *>(roots);
     cudaError_t e;
     // node slabs of the CTA's games in shared memory when they fit
-    size_t slab_bytes = (size_t)MCTS_WARPS_PER_CTA * (cfg.iterations + 1) * (sizeof(typename G::State) + 20);
+    size_t slab_bytes = (size_t)MCTS_WARPS_PER_CTA * (cfg.iterations + 1) * (sizeof(typename G::State) + 24);
     const bool in_smem = slab_bytes <= 160 * 1024;
     if (!in_smem) slab_bytes = 0;
     if (in_smem) {

@@ -218,7 +218,7 @@ __global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32
 
 template <bool ROLLOUT>
 static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) {
-    // tuning knobs, read once: waiting-time weight of the vote and resident CTAs (x 4 warps) per SM.  Measured on
+    // tuning knobs, read once: waiting-time weight of the vote, resident CTAs (x 2 warps) per SM, walk threshold.  Measured on
     // B200 with 102,400 rollouts: 10 CTAs of 64 lanes per SM and weight 0 are best.
     static int sms = 0, lag_weight = 0, blocks_per_sm = 10, walk_min = 24;
     if (sms == 0) {
@@ -231,11 +231,16 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
         if (const char *e = getenv("DIEE_LANE_BLOCKS_PER_SM")) blocks_per_sm = atoi(e) > 0 ? atoi(e) : 10;
     }
     job.lag_weight = lag_weight;
+    // one item per lane as long as the job fits ~10 CTAs per SM (the C2 / C3 sizes: fewer, fuller warps); a bigger job
+    // runs at full occupancy and lanes are refilled from the queue (measured at 819,200 rollouts: 77.7 M simulations/s
+    // with 10 CTAs per SM, 82.6 M with 16)
+    const bool refilled = job.n_items > (long long)sms * blocks_per_sm * LANE_CTA * 5 / 4;
+    const int bps = refilled ? 16 : blocks_per_sm;
     // (only while every lane holds about one item: with a refilled queue the closed path never runs dry, and holding
     // the walk back would starve it -- measured 78 M -> 64 M simulations/s at 8,192 games)
-    job.walk_min = job.n_items <= (long long)sms * blocks_per_sm * LANE_CTA * 5 / 4 ? walk_min : 0;
+    job.walk_min = refilled ? 0 : walk_min;
     long long blocks = (job.n_items + LANE_CTA - 1) / LANE_CTA;
-    if (blocks > (long long)sms * blocks_per_sm) blocks = (long long)sms * blocks_per_sm;
+    if (blocks > (long long)sms * bps) blocks = (long long)sms * bps;
     cudaError_t e = cudaMemsetAsync(job.next_item, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     lane_run_kernel<ROLLOUT><<<(unsigned)blocks, LANE_CTA, 0, st>>>(job);

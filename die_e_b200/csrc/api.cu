@@ -15,6 +15,7 @@
 
 using namespace diee;
 
+#include "bg_pb_table.h"
 #include "ctx.h"
 
 extern "C" {
@@ -44,6 +45,19 @@ int32_t diee_ctx_create(int32_t device, diee_ctx **out) {
     }
     for (int i = 0; i < 3; ++i)
         if (cudaEventCreate(&ctx->ev_time[i]) != cudaSuccess) { delete ctx; return DIEE_ERR_CUDA; }
+    {   // the pure bear-off play table: filled on the host by the lane engine itself, 1 MB on the device
+        std::vector<uint32_t> index;
+        std::vector<uint16_t> plays;
+        pb_build_table(index, plays);
+        if (cudaMalloc(&ctx->pb_index.p, index.size() * 4) != cudaSuccess || cudaMalloc(&ctx->pb_plays.p, plays.size() * 2) != cudaSuccess ||
+            cudaMemcpy(ctx->pb_index.p, index.data(), index.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(ctx->pb_plays.p, plays.data(), plays.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete ctx;
+            return DIEE_ERR_CUDA;
+        }
+        ctx->pb_index.cap = index.size() * 4;
+        ctx->pb_plays.cap = plays.size() * 2;
+    }
     *out = ctx;
     return DIEE_OK;
 }
@@ -70,6 +84,8 @@ int32_t diee_ctx_destroy(diee_ctx *ctx) {
     for (int i = 0; i < 3; ++i)
         if (ctx->ev_time[i]) cudaEventDestroy(ctx->ev_time[i]);
     if (ctx->q_head.p) cudaFree(ctx->q_head.p);
+    if (ctx->pb_index.p) cudaFree(ctx->pb_index.p);
+    if (ctx->pb_plays.p) cudaFree(ctx->pb_plays.p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return DIEE_OK;
@@ -203,7 +219,7 @@ int32_t diee_bg_playout_dev(diee_ctx *ctx, const diee_bg_state *starts, int32_t 
     int nl = 0;
     RESERVE(ctx->q_head, sizeof(unsigned long long) * 8);
     CU(launch_bg_playout(ctx->stream, starts, n, seed, first_game_id, round_limit, winners_out, plies_out, finals_out,
-                         (unsigned long long *)ctx->q_head.p, &nl));
+                         (unsigned long long *)ctx->q_head.p, PbTable{(const uint32_t *)ctx->pb_index.p, (const uint16_t *)ctx->pb_plays.p}, &nl));
     ctx->launches += nl;
     return DIEE_OK;
 }
@@ -345,7 +361,8 @@ static int32_t mcts_search_dev_impl(diee_ctx *ctx, int32_t game_kind, const void
     if (rc != DIEE_OK) return rc;
     PoolPtrs pp{ctx->p_states.p, (int32_t *)ctx->p_parent.p, (float *)ctx->p_visits.p, (float *)ctx->p_value.p,
                 (uint32_t *)ctx->p_action.p, (uint32_t *)ctx->p_nmoves.p, (int32_t *)ctx->p_nnodes.p,
-                (int32_t *)ctx->p_simnode.p, ctx->p_finals.p};
+                (int32_t *)ctx->p_simnode.p, ctx->p_finals.p,
+                PbTable{(const uint32_t *)ctx->pb_index.p, (const uint16_t *)ctx->pb_plays.p}};
     RESERVE(ctx->q_head, sizeof(unsigned long long) * 8);
     SearchPipe pipe;
     for (int i = 0; i < SEARCH_SLICES; ++i) { pipe.side[i] = ctx->side[i]; pipe.tree_done[i] = ctx->ev_tree[i]; pipe.roll_done[i] = ctx->ev_roll[i]; }

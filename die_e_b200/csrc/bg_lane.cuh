@@ -802,6 +802,24 @@ LANE_HD void l_movegen_pb(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int s
     gen.U = U;
 }
 
+// ---------------- pure bear-off by table (bg_pb_table.h builds it, once per context) ----------------
+// key = side, dice, occupied home points, home points holding exactly one checker; index[key] = first << 8 | count;
+// a play is packed n | x1 << 2 | t1 << 5 | x2 << 8 | t2 << 11 (points 0..5, 7 = collected).
+LANE_HD int l_pb_key(const LaneBoard &g) {
+    const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;
+    const uint32_t o123 = g.own[1] | g.own[2] | g.own[3];
+    const uint32_t occ = (g.own[0] | o123) & 0x3Fu, single = g.own[0] & ~o123 & 0x3Fu;
+    return (((g.player > 0 ? 21 : 0) + hi * (hi - 1) / 2 + (lo - 1)) * 64 + (int)occ) * 64 + (int)single;
+}
+LANE_HD LanePlay l_pb_unpack(uint32_t w) {
+    LanePlay pl;
+    pl.n = (int)(w & 3u);
+    const int x1 = (int)((w >> 2) & 7u), t1 = (int)((w >> 5) & 7u), x2 = (int)((w >> 8) & 7u), t2 = (int)((w >> 11) & 7u);
+    pl.x1 = x1; pl.t1 = t1 == 7 ? L_OFF : t1;
+    pl.x2 = x2; pl.t2 = t2 == 7 ? L_OFF : t2;
+    return pl;
+}
+
 // Counts the distinct plays of `g`.  Contact play is counted in closed form; otherwise root by root.
 LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stride) {
     const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;

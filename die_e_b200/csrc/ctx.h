@@ -25,6 +25,7 @@ struct diee_ctx {
     // pure-MCTS node pool (HBM resident, reused between searches)
     DevBuf p_states, p_parent, p_visits, p_value, p_action, p_nmoves, p_nnodes, p_simnode, p_finals, ln_table;
     uint32_t ln_table_n = 0;
+    DevBuf pb_index, pb_plays;  // pure bear-off play table (bg_pb_table.h)
     DevBuf q_head;  // job queue heads of the persistent lane kernel (lane_kernels.cu)
     // side streams / events of the sliced search (mcts_kernels.cu launch_typed)
     cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -48,9 +48,9 @@ struct LaneJob {
     uint64_t seed;
     uint32_t first_game_id, epoch;
     int store_min;                 // scheduling: lanes that must wait to write a result / take an item before it happens
-    int walk_min;                  // scheduling: lanes that must wait for the bear-off walk before it runs
     int lag_weight;                // scheduling: how much one step of waiting counts against one more waiting lane
     unsigned long long *next_item; // job queue head (zeroed before the launch)
+    PbTable pb;                    // pure bear-off play table
     const diee_bg_state *states;   // PLAYOUT: starts[n]; ROLLOUT: node pool states
     const int32_t *sim_node;       // ROLLOUT: node each simulation rolls out from, or -1
     diee_bg_state *finals;         // PLAYOUT: nullable
@@ -70,7 +70,11 @@ __device__ __forceinline__ int lane_path(const LaneBoard &g) {
     const uint32_t own1 = g.own[0] | o123;
     if (g.bar_own > 0 || own1 == 0) return PATH_CLOSED;
     const uint32_t outside = own1 & ~0x3Fu;
-    if ((outside & (outside - 1u)) == 0 && (outside & ~(g.own[0] & ~o123)) == 0) return PATH_WALK;
+    if ((outside & (outside - 1u)) == 0 && (outside & ~(g.own[0] & ~o123)) == 0) {
+        // bearing off.  Every checker home and no opposing checker there: the play comes out of the table (cheap, so it
+        // rides with the closed path); one checker still outside, or contact inside the home board: the walk.
+        return (outside == 0 && ((g.opp[0] | g.opp[1] | g.opp[2] | g.opp[3]) & 0x3Fu) == 0) ? PATH_CLOSED : PATH_WALK;
+    }
     return PATH_CLOSED;
 }
 
@@ -142,13 +146,6 @@ lane_run_kernel(LaneJob job) {
                 if (score > best_score) { best_score = score; best = p; }
             }
         }
-        if (best == PATH_WALK && job.walk_min > 0) {
-            // the walk is the expensive, badly vectorised path: it waits until most of the warp wants it (or nobody
-            // wants anything else), the closed path goes first meanwhile.  Measured: 24 of 32 is best (1.64 -> 1.56 ms
-            // for the C3 rollouts, 1.27 -> 1.17 ms for C2); 32 starves the walkers.
-            const uint32_t wl = __ballot_sync(0xFFFFFFFFu, need == PATH_WALK), cl = __ballot_sync(0xFFFFFFFFu, need == PATH_CLOSED);
-            if (cl && __popc(wl) < job.walk_min) best = PATH_CLOSED;
-        }
         {   // results are written in batches: when enough of the warp waits to, or nothing else is left to do
             const uint32_t storing = __ballot_sync(0xFFFFFFFFu, need == PATH_STORE);
             if (storing && (best == PATH_DONE || __popc(storing) >= job.store_min)) best = PATH_STORE;
@@ -188,11 +185,18 @@ lane_run_kernel(LaneJob job) {
             const int hi = max(g.roll0, g.roll1), lo = min(g.roll0, g.roll1);
             LaneMasks m;
             l_closed_applies(g, m, lo, hi);
-            LaneGen gen;
-            gen.U = 0;
-            if (g.bar_own > 0) l_movegen_bar(g, m, lo, hi, gen);
-            else if (m.own1 != 0) l_movegen_closed(g, m, lo, hi, gen);
-            if (gen.U > 0) pl = l_pick(g, gen, scr, LANE_CTA, (int)l_index(o[2], (uint32_t)gen.U));
+            if (g.bar_own == 0 && m.own1 != 0 && (m.own1 & ~0x3Fu) == 0) {
+                // pure bear-off (lane_path sends only those here with every checker home): two loads
+                const uint32_t e = __ldg(job.pb.index + l_pb_key(g));
+                const uint32_t U = e & 255u;
+                if (U > 0) pl = l_pb_unpack(__ldg(job.pb.plays + (e >> 8) + l_index(o[2], U)));
+            } else {
+                LaneGen gen;
+                gen.U = 0;
+                if (g.bar_own > 0) l_movegen_bar(g, m, lo, hi, gen);
+                else if (m.own1 != 0) l_movegen_closed(g, m, lo, hi, gen);
+                if (gen.U > 0) pl = l_pick(g, gen, scr, LANE_CTA, (int)l_index(o[2], (uint32_t)gen.U));
+            }
         } else {
             LaneGen gen;
             l_movegen_walk(g, gen, scr, LANE_CTA);
@@ -221,14 +225,13 @@ template <bool ROLLOUT>
 static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) {
     // tuning knobs, read once: waiting-time weight of the vote, resident CTAs (x 2 warps) per SM, walk threshold.  Measured on
     // B200 with 102,400 rollouts: 10 CTAs of 64 lanes per SM and weight 0 are best.
-    static int sms = 0, lag_weight = 0, blocks_per_sm = 10, walk_min = 24;
+    static int sms = 0, lag_weight = 0, blocks_per_sm = 10;
     if (sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
         if (const char *e = getenv("DIEE_LANE_LAG")) lag_weight = atoi(e);
-        if (const char *e = getenv("DIEE_LANE_WALK_MIN")) walk_min = atoi(e);
         if (const char *e = getenv("DIEE_LANE_BLOCKS_PER_SM")) blocks_per_sm = atoi(e) > 0 ? atoi(e) : 10;
     }
     job.lag_weight = lag_weight;
@@ -237,9 +240,6 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
     // with 10 CTAs per SM, 82.6 M with 16)
     const bool refilled = job.n_items > (long long)sms * blocks_per_sm * LANE_CTA * 5 / 4;
     const int bps = refilled ? 16 : blocks_per_sm;
-    // (only while every lane holds about one item: with a refilled queue the closed path never runs dry, and holding
-    // the walk back would starve it -- measured 78 M -> 64 M simulations/s at 8,192 games)
-    job.walk_min = refilled ? 0 : walk_min;
     // results are written / items taken once this many lanes wait (a quarter of the warp; three quarters when the queue
     // keeps every lane busy anyway: 81.8 M -> 85.2 M simulations/s at 8,192 games)
     job.store_min = refilled ? 24 : 8;
@@ -254,10 +254,11 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
 
 cudaError_t launch_bg_playout(cudaStream_t st, const diee_bg_state *starts, int n, uint64_t seed, uint32_t first_game_id,
                               int round_limit, int8_t *winners_out, int32_t *plies_out, diee_bg_state *finals_out,
-                              unsigned long long *queue_head, int *launches) {
+                              unsigned long long *queue_head, const PbTable &pb, int *launches) {
     if (n <= 0) return cudaSuccess;
     LaneJob job{};
     job.next_item = queue_head;
+    job.pb = pb;
     job.n_items = n; job.limit = (uint32_t)round_limit; job.seed = seed; job.first_game_id = first_game_id;
     job.states = starts; job.finals = finals_out; job.winners = winners_out; job.plies = plies_out;
     return launch_lane_job<false>(st, job, launches);
@@ -274,6 +275,7 @@ cudaError_t launch_bg_rollouts(cudaStream_t st, int n_games, const diee_mcts_cfg
     job.states = static_cast<const diee_bg_state *>(pp.states); job.sim_node = pp.sim_node;
     job.finals = static_cast<diee_bg_state *>(pp.finals);
     job.next_item = queue_head;
+    job.pb = pp.pb;
     return launch_lane_job<true>(st, job, launches);
 }
 

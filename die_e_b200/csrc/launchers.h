@@ -7,6 +7,12 @@
 
 namespace diee {
 
+// the pure bear-off play table (bg_pb_table.h), device copies owned by the context
+struct PbTable {
+    const uint32_t *index;
+    const uint16_t *plays;
+};
+
 struct PoolPtrs {
     void *states;
     int32_t *parent;
@@ -16,6 +22,7 @@ struct PoolPtrs {
     int32_t *n_nodes;
     int32_t *sim_node;
     void *finals;
+    PbTable pb;
 };
 
 // side streams of a split search: rollouts of one slice of iterations run beside the tree kernel of the next
@@ -33,7 +40,7 @@ cudaError_t launch_bg_valid_moves(cudaStream_t st, const diee_bg_state *states, 
 cudaError_t launch_bg_apply(cudaStream_t st, diee_bg_state *states, const diee_move *moves, const uint8_t *next_rolls, int n);
 cudaError_t launch_bg_playout(cudaStream_t st, const diee_bg_state *starts, int n, uint64_t seed, uint32_t first_game_id,
                               int round_limit, int8_t *winners_out, int32_t *plies_out, diee_bg_state *finals_out,
-                              unsigned long long *queue_head, int *launches);
+                              unsigned long long *queue_head, const PbTable &pb, int *launches);
 // every deferred rollout of a split backgammon search, one lane per (game, iteration)  (lane_kernels.cu)
 cudaError_t launch_bg_rollouts(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, uint32_t it_begin, uint32_t it_end,
                                uint64_t seed, uint32_t first_game_id, uint32_t epoch, const PoolPtrs &pp,

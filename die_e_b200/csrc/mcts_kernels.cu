@@ -54,7 +54,8 @@ __device__ __forceinline__ void bg_to_planes(const BgWarp &g, lane::LaneBoard &b
 // instruction-fetch bound); everything travels BY VALUE in registers: a reference to the caller's board
 // would force it into local memory and every call would start with a round trip through it.
 // k >= 0: the k-th play; k == -1: count only; k == -2: the play at index_of(w, U) (a rollout's uniform choice).
-__device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal, WarpSlab *slab, int lane, int k, uint32_t w) {
+__device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal, WarpSlab *slab, int lane, int k, uint32_t w,
+                                                            const uint32_t *pb_index, const uint16_t *pb_plays) {
     BgWarp g;
     g.v = v;
     g.bar0 = (int)(scal & 15u); g.bar1 = (int)((scal >> 4) & 15u); g.off0 = (int)((scal >> 8) & 15u); g.off1 = (int)((scal >> 12) & 15u);
@@ -76,14 +77,12 @@ __device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal
         if (k >= 0 && k < gen.U) seq = lane::l_play_to_seq(lane::l_pick(b, gen, nullptr, 0, k), g.player);
         return ((unsigned long long)(uint32_t)gen.U << 32) | seq;
     }
-    if (lane::l_pure_bearoff(b)) {  // six-point mask walk, redundantly on every lane; the slab is its scratch
-        lane::LaneGen gen;
-        lane::l_movegen_pb(b, gen, slab->raw, 1);
-        __syncwarp();
-        if (k == -2 && gen.U > 0) k = (int)index_of(w, (uint32_t)gen.U);
-        if (k >= 0 && k < gen.U) seq = lane::l_play_to_seq(lane::l_pick_walk(gen, slab->raw, 1, k), g.player);
-        __syncwarp();
-        return ((unsigned long long)(uint32_t)gen.U << 32) | seq;
+    if (lane::l_pure_bearoff(b)) {  // every checker home, no opposing checker there: the play table
+        const uint32_t e = __ldg(pb_index + lane::l_pb_key(b));
+        const int U = (int)(e & 255u);
+        if (k == -2 && U > 0) k = (int)index_of(w, (uint32_t)U);
+        if (k >= 0 && k < U) seq = lane::l_play_to_seq(lane::l_pb_unpack(__ldg(pb_plays + (e >> 8) + k)), g.player);
+        return ((unsigned long long)(uint32_t)U << 32) | seq;
     }
     bool ovf = false;
     const int U = bg_movegen(g, *slab, lane, ovf);
@@ -96,11 +95,14 @@ __device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal
 struct BgGame {
     using State = diee_bg_state;
     BgWarp g;
+    const uint32_t *pb_index;
+    const uint16_t *pb_plays;
+    __device__ __forceinline__ void attach(const PbTable &t) { pb_index = t.index; pb_plays = t.plays; }
     __device__ __forceinline__ int count_and_kth(WarpSlab &slab, int lane, bool &ovf, int k, uint32_t &seq) const {
         const uint32_t scal = (uint32_t)g.bar0 | ((uint32_t)g.bar1 << 4) | ((uint32_t)g.off0 << 8) | ((uint32_t)g.off1 << 12) |
                               ((uint32_t)g.roll0 << 16) | ((uint32_t)g.roll1 << 20) | ((g.player > 0 ? 1u : 0u) << 24) |
                               ((uint32_t)(g.second ? 1 : 0) << 25);
-        const unsigned long long r = bg_count_and_kth(g.v, scal, &slab, lane, k, 0u);
+        const unsigned long long r = bg_count_and_kth(g.v, scal, &slab, lane, k, 0u, pb_index, pb_plays);
         if (r >> 63) ovf = true;
         if (k >= 0) seq = (uint32_t)r;
         return (int)((r >> 32) & 0x7FFFFFFFu);
@@ -110,7 +112,7 @@ struct BgGame {
         const uint32_t scal = (uint32_t)g.bar0 | ((uint32_t)g.bar1 << 4) | ((uint32_t)g.off0 << 8) | ((uint32_t)g.off1 << 12) |
                               ((uint32_t)g.roll0 << 16) | ((uint32_t)g.roll1 << 20) | ((g.player > 0 ? 1u : 0u) << 24) |
                               ((uint32_t)(g.second ? 1 : 0) << 25);
-        const unsigned long long r = bg_count_and_kth(g.v, scal, &slab, lane, -2, w);
+        const unsigned long long r = bg_count_and_kth(g.v, scal, &slab, lane, -2, w, pb_index, pb_plays);
         if (r >> 63) ovf = true;
         return (uint32_t)r;
     }
@@ -124,6 +126,7 @@ struct BgGame {
 
 struct TttGame {  // tictactoe/mod.rs; the whole state is warp-uniform
     using State = diee_ttt_state;
+    __device__ __forceinline__ void attach(const PbTable &) {}
     uint32_t xm, om;  // cells held by -1 / +1
     int player;
     __device__ __forceinline__ void load(const State *s, int lane) {
@@ -181,6 +184,7 @@ struct Pool {
     int32_t *n_nodes;  // per game
     int32_t *sim_node; // [game][iteration]: node whose rollout the rollout kernel still has to run, or -1
     void *finals;      // [game][iteration]: state each simulation's rollout ended in (zero = no rollout)
+    PbTable pb;        // pure bear-off play table (backgammon)
 };
 
 __device__ __forceinline__ float outcome(int winner, int player) {  // simple_mcts.rs:26-28
@@ -271,6 +275,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     // rollouts of a slice can run beside the tree work of the next): everything a later slice needs is in
     // the pool; n_nodes == 0 marks a terminal root.
     G game;
+    game.attach(pool.pb);
     uint32_t best = SEQ_EMPTY;
     int status = DIEE_OK;
     int n_nodes = 0;
@@ -513,6 +518,7 @@ rollout_kernel(int n_games, diee_mcts_cfg cfg, uint64_t seed, uint32_t first_gam
     if (node < 0) return;
     const size_t cap = (size_t)cfg.iterations + 1;
     G game;
+    game.attach(pool.pb);
     game.load(reinterpret_cast<const typename G::State *>(pool.states) + (size_t)g * cap + node, lane);
     bool ovf = false;
     unsigned long long plies = 0;
@@ -606,7 +612,7 @@ cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots
                                int32_t *status_out, diee_search_stats *stats_out, bool dump, int *launches) {
     *launches = 0;
     if (n <= 0) return cudaSuccess;
-    Pool pool{pp.states, pp.parent, pp.visits, pp.value, pp.action, pp.nmoves, pp.n_nodes, pp.sim_node, pp.finals};
+    Pool pool{pp.states, pp.parent, pp.visits, pp.value, pp.action, pp.nmoves, pp.n_nodes, pp.sim_node, pp.finals, pp.pb};
     if (game_kind == DIEE_GAME_BACKGAMMON)
         return launch_typed<BgGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, pp, pipe, ln_table, best_out,
                                     status_out, stats_out, dump, launches);

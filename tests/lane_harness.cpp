@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "../die_e_b200/csrc/bg_lane.cuh"
+#include "../die_e_b200/csrc/bg_pb_table.h"
 #include "../oracle/orc.h"
 
 using namespace diee::lane;
@@ -36,6 +37,8 @@ static void print_state(const orc_bg_state &s) {
 static long long n_checked = 0, n_moves_checked = 0, n_boregime = 0, n_bo_opp_home = 0, n_doubles = 0, n_bar = 0;
 static int max_moves = 0;
 static long long n_closed = 0, n_pb = 0;
+static std::vector<uint32_t> pb_index;
+static std::vector<uint16_t> pb_plays;
 
 static bool check_position(const orc_bg_state &s) {
     uint32_t w[8];
@@ -68,6 +71,16 @@ static bool check_position(const orc_bg_state &s) {
         if (n > max_moves) max_moves = n;
         if (gen.closed && n > 0) ++n_closed;
         if (l_pure_bearoff(g) && n > 0) ++n_pb;
+        if (l_pure_bearoff(g)) {  // the play table the kernels use for these positions
+            const uint32_t e = pb_index[l_pb_key(g)];
+            if ((int)(e & 255u) != n) { fprintf(stderr, "table count differs: %u oracle %d\n", e & 255u, n); print_state(s); return false; }
+            for (int k = 0; k < n; ++k) {
+                const uint32_t q = l_play_to_seq(l_pb_unpack(pb_plays[(e >> 8) + k]), g.player);
+                uint32_t o;
+                memcpy(&o, &mv[k], 4);
+                if (q != o) { fprintf(stderr, "table play %d differs\n", k); print_state(s); return false; }
+            }
+        }
     }
     if (gen.U != n) {
         fprintf(stderr, "count differs: lane %d oracle %d\n", gen.U, n);
@@ -168,6 +181,7 @@ int main(int argc, char **argv) {
     const int n_playouts = argc > 1 ? atoi(argv[1]) : 200;
     const long long n_syn = argc > 2 ? atoll(argv[2]) : 200000;
     rng_state = argc > 3 ? strtoull(argv[3], nullptr, 0) : 1;
+    diee::pb_build_table(pb_index, pb_plays);
 
     // (a) every ply of oracle-driven playouts, plus the lane engine playing the same games on its own
     for (int gm = 0; gm < n_playouts; ++gm) {

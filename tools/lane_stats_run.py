@@ -10,6 +10,6 @@ cfg = orc.mcts_cfg(iterations=100, c=2.0, limit=400, mode=_ffi.MODE_PASS_CHILD)
 lib.diee_debug_lane_stats(out,1)
 ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, states["player"].copy(), cfg, 0xD1EE, 0, 0)
 lib.diee_debug_lane_stats(out,1)
-names=['done','closed','bearoff','walk']
+names=['done','closed','walk','store']
 for p in range(1,4):
     print(names[p], 'steps', out[p], 'lanes', out[8+p], 'avg lanes/step %.1f'%(out[8+p]/max(out[p],1)))

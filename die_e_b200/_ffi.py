@@ -44,7 +44,8 @@ SYMBOLS = [
     "diee_bg_playout", "diee_bg_playout_dev", "diee_bg_encode_moves", "diee_bg_decode_moves",
     "diee_bg_encode_states", "diee_bg_encode_states_dev", "diee_mcts_search", "diee_mcts_search_dev",
     "diee_net_create", "diee_net_destroy", "diee_net_set_precision", "diee_net_param_count", "diee_net_forward", "diee_net_forward_dev",
-    "diee_search_timing", "diee_dirichlet", "diee_alpha_search", "diee_alpha_search_dev", "diee_selfplay_run", "diee_net_eval_count",
+    "diee_search_timing", "diee_comm_unique_id", "diee_comm_init", "diee_comm_destroy", "diee_traj_allgather",
+    "diee_net_broadcast", "diee_dirichlet", "diee_alpha_search", "diee_alpha_search_dev", "diee_selfplay_run", "diee_net_eval_count",
 ]
 
 
@@ -100,6 +101,18 @@ def dirichlet(seed, epoch, alpha, n=ACTION_SPACE):
     if rc != OK:
         raise DieeError(rc, "diee_dirichlet: bad argument")
     return out
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """the NCCL rendezvous id: rank 0 draws it and ships it to the other ranks (diee_comm_init)"""
+    out = np.zeros(COMM_ID_BYTES, dtype=np.uint8)
+    rc = lib().diee_comm_unique_id(_p(out))
+    if rc != OK:
+        raise DieeError(rc, "diee_comm_unique_id: NCCL is not available")
+    return out.tobytes()
 
 
 def die_of(w):
@@ -266,6 +279,38 @@ class Context:
                                           C.c_uint32(first_game_id), C.c_int32(max_nodes), _p(rec), C.c_int32(rec_cap), _p(pi_ids),
                                           _p(pi_vals), C.c_int32(pi_cap), C.byref(n_rec), C.byref(n_pi), C.byref(n_waves)))
         return rec[: n_rec.value], pi_ids[: n_pi.value], pi_vals[: n_pi.value], n_waves.value
+
+    # ---- multi-GPU exchange over NCCL (one rank per context) ----
+    def comm_init(self, nranks, rank, unique_id):
+        uid = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        assert len(uid) == COMM_ID_BYTES
+        self._chk(lib().diee_comm_init(self._h, C.c_int32(nranks), C.c_int32(rank), _p(uid)))
+
+    def comm_destroy(self):
+        self._chk(lib().diee_comm_destroy(self._h))
+
+    def traj_allgather(self, rec, pi_ids, pi_vals, rec_cap, pi_cap):
+        """every rank's packed records -> all of them on every rank, rank-major, pi_offset rebased"""
+        rec = np.ascontiguousarray(rec, dtype=TRAJ).reshape(-1)
+        pi_ids = np.ascontiguousarray(pi_ids, dtype=np.uint16).reshape(-1)
+        pi_vals = np.ascontiguousarray(pi_vals, dtype=np.float32).reshape(-1)
+        assert len(pi_ids) == len(pi_vals)
+        rec_out = np.zeros(max(1, rec_cap), dtype=TRAJ)
+        ids_out = np.zeros(max(1, pi_cap), dtype=np.uint16)
+        vals_out = np.zeros(max(1, pi_cap), dtype=np.float32)
+        n_rec, n_pi = C.c_int32(0), C.c_int32(0)
+        self._chk(lib().diee_traj_allgather(self._h, _p(rec), C.c_int32(len(rec)), _p(pi_ids), _p(pi_vals), C.c_int32(len(pi_ids)),
+                                            _p(rec_out), C.c_int32(rec_cap), _p(ids_out), _p(vals_out), C.c_int32(pi_cap),
+                                            C.byref(n_rec), C.byref(n_pi)))
+        return rec_out[: n_rec.value], ids_out[: n_pi.value], vals_out[: n_pi.value]
+
+    def net_broadcast(self, tensors, root=0):
+        """in place: every rank's float32 arrays take rank `root`'s values"""
+        for t in tensors:
+            assert t.dtype == np.float32 and t.flags["C_CONTIGUOUS"]
+        ptrs = (C.c_void_p * len(tensors))(*[t.ctypes.data for t in tensors])
+        numels = np.array([t.size for t in tensors], dtype=np.int64)
+        self._chk(lib().diee_net_broadcast(self._h, ptrs, _p(numels), C.c_int32(len(tensors)), C.c_int32(root)))
 
     # ---- device-pointer forms (ints = raw device addresses, e.g. torch tensor .data_ptr()) ----
     def bg_playout_dev(self, d_starts, n, seed, first_game_id, round_limit, d_winners, d_plies, d_finals=0):

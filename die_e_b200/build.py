@@ -28,7 +28,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
-    cmd = [NVCC] + FLAGS + ["-o", OUT] + sources() + ["-lcudart"]
+    cmd = [NVCC] + FLAGS + ["-o", OUT] + sources() + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

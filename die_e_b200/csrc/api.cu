@@ -64,6 +64,7 @@ int32_t diee_ctx_create(int32_t device, diee_ctx **out) {
 
 int32_t diee_ctx_destroy(diee_ctx *ctx) {
     if (!ctx) return DIEE_ERR_INVALID;
+    diee_comm_destroy(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->s_states, &ctx->s_moves, &ctx->s_counts, &ctx->s_ids, &ctx->s_aux, &ctx->s_out,
@@ -84,6 +85,8 @@ int32_t diee_ctx_destroy(diee_ctx *ctx) {
     for (int i = 0; i < 3; ++i)
         if (ctx->ev_time[i]) cudaEventDestroy(ctx->ev_time[i]);
     if (ctx->q_head.p) cudaFree(ctx->q_head.p);
+    for (DevBuf *b : {&ctx->c_counts, &ctx->c_send, &ctx->c_recv})
+        if (b->p) cudaFree(b->p);
     if (ctx->pb_index.p) cudaFree(ctx->pb_index.p);
     if (ctx->pb_plays.p) cudaFree(ctx->pb_plays.p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -1,0 +1,201 @@
+// comm.cu -- the one exchange step of the path: finished self-play trajectories are all-gathered
+// into every rank's replay buffer, and a promoted model's weights are broadcast, over NCCL (NVLink 5 / NVSwitch on a
+// B200 node).  One rank per context / GPU.  Games never interact (the reference runs them as independent rayon
+// tasks, versus.rs:303-316), so nothing else on the path communicates.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2), not at link time: the library must load on a box that has no
+// NCCL at all, and inside a process where torch has already loaded its own copy.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstring>
+#include <vector>
+
+#include "ctx.h"
+
+namespace {
+
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclInt8 = 0, ncclChar = 0, ncclUint8 = 1, ncclFloat32 = 7, ncclInt64 = 4 };
+
+struct Nccl {
+    void *h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+
+Nccl *nccl() {
+    static Nccl n;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        n.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!n.h) n.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (n.h) {
+            n.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(n.h, "ncclGetUniqueId");
+            n.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(n.h, "ncclCommInitRank");
+            n.CommDestroy = (int (*)(ncclComm_t))dlsym(n.h, "ncclCommDestroy");
+            n.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(n.h, "ncclAllGather");
+            n.Broadcast = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(n.h, "ncclBroadcast");
+            n.GetErrorString = (const char *(*)(int))dlsym(n.h, "ncclGetErrorString");
+            if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.AllGather || !n.Broadcast) n.h = nullptr;
+        }
+    }
+    return n.h ? &n : nullptr;
+}
+
+#define NC(call)                                                                                                   \
+    do {                                                                                                           \
+        int r_ = (call);                                                                                           \
+        if (r_ != ncclSuccess)                                                                                     \
+            return fail(ctx, DIEE_ERR_CUDA, "%s: %s", #call, N->GetErrorString ? N->GetErrorString(r_) : "NCCL error"); \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int32_t diee_comm_unique_id(uint8_t *id_out) {
+    Nccl *N = nccl();
+    if (!N || !id_out) return DIEE_ERR_CUDA;
+    ncclUniqueId id;
+    if (N->GetUniqueId(&id) != ncclSuccess) return DIEE_ERR_CUDA;
+    memcpy(id_out, &id, DIEE_COMM_ID_BYTES);
+    return DIEE_OK;
+}
+
+int32_t diee_comm_init(diee_ctx *ctx, int32_t nranks, int32_t rank, const uint8_t *id) {
+    if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, DIEE_ERR_INVALID, "comm_init: bad argument");
+    Nccl *N = nccl();
+    if (!N) return fail(ctx, DIEE_ERR_CUDA, "comm_init: libnccl.so.2 could not be loaded");
+    if (ctx->comm) return fail(ctx, DIEE_ERR_INVALID, "comm_init: the context already has a communicator");
+    CU(cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, DIEE_COMM_ID_BYTES);
+    ncclComm_t c = nullptr;
+    NC(N->CommInitRank(&c, nranks, uid, rank));
+    ctx->comm = c;
+    ctx->comm_ranks = nranks;
+    ctx->comm_rank = rank;
+    return DIEE_OK;
+}
+
+int32_t diee_comm_destroy(diee_ctx *ctx) {
+    if (!ctx) return DIEE_ERR_INVALID;
+    Nccl *N = nccl();
+    if (ctx->comm && N) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        N->CommDestroy((ncclComm_t)ctx->comm);
+    }
+    ctx->comm = nullptr;
+    ctx->comm_ranks = 0;
+    return DIEE_OK;
+}
+
+// Ragged sizes: the counts first, then slabs padded to the largest contribution; the host keeps each rank's valid prefix,
+// rank-major, and rebases pi_offset into the concatenated pi arrays.
+int32_t diee_traj_allgather(diee_ctx *ctx, const diee_traj_record *rec, int32_t n_rec, const uint16_t *pi_ids, const float *pi_vals,
+                            int32_t n_pi, diee_traj_record *rec_out, int32_t rec_cap, uint16_t *pi_ids_out, float *pi_vals_out,
+                            int32_t pi_cap, int32_t *n_rec_out, int32_t *n_pi_out) {
+    if (!ctx || n_rec < 0 || n_pi < 0 || !n_rec_out || !n_pi_out || (n_rec && !rec) || (n_pi && (!pi_ids || !pi_vals)))
+        return fail(ctx, DIEE_ERR_INVALID, "traj_allgather: bad argument");
+    Nccl *N = nccl();
+    if (!N || !ctx->comm) return fail(ctx, DIEE_ERR_INVALID, "traj_allgather: diee_comm_init has not been called on this context");
+    CU(cudaSetDevice(ctx->device));
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    const int W = ctx->comm_ranks;
+    cudaStream_t st = ctx->stream;
+    // counts
+    RESERVE(ctx->c_counts, sizeof(long long) * 2 * (size_t)(W + 1));
+    long long mine[2] = {n_rec, n_pi};
+    long long *d_mine = (long long *)ctx->c_counts.p, *d_all = d_mine + 2;
+    CU(cudaMemcpyAsync(d_mine, mine, sizeof mine, cudaMemcpyHostToDevice, st));
+    NC(N->AllGather(d_mine, d_all, 2, ncclInt64, comm, st));
+    std::vector<long long> all(2 * (size_t)W);
+    CU(cudaMemcpyAsync(all.data(), d_all, sizeof(long long) * 2 * W, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    long long max_rec = 1, max_pi = 1, tot_rec = 0, tot_pi = 0;
+    for (int r = 0; r < W; ++r) {
+        max_rec = all[2 * r] > max_rec ? all[2 * r] : max_rec;
+        max_pi = all[2 * r + 1] > max_pi ? all[2 * r + 1] : max_pi;
+        tot_rec += all[2 * r];
+        tot_pi += all[2 * r + 1];
+    }
+    *n_rec_out = (int32_t)tot_rec;
+    *n_pi_out = (int32_t)tot_pi;
+    if (tot_rec > rec_cap || tot_pi > pi_cap) return fail(ctx, DIEE_ERR_OVERFLOW, "traj_allgather: %lld records / %lld pi entries do not fit", tot_rec, tot_pi);
+    if ((tot_rec && !rec_out) || (tot_pi && (!pi_ids_out || !pi_vals_out))) return fail(ctx, DIEE_ERR_INVALID, "traj_allgather: null output");
+    // slabs: [records | ids | values] of one rank, padded
+    const size_t b_rec = sizeof(diee_traj_record) * (size_t)max_rec, b_ids = (2 * (size_t)max_pi + 3) & ~(size_t)3, b_val = 4 * (size_t)max_pi;
+    const size_t slab = b_rec + b_ids + b_val;
+    RESERVE(ctx->c_send, slab);
+    RESERVE(ctx->c_recv, slab * (size_t)W);
+    unsigned char *d_send = (unsigned char *)ctx->c_send.p, *d_recv = (unsigned char *)ctx->c_recv.p;
+    if (n_rec) CU(cudaMemcpyAsync(d_send, rec, sizeof(diee_traj_record) * (size_t)n_rec, cudaMemcpyHostToDevice, st));
+    if (n_pi) {
+        CU(cudaMemcpyAsync(d_send + b_rec, pi_ids, 2 * (size_t)n_pi, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_send + b_rec + b_ids, pi_vals, 4 * (size_t)n_pi, cudaMemcpyHostToDevice, st));
+    }
+    NC(N->AllGather(d_send, d_recv, slab, ncclChar, comm, st));
+    long long o_rec = 0, o_pi = 0;
+    for (int r = 0; r < W; ++r) {
+        const long long nr = all[2 * r], np = all[2 * r + 1];
+        const unsigned char *src = d_recv + slab * (size_t)r;
+        if (nr) CU(cudaMemcpyAsync(rec_out + o_rec, src, sizeof(diee_traj_record) * (size_t)nr, cudaMemcpyDeviceToHost, st));
+        if (np) {
+            CU(cudaMemcpyAsync(pi_ids_out + o_pi, src + b_rec, 2 * (size_t)np, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(pi_vals_out + o_pi, src + b_rec + b_ids, 4 * (size_t)np, cudaMemcpyDeviceToHost, st));
+        }
+        o_rec += nr;
+        o_pi += np;
+    }
+    CU(cudaStreamSynchronize(st));
+    o_rec = 0; o_pi = 0;
+    for (int r = 0; r < W; ++r) {  // pi_offset of rank r's records now counts from the start of the concatenated arrays
+        for (long long i = 0; i < all[2 * r]; ++i) rec_out[o_rec + i].pi_offset += (uint32_t)o_pi;
+        o_rec += all[2 * r];
+        o_pi += all[2 * r + 1];
+    }
+    return DIEE_OK;
+}
+
+// every rank passes the same tensor list (host f32 arrays); on return all hold rank `root`'s values
+int32_t diee_net_broadcast(diee_ctx *ctx, float *const *tensors, const int64_t *numels, int32_t n_tensors, int32_t root) {
+    if (!ctx || !tensors || !numels || n_tensors < 0) return fail(ctx, DIEE_ERR_INVALID, "net_broadcast: bad argument");
+    Nccl *N = nccl();
+    if (!N || !ctx->comm) return fail(ctx, DIEE_ERR_INVALID, "net_broadcast: diee_comm_init has not been called on this context");
+    if (root < 0 || root >= ctx->comm_ranks) return fail(ctx, DIEE_ERR_INVALID, "net_broadcast: bad root");
+    CU(cudaSetDevice(ctx->device));
+    size_t total = 0;
+    for (int i = 0; i < n_tensors; ++i) total += (size_t)numels[i];
+    if (total == 0) return DIEE_OK;
+    RESERVE(ctx->c_send, total * sizeof(float));
+    float *d = (float *)ctx->c_send.p;
+    cudaStream_t st = ctx->stream;
+    if (ctx->comm_rank == root) {
+        size_t off = 0;
+        for (int i = 0; i < n_tensors; ++i) {
+            CU(cudaMemcpyAsync(d + off, tensors[i], sizeof(float) * (size_t)numels[i], cudaMemcpyHostToDevice, st));
+            off += (size_t)numels[i];
+        }
+    }
+    NC(N->Broadcast(d, d, total, ncclFloat32, root, (ncclComm_t)ctx->comm, st));
+    if (ctx->comm_rank != root) {
+        size_t off = 0;
+        for (int i = 0; i < n_tensors; ++i) {
+            CU(cudaMemcpyAsync(tensors[i], d + off, sizeof(float) * (size_t)numels[i], cudaMemcpyDeviceToHost, st));
+            off += (size_t)numels[i];
+        }
+    }
+    CU(cudaStreamSynchronize(st));
+    return DIEE_OK;
+}
+
+}  // extern "C"

@@ -38,6 +38,10 @@ struct diee_ctx {
         a_root_counts, a_moves_in, a_rolls_in;
     std::vector<float> dir_host;
     uint64_t net_evals = 0;
+    // NCCL communicator of this rank (comm.cu), bound at run time
+    void *comm = nullptr;
+    int comm_ranks = 0, comm_rank = 0;
+    DevBuf c_counts, c_send, c_recv;
 };
 
 static inline int32_t fail(diee_ctx *ctx, int32_t code, const char *fmt, ...) {

@@ -57,6 +57,12 @@ def allgather_trajectories(rec, pi_ids, pi_vals, group=None):
     return np.concatenate(out_rec), np.concatenate(out_ids), np.concatenate(out_vals)
 
 
+def allgather_trajectories_abi(ctx, rec, pi_ids, pi_vals, rec_cap, pi_cap):
+    """the same exchange through the C ABI (diee_traj_allgather: NCCL bound inside the library, no torch involved);
+    `ctx` must have joined a communicator with ctx.comm_init(nranks, rank, _ffi.comm_unique_id() of rank 0)"""
+    return ctx.traj_allgather(rec, pi_ids, pi_vals, rec_cap, pi_cap)
+
+
 def broadcast_weights(tensors, src=0, group=None):
     """new model -> every rank (94 MB fp32 for the backgammon net)"""
     dev = _dev(group)

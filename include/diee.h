@@ -283,6 +283,26 @@ int32_t diee_selfplay_run(diee_ctx *ctx, diee_net *net, int32_t n_games, const d
                           int32_t *n_waves_out);
 uint64_t diee_net_eval_count(const diee_ctx *ctx);
 
+/* ---- multi-GPU: the one exchange step of the path ----
+ * Games never interact (the reference runs them as independent rayon tasks, versus.rs:303-316): each GPU plays
+ * its own shard of game ids and no collective sits on the data path.  What is exchanged is the OUTPUT: finished
+ * self-play trajectories are all-gathered into every rank's replay buffer (the cumulative `memory` of
+ * alpha_parallel.rs:53), and a promoted model's weights are broadcast.  One rank per context / GPU, NCCL over
+ * NVLink; NCCL is bound at run time (libnccl.so.2), DIEE_ERR_CUDA if it is not there.
+ *   diee_comm_unique_id: rank 0 draws the rendezvous id and ships it to the other ranks by any means.
+ *   diee_traj_allgather: every rank contributes its records (host buffers); all receive all of them, rank-major,
+ *     with pi_offset rebased into the concatenated pi arrays.  *n_rec_out / *n_pi_out are the totals (set even when
+ *     they exceed the capacities and DIEE_ERR_OVERFLOW is returned).
+ *   diee_net_broadcast: the tensor list of diee_net_create, in place: on return every rank holds root's values. */
+#define DIEE_COMM_ID_BYTES 128
+int32_t diee_comm_unique_id(uint8_t *id_out);
+int32_t diee_comm_init(diee_ctx *ctx, int32_t nranks, int32_t rank, const uint8_t *id);
+int32_t diee_comm_destroy(diee_ctx *ctx);
+int32_t diee_traj_allgather(diee_ctx *ctx, const diee_traj_record *rec, int32_t n_rec, const uint16_t *pi_ids, const float *pi_vals,
+                            int32_t n_pi, diee_traj_record *rec_out, int32_t rec_cap, uint16_t *pi_ids_out, float *pi_vals_out,
+                            int32_t pi_cap, int32_t *n_rec_out, int32_t *n_pi_out);
+int32_t diee_net_broadcast(diee_ctx *ctx, float *const *tensors, const int64_t *numels, int32_t n_tensors, int32_t root);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,13 +1,14 @@
 // lane_kernels.cu -- one LANE per game: the throughput kernels of the path.
 //
-//   bg_lane_run_kernel<false>   C2: whole random-vs-random games
-//   bg_lane_run_kernel<true>    T4: every deferred Node::simulate of a split search (node.rs:176-196),
-//                               one lane per (game, iteration)
+//   lane_run_kernel<false>   C2: whole random-vs-random games
+//   lane_run_kernel<true>    T4: every deferred Node::simulate of a split search (node.rs:176-196),
+//                            one lane per (game, iteration)
 //
 // A ply is get_valid_moves -> uniform choice -> apply_move | skip_turn.  The board lives in the lane's
-// registers as bit planes (bg_lane.cuh); the only memory a ply touches is the lane's own column of a
-// shared-memory scratch (new-children masks per root), laid out [word][lane] so that a warp's accesses
-// never conflict.  HBM: 32 B in and 32 B (+5 B) out per game / per rollout, nothing in between.
+// registers as bit planes (bg_lane.cuh).  Contact plies touch no memory at all (closed forms); pure bear-off
+// plies read two words of the 1 MB play table (L2 / L1 resident); the remaining bear-off plies use the lane's
+// own column of a shared-memory scratch (new-children masks per root), laid out [word][lane] so that a warp's
+// accesses never conflict.  HBM: 32 B in and 32 B (+5 B) out per game / per rollout, nothing in between.
 // Randomness: one Philox4x32-10 block per ply, counter = (ply, game id, stream, epoch<<16|iteration)
 // -- the contract of include/diee.h, identical to the warp-per-game kernels and to the oracle.
 #include <climits>
@@ -228,8 +229,8 @@ __global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32
 
 template <bool ROLLOUT>
 static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) {
-    // tuning knobs, read once: waiting-time weight of the vote, resident CTAs (x 2 warps) per SM, walk threshold.  Measured on
-    // B200 with 102,400 rollouts: 10 CTAs of 64 lanes per SM and weight 0 are best.
+    // tuning knobs, read once: waiting-time weight of the vote and resident CTAs (x 2 warps) per SM.  Measured on B200 with
+    // 102,400 rollouts: 10 CTAs of 64 lanes per SM and weight 0 are best.
     static int sms = 0, lag_weight = 0, blocks_per_sm = 10;
     if (sms == 0) {
         int dev = 0;

@@ -898,5 +898,54 @@ LANE_HD LanePlay l_pick(const LaneBoard &g, const LaneGen &gen, const uint32_t *
     return l_play_from(y, hi, lo, l_two_newmask1(t, lo, hi, y), j, isplus);
 }
 
+// Count and selection in one go for the closed form (the masks are built once): returns U; k >= 0 asks for the
+// k-th play, k == -1 for the count only, k == -2 for the play at index_of(w, U) -- a rollout's uniform choice.
+// pl.n == 0 on return when there is no play to report.
+LANE_HD int l_closed_select(const LaneBoard &g, const LaneMasks &m, int lo, int hi, int k, uint32_t w, LanePlay &pl) {
+    const bool isplus = g.player > 0;
+    pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
+    LaneCum c;
+    int j;
+    if (lo == hi) {
+        LaneDbl t;
+        l_dbl(m, lo, isplus, t);
+        const int U = t.nR * (t.nR + 1) / 2 - l_popc(t.R & (t.R >> lo)) - l_popc(t.Lx) + l_popc(t.HIT) + l_popc(t.NEWRUN | t.NEWLEAPF) + l_popc(t.Z);
+        if (k == -2 && U > 0) k = (int)l_index(w, (uint32_t)U);
+        if (k < 0 || k >= U) return U;
+        c.R = t.R; c.base = t.nR; c.tri = true;
+        c.plus0 = t.HIT | t.NEWRUN | t.Z;
+        c.plus1 = (t.NEWLEAPF >> lo) & t.R;
+        c.minus0 = t.Lx;
+        c.minus1 = t.R & (isplus ? (t.R << lo) : (t.R >> lo));
+        const int x = l_find_root(c, k, isplus, j);
+        pl = l_play_from(x, lo, lo, l_dbl_newmask(m, t, lo, isplus, x), j, isplus);
+        return U;
+    }
+    LaneTwo t;
+    l_two(m, lo, hi, isplus, t);
+    const int N0 = t.nR0 * t.nR1 - l_popc(t.L) + l_popc(t.G0) - l_popc(t.D0) + l_popc(t.Z0);
+    const int U = N0 + l_popc(t.NR1) + l_popc(t.NL1) + l_popc(t.Z1);
+    if (k == -2 && U > 0) k = (int)l_index(w, (uint32_t)U);
+    if (k < 0 || k >= U) return U;
+    c.tri = false;
+    if (k < N0) {
+        c.R = t.R0; c.base = t.nR1;
+        c.plus0 = t.G0 | t.Z0;
+        c.plus1 = 0;
+        c.minus0 = t.L;
+        c.minus1 = isplus ? ((t.D0 >> hi) & t.R0) : t.D0;
+        const int x = l_find_root(c, k, isplus, j);
+        pl = l_play_from(x, lo, hi, l_two_newmask0(m, t, lo, hi, isplus, x), j, isplus);
+        return U;
+    }
+    c.R = t.R1; c.base = 0;
+    c.plus0 = t.NR1 | t.Z1;
+    c.plus1 = t.NL1;
+    c.minus0 = c.minus1 = 0;
+    const int y = l_find_root(c, k - N0, isplus, j);
+    pl = l_play_from(y, hi, lo, l_two_newmask1(t, lo, hi, y), j, isplus);
+    return U;
+}
+
 }  // namespace lane
 }  // namespace diee

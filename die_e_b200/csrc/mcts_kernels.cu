@@ -69,13 +69,20 @@ __device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal
     const bool closed = lane::l_closed_applies(b, m, lo, hi);
     uint32_t seq = SEQ_EMPTY;
     if (closed || b.bar_own > 0 || m.own1 == 0) {
-        lane::LaneGen gen;
-        gen.U = 0;
-        if (b.bar_own > 0) lane::l_movegen_bar(b, m, lo, hi, gen);
-        else if (m.own1 != 0) lane::l_movegen_closed(b, m, lo, hi, gen);
-        if (k == -2 && gen.U > 0) k = (int)index_of(w, (uint32_t)gen.U);
-        if (k >= 0 && k < gen.U) seq = lane::l_play_to_seq(lane::l_pick(b, gen, nullptr, 0, k), g.player);
-        return ((unsigned long long)(uint32_t)gen.U << 32) | seq;
+        int U = 0;
+        lane::LanePlay pl;
+        pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
+        if (b.bar_own > 0) {
+            lane::LaneGen gen;
+            lane::l_movegen_bar(b, m, lo, hi, gen);
+            U = gen.U;
+            if (k == -2 && U > 0) k = (int)index_of(w, (uint32_t)U);
+            if (k >= 0 && k < U) pl = lane::l_pick_bar(b, m, lo, hi, k);
+        } else if (m.own1 != 0) {
+            U = lane::l_closed_select(b, m, lo, hi, k, w, pl);
+        }
+        if (pl.n > 0) seq = lane::l_play_to_seq(pl, g.player);
+        return ((unsigned long long)(uint32_t)U << 32) | seq;
     }
     if (lane::l_pure_bearoff(b)) {  // every checker home, no opposing checker there: the play table
         const uint32_t e = __ldg(pb_index + lane::l_pb_key(b));

@@ -70,6 +70,20 @@ static bool check_position(const orc_bg_state &s) {
         if (g.bar_own > 0 && n > 0) ++n_bar;
         if (n > max_moves) max_moves = n;
         if (gen.closed && n > 0) ++n_closed;
+        {   // the fused count + select the kernels call for contact play
+            const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;
+            LaneMasks mm;
+            if (l_closed_applies(g, mm, lo, hi)) {
+                LanePlay pl;
+                if (l_closed_select(g, mm, lo, hi, -1, 0u, pl) != n) { fprintf(stderr, "closed_select count differs\n"); print_state(s); return false; }
+                for (int k = 0; k < n; ++k) {
+                    l_closed_select(g, mm, lo, hi, k, 0u, pl);
+                    uint32_t o;
+                    memcpy(&o, &mv[k], 4);
+                    if (l_play_to_seq(pl, g.player) != o) { fprintf(stderr, "closed_select play %d differs\n", k); print_state(s); return false; }
+                }
+            }
+        }
         if (l_pure_bearoff(g) && n > 0) ++n_pb;
         if (l_pure_bearoff(g)) {  // the play table the kernels use for these positions
             const uint32_t e = pb_index[l_pb_key(g)];

@@ -703,6 +703,28 @@ LANE_HD LanePlay l_pick_bar(const LaneBoard &g, const LaneMasks &m, int lo, int 
     return l_play_from(L_BAR, hi, lo, t.single1 ? L_SINGLE : t.N1, k - t.n0, isplus);
 }
 
+// count and selection in one go (same convention as l_closed_select)
+LANE_HD int l_bar_select(const LaneBoard &g, const LaneMasks &m, int lo, int hi, int k, uint32_t w, LanePlay &pl) {
+    LaneBarMasks t;
+    l_bar(g, m, lo, hi, t);
+    const bool isplus = g.player > 0;
+    const int U = t.n0 + t.n1;
+    pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
+    if (k == -2 && U > 0) k = (int)l_index(w, (uint32_t)U);
+    if (k < 0 || k >= U) return U;
+    if (g.bar_own >= 2) {
+        const bool both = t.fl && t.fh;
+        pl.x1 = L_BAR;
+        pl.t1 = t.fl ? 24 - lo : 24 - hi;
+        pl.n = both ? 2 : 1;
+        if (both) { pl.x2 = L_BAR; pl.t2 = 24 - hi; }
+        return U;
+    }
+    pl = k < t.n0 ? l_play_from(L_BAR, lo, hi, t.C0 ? t.C0 : L_SINGLE, k, isplus)
+                  : l_play_from(L_BAR, hi, lo, t.single1 ? L_SINGLE : t.N1, k - t.n0, isplus);
+    return U;
+}
+
 // ---------------- pure bear-off: every own checker in the home board, no opposing checker there ----------------
 // Six points, no hits, no blocks: the sources of die d are the own points >= d-1 (d-1 itself collects, the higher
 // ones move down), or, when all checkers sit below d-1, the highest own point (it collects with the bigger die).

@@ -196,9 +196,7 @@ lane_run_kernel(LaneJob job) {
                 if (U > 0) pl = l_pb_unpack(__ldg(job.pb.plays + (e >> 8) + l_index(o[2], U)));
             } else {
                 if (g.bar_own > 0) {
-                    LaneGen gen;
-                    l_movegen_bar(g, m, lo, hi, gen);
-                    if (gen.U > 0) pl = l_pick_bar(g, m, lo, hi, (int)l_index(o[2], (uint32_t)gen.U));
+                    l_bar_select(g, m, lo, hi, -2, o[2], pl);
                 } else if (m.own1 != 0) {
                     l_closed_select(g, m, lo, hi, -2, o[2], pl);
                 }

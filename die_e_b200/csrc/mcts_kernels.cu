@@ -73,11 +73,7 @@ __device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal
         lane::LanePlay pl;
         pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
         if (b.bar_own > 0) {
-            lane::LaneGen gen;
-            lane::l_movegen_bar(b, m, lo, hi, gen);
-            U = gen.U;
-            if (k == -2 && U > 0) k = (int)index_of(w, (uint32_t)U);
-            if (k >= 0 && k < U) pl = lane::l_pick_bar(b, m, lo, hi, k);
+            U = lane::l_bar_select(b, m, lo, hi, k, w, pl);
         } else if (m.own1 != 0) {
             U = lane::l_closed_select(b, m, lo, hi, k, w, pl);
         }

@@ -73,7 +73,17 @@ static bool check_position(const orc_bg_state &s) {
         {   // the fused count + select the kernels call for contact play
             const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;
             LaneMasks mm;
-            if (l_closed_applies(g, mm, lo, hi)) {
+            if (g.bar_own > 0) {
+                l_closed_applies(g, mm, lo, hi);
+                LanePlay pl;
+                if (l_bar_select(g, mm, lo, hi, -1, 0u, pl) != n) { fprintf(stderr, "bar_select count differs\n"); print_state(s); return false; }
+                for (int k = 0; k < n; ++k) {
+                    l_bar_select(g, mm, lo, hi, k, 0u, pl);
+                    uint32_t o;
+                    memcpy(&o, &mv[k], 4);
+                    if (l_play_to_seq(pl, g.player) != o) { fprintf(stderr, "bar_select play %d differs\n", k); print_state(s); return false; }
+                }
+            } else if (l_closed_applies(g, mm, lo, hi)) {
                 LanePlay pl;
                 if (l_closed_select(g, mm, lo, hi, -1, 0u, pl) != n) { fprintf(stderr, "closed_select count differs\n"); print_state(s); return false; }
                 for (int k = 0; k < n; ++k) {

@@ -926,46 +926,80 @@ LANE_HD LanePlay l_pick(const LaneBoard &g, const LaneGen &gen, const uint32_t *
 LANE_HD int l_closed_select(const LaneBoard &g, const LaneMasks &m, int lo, int hi, int k, uint32_t w, LanePlay &pl) {
     const bool isplus = g.player > 0;
     pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
+    // The die orders differ only in WHICH masks drive the root walk and the new-children mask, so each branch just
+    // picks its masks; the walk and the child pick then run once, for all lanes of the warp together.
     LaneCum c;
-    int j;
+    uint32_t aZ, a1, a2, a3;  // per mode: roots that are plays on their own, and the three masks of the new-children rule
+    int mode, m1 = lo, m2 = hi, U;
     if (lo == hi) {
         LaneDbl t;
         l_dbl(m, lo, isplus, t);
-        const int U = t.nR * (t.nR + 1) / 2 - l_popc(t.R & (t.R >> lo)) - l_popc(t.Lx) + l_popc(t.HIT) + l_popc(t.NEWRUN | t.NEWLEAPF) + l_popc(t.Z);
+        U = t.nR * (t.nR + 1) / 2 - l_popc(t.R & (t.R >> lo)) - l_popc(t.Lx) + l_popc(t.HIT) + l_popc(t.NEWRUN | t.NEWLEAPF) + l_popc(t.Z);
         if (k == -2 && U > 0) k = (int)l_index(w, (uint32_t)U);
-        if (k < 0 || k >= U) return U;
+        mode = 0;
         c.R = t.R; c.base = t.nR; c.tri = true;
-        c.plus0 = t.HIT | t.NEWRUN | t.Z;
-        c.plus1 = (t.NEWLEAPF >> lo) & t.R;
-        c.minus0 = t.Lx;
-        c.minus1 = t.R & (isplus ? (t.R << lo) : (t.R >> lo));
-        const int x = l_find_root(c, k, isplus, j);
-        pl = l_play_from(x, lo, lo, l_dbl_newmask(m, t, lo, isplus, x), j, isplus);
-        return U;
+        c.plus0 = t.HIT | t.NEWRUN | t.Z;                       // disjoint: a root without children neither runs on nor hits
+        c.plus1 = (t.NEWLEAPF >> lo) & t.R;                     // the root whose refill child is new
+        c.minus0 = t.Lx;                                        // a lone checker cannot be moved twice
+        c.minus1 = t.R & (isplus ? (t.R << lo) : (t.R >> lo));  // the run-on / refill partner is judged on its own
+        aZ = t.Z; a1 = t.R; a2 = t.HIT | t.NEWRUN; a3 = t.NEWLEAPF;
+    } else {
+        LaneTwo t;
+        l_two(m, lo, hi, isplus, t);
+        const int N0 = t.nR0 * t.nR1 - l_popc(t.L) + l_popc(t.G0) - l_popc(t.D0) + l_popc(t.Z0);
+        U = N0 + l_popc(t.NR1) + l_popc(t.NL1) + l_popc(t.Z1);
+        if (k == -2 && U > 0) k = (int)l_index(w, (uint32_t)U);
+        c.tri = false;
+        if (k < N0) {
+            mode = 1;
+            c.R = t.R0; c.base = t.nR1;
+            c.plus0 = t.G0 | t.Z0;                              // disjoint
+            c.plus1 = 0;
+            c.minus0 = t.L;
+            c.minus1 = isplus ? ((t.D0 >> hi) & t.R0) : t.D0;   // the root holding the later copy of a repeated net move
+            aZ = t.Z0; a1 = t.R1; a2 = t.G0; a3 = t.D0;
+        } else {
+            mode = 2;
+            k -= N0; U -= N0;                                   // (undone below)
+            m1 = hi; m2 = lo;
+            c.R = t.R1; c.base = 0;
+            c.plus0 = t.NR1 | t.Z1;                             // disjoint
+            c.plus1 = t.NL1;
+            c.minus0 = c.minus1 = 0;
+            aZ = t.Z1; a1 = 0; a2 = t.NR1; a3 = t.NL1;
+            if (k >= U) k = -1;
+            U += N0;
+        }
     }
-    LaneTwo t;
-    l_two(m, lo, hi, isplus, t);
-    const int N0 = t.nR0 * t.nR1 - l_popc(t.L) + l_popc(t.G0) - l_popc(t.D0) + l_popc(t.Z0);
-    const int U = N0 + l_popc(t.NR1) + l_popc(t.NL1) + l_popc(t.Z1);
-    if (k == -2 && U > 0) k = (int)l_index(w, (uint32_t)U);
-    if (k < 0 || k >= U) return U;
-    c.tri = false;
-    if (k < N0) {
-        c.R = t.R0; c.base = t.nR1;
-        c.plus0 = t.G0 | t.Z0;
-        c.plus1 = 0;
-        c.minus0 = t.L;
-        c.minus1 = isplus ? ((t.D0 >> hi) & t.R0) : t.D0;
-        const int x = l_find_root(c, k, isplus, j);
-        pl = l_play_from(x, lo, hi, l_two_newmask0(m, t, lo, hi, isplus, x), j, isplus);
-        return U;
+    if (k < 0 || (mode != 2 && k >= U)) return U;
+    int j;
+    const int x = l_find_root(c, k, isplus, j);
+    const uint32_t xb = 1u << x;
+    uint32_t nm;
+    if (aZ & xb) {
+        nm = L_SINGLE;
+    } else if (mode == 0) {
+        // doubles: an own-point child repeats an earlier root's pair unless it comes at or after x in root order; the
+        // run-on and the refill child are judged on their own
+        const uint32_t upto = (xb << 1) - 1u;
+        nm = a1 & (isplus ? upto : ~(upto >> 1));
+        nm &= ~(xb & m.single);
+        const uint32_t tb = x >= lo ? (xb >> lo) : 0u, lb = (xb << lo) & L_M24;
+        nm &= ~(tb | lb);
+        if (a2 & xb) nm |= tb;
+        nm |= a3 & lb;
+    } else if (mode == 1) {
+        nm = a1 & ~(xb & m.single);
+        if (a2 & xb) nm |= xb >> lo;
+        // F -> F-lo-hi produced twice: the later root's copy is the duplicate
+        if (isplus) nm &= ~(((xb << hi) & L_M24) & a3);
+        else if (a3 & xb) nm &= ~(xb >> lo);
+    } else {
+        nm = 0;
+        if (a2 & xb) nm |= xb >> hi;
+        if (a3 & xb) nm |= xb << lo;
     }
-    c.R = t.R1; c.base = 0;
-    c.plus0 = t.NR1 | t.Z1;
-    c.plus1 = t.NL1;
-    c.minus0 = c.minus1 = 0;
-    const int y = l_find_root(c, k - N0, isplus, j);
-    pl = l_play_from(y, hi, lo, l_two_newmask1(t, lo, hi, y), j, isplus);
+    pl = l_play_from(x, m1, m2, nm, j, isplus);
     return U;
 }
 

@@ -703,28 +703,6 @@ LANE_HD LanePlay l_pick_bar(const LaneBoard &g, const LaneMasks &m, int lo, int 
     return l_play_from(L_BAR, hi, lo, t.single1 ? L_SINGLE : t.N1, k - t.n0, isplus);
 }
 
-// count and selection in one go (same convention as l_closed_select)
-LANE_HD int l_bar_select(const LaneBoard &g, const LaneMasks &m, int lo, int hi, int k, uint32_t w, LanePlay &pl) {
-    LaneBarMasks t;
-    l_bar(g, m, lo, hi, t);
-    const bool isplus = g.player > 0;
-    const int U = t.n0 + t.n1;
-    pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
-    if (k == -2 && U > 0) k = (int)l_index(w, (uint32_t)U);
-    if (k < 0 || k >= U) return U;
-    if (g.bar_own >= 2) {
-        const bool both = t.fl && t.fh;
-        pl.x1 = L_BAR;
-        pl.t1 = t.fl ? 24 - lo : 24 - hi;
-        pl.n = both ? 2 : 1;
-        if (both) { pl.x2 = L_BAR; pl.t2 = 24 - hi; }
-        return U;
-    }
-    pl = k < t.n0 ? l_play_from(L_BAR, lo, hi, t.C0 ? t.C0 : L_SINGLE, k, isplus)
-                  : l_play_from(L_BAR, hi, lo, t.single1 ? L_SINGLE : t.N1, k - t.n0, isplus);
-    return U;
-}
-
 // ---------------- pure bear-off: every own checker in the home board, no opposing checker there ----------------
 // Six points, no hits, no blocks: the sources of die d are the own points >= d-1 (d-1 itself collects, the higher
 // ones move down), or, when all checkers sit below d-1, the highest own point (it collects with the bigger die).
@@ -887,7 +865,7 @@ LANE_HD LanePlay l_pick(const LaneBoard &g, const LaneGen &gen, const uint32_t *
     LaneMasks m;
     l_closed_applies(g, m, lo, hi);
     if (g.bar_own > 0) return l_pick_bar(g, m, lo, hi, k);
-    LaneCum c;
+        LaneCum c;
     int j;
     if (lo == hi) {
         LaneDbl t;
@@ -920,17 +898,36 @@ LANE_HD LanePlay l_pick(const LaneBoard &g, const LaneGen &gen, const uint32_t *
     return l_play_from(y, hi, lo, l_two_newmask1(t, lo, hi, y), j, isplus);
 }
 
-// Count and selection in one go for the closed form (the masks are built once): returns U; k >= 0 asks for the
-// k-th play, k == -1 for the count only, k == -2 for the play at index_of(w, U) -- a rollout's uniform choice.
-// pl.n == 0 on return when there is no play to report.
-LANE_HD int l_closed_select(const LaneBoard &g, const LaneMasks &m, int lo, int hi, int k, uint32_t w, LanePlay &pl) {
+// Count and selection in one go for contact play, bar entries included (the masks are built once): returns U;
+// k >= 0 asks for the k-th play, k == -1 for the count only, k == -2 for the play at index_of(w, U) -- a rollout's
+// uniform choice.  pl.n == 0 on return when there is no play to report.
+LANE_HD int l_contact_select(const LaneBoard &g, const LaneMasks &m, int lo, int hi, int k, uint32_t w, LanePlay &pl) {
     const bool isplus = g.player > 0;
     pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
     // The die orders differ only in WHICH masks drive the root walk and the new-children mask, so each branch just
     // picks its masks; the walk and the child pick then run once, for all lanes of the warp together.
-    LaneCum c;
+    int x = -1, m1 = lo, m2 = hi, j = 0, U;
+    uint32_t nm = 0;
+    if (g.bar_own > 0) {
+        LaneBarMasks t;
+        l_bar(g, m, lo, hi, t);
+        U = t.n0 + t.n1;
+        if (k == -2 && U > 0) k = (int)l_index(w, (uint32_t)U);
+        if (k >= 0 && k < U) {
+            x = L_BAR;
+            if (g.bar_own >= 2) {  // two entries (the second one is the bar's own bit), or the one that is possible
+                if (t.fl) nm = t.fh ? (1u << L_BAR) : L_SINGLE;
+                else { m1 = hi; m2 = lo; nm = L_SINGLE; }
+            } else if (k < t.n0) {
+                nm = t.C0 ? t.C0 : L_SINGLE; j = k;
+            } else {
+                m1 = hi; m2 = lo; nm = t.single1 ? L_SINGLE : t.N1; j = k - t.n0;
+            }
+        }
+    } else {
+        LaneCum c;
     uint32_t aZ, a1, a2, a3;  // per mode: roots that are plays on their own, and the three masks of the new-children rule
-    int mode, m1 = lo, m2 = hi, U;
+    int mode;
     if (lo == hi) {
         LaneDbl t;
         l_dbl(m, lo, isplus, t);
@@ -971,11 +968,9 @@ LANE_HD int l_closed_select(const LaneBoard &g, const LaneMasks &m, int lo, int 
             U += N0;
         }
     }
-    if (k < 0 || (mode != 2 && k >= U)) return U;
-    int j;
-    const int x = l_find_root(c, k, isplus, j);
+    if (k >= 0 && (mode == 2 || k < U)) {
+    x = l_find_root(c, k, isplus, j);
     const uint32_t xb = 1u << x;
-    uint32_t nm;
     if (aZ & xb) {
         nm = L_SINGLE;
     } else if (mode == 0) {
@@ -999,7 +994,9 @@ LANE_HD int l_closed_select(const LaneBoard &g, const LaneMasks &m, int lo, int 
         if (a2 & xb) nm |= xb >> hi;
         if (a3 & xb) nm |= xb << lo;
     }
-    pl = l_play_from(x, m1, m2, nm, j, isplus);
+    }
+    }
+    if (x >= 0) pl = l_play_from(x, m1, m2, nm, j, isplus);
     return U;
 }
 

@@ -195,11 +195,7 @@ lane_run_kernel(LaneJob job) {
                 const uint32_t U = e & 255u;
                 if (U > 0) pl = l_pb_unpack(__ldg(job.pb.plays + (e >> 8) + l_index(o[2], U)));
             } else {
-                if (g.bar_own > 0) {
-                    l_bar_select(g, m, lo, hi, -2, o[2], pl);
-                } else if (m.own1 != 0) {
-                    l_closed_select(g, m, lo, hi, -2, o[2], pl);
-                }
+                if (m.own1 != 0 || g.bar_own > 0) l_contact_select(g, m, lo, hi, -2, o[2], pl);
             }
         } else {
             LaneGen gen;

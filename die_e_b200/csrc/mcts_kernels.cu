@@ -72,11 +72,7 @@ __device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal
         int U = 0;
         lane::LanePlay pl;
         pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
-        if (b.bar_own > 0) {
-            U = lane::l_bar_select(b, m, lo, hi, k, w, pl);
-        } else if (m.own1 != 0) {
-            U = lane::l_closed_select(b, m, lo, hi, k, w, pl);
-        }
+        if (b.bar_own > 0 || m.own1 != 0) U = lane::l_contact_select(b, m, lo, hi, k, w, pl);
         if (pl.n > 0) seq = lane::l_play_to_seq(pl, g.player);
         return ((unsigned long long)(uint32_t)U << 32) | seq;
     }

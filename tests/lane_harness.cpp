@@ -76,18 +76,18 @@ static bool check_position(const orc_bg_state &s) {
             if (g.bar_own > 0) {
                 l_closed_applies(g, mm, lo, hi);
                 LanePlay pl;
-                if (l_bar_select(g, mm, lo, hi, -1, 0u, pl) != n) { fprintf(stderr, "bar_select count differs\n"); print_state(s); return false; }
+                if (l_contact_select(g, mm, lo, hi, -1, 0u, pl) != n) { fprintf(stderr, "bar_select count differs\n"); print_state(s); return false; }
                 for (int k = 0; k < n; ++k) {
-                    l_bar_select(g, mm, lo, hi, k, 0u, pl);
+                    l_contact_select(g, mm, lo, hi, k, 0u, pl);
                     uint32_t o;
                     memcpy(&o, &mv[k], 4);
                     if (l_play_to_seq(pl, g.player) != o) { fprintf(stderr, "bar_select play %d differs\n", k); print_state(s); return false; }
                 }
             } else if (l_closed_applies(g, mm, lo, hi)) {
                 LanePlay pl;
-                if (l_closed_select(g, mm, lo, hi, -1, 0u, pl) != n) { fprintf(stderr, "closed_select count differs\n"); print_state(s); return false; }
+                if (l_contact_select(g, mm, lo, hi, -1, 0u, pl) != n) { fprintf(stderr, "closed_select count differs\n"); print_state(s); return false; }
                 for (int k = 0; k < n; ++k) {
-                    l_closed_select(g, mm, lo, hi, k, 0u, pl);
+                    l_contact_select(g, mm, lo, hi, k, 0u, pl);
                     uint32_t o;
                     memcpy(&o, &mv[k], 4);
                     if (l_play_to_seq(pl, g.player) != o) { fprintf(stderr, "closed_select play %d differs\n", k); print_state(s); return false; }

@@ -295,8 +295,8 @@ def run_ours(args, rank, world):
             units += float(d_plies.sum().item())
         elif args.workload == "mcts":
             evs[i][1].synchronize()
-            if args.rollout == "ref_exact":
-                split_ms.append(ctx.search_timing())
+            if args.rollout == "ref_exact" and int(os.environ.get("DIEE_SEARCH_SLICES", "1")) <= 1:
+                split_ms.append(ctx.search_timing())  # (a sliced search runs its kernels concurrently: no per-kernel times)
             st = d_stats.cpu().numpy().view(ffi.SEARCH_STATS).reshape(-1)
             stats_acc = st if stats_acc is None else np.concatenate([stats_acc, st])
             units += units_per_step

@@ -144,7 +144,8 @@ lane_run_kernel(LaneJob job) {
         for (int p = PATH_CLOSED; p <= PATH_WALK; ++p) {
             const uint32_t waiting = __ballot_sync(0xFFFFFFFFu, need == p);
             if (waiting) {
-                const int score = __popc(waiting) + job.lag_weight * (int)__reduce_max_sync(0xFFFFFFFFu, need == p ? age : 0u);
+                int score = __popc(waiting);
+                if (job.lag_weight) score += job.lag_weight * (int)__reduce_max_sync(0xFFFFFFFFu, need == p ? age : 0u);
                 if (score > best_score) { best_score = score; best = p; }
             }
         }
@@ -154,7 +155,17 @@ lane_run_kernel(LaneJob job) {
         }
         if (best == PATH_DONE) break;
 #ifdef DIEE_LANE_STATS
-        { const uint32_t adv = __ballot_sync(0xFFFFFFFFu, need == best); if (lane == 0) { atomicAdd(&g_lane_stats[best], 1ull); atomicAdd(&g_lane_stats[8 + best], (unsigned long long)__popc(adv)); } }
+        {   // [p] steps on path p, [8+p] lanes advanced; [4] votes, [5..7],[12] lanes idle / waiting for closed / walk / store at the vote
+            const uint32_t adv = __ballot_sync(0xFFFFFFFFu, need == best);
+            const uint32_t n0 = __ballot_sync(0xFFFFFFFFu, need == PATH_DONE), n1 = __ballot_sync(0xFFFFFFFFu, need == PATH_CLOSED);
+            const uint32_t n2 = __ballot_sync(0xFFFFFFFFu, need == PATH_WALK), n3 = __ballot_sync(0xFFFFFFFFu, need == PATH_STORE);
+            if (lane == 0) {
+                atomicAdd(&g_lane_stats[best], 1ull); atomicAdd(&g_lane_stats[8 + best], (unsigned long long)__popc(adv));
+                atomicAdd(&g_lane_stats[4], 1ull); atomicAdd(&g_lane_stats[5], (unsigned long long)__popc(n0));
+                atomicAdd(&g_lane_stats[6], (unsigned long long)__popc(n1)); atomicAdd(&g_lane_stats[7], (unsigned long long)__popc(n2));
+                atomicAdd(&g_lane_stats[12], (unsigned long long)__popc(n3));
+            }
+        }
 #endif
         if (need != best) { ++age; continue; }
         age = 0;
@@ -181,6 +192,9 @@ lane_run_kernel(LaneJob job) {
         // ---- plies on path `best` (warp-uniform) for the lanes that wait for it: a lane keeps going while its next ply
         // needs the same path again (most do), up to job.reps plies per vote ----
         for (int rep = 0; rep < job.reps; ++rep) {
+#ifdef DIEE_LANE_STATS
+        { const uint32_t act = __activemask(); if (lane == (int)(__ffs(act) - 1)) { atomicAdd(&g_lane_stats[13], 1ull); atomicAdd(&g_lane_stats[14], (unsigned long long)__popc(act)); } }  // plies executed: warp-level, lanes
+#endif
         uint32_t o[4];
         l_philox((uint32_t)job.seed, (uint32_t)(job.seed >> 32), k, gid, stream, c3, o);
         LanePlay pl;
@@ -227,7 +241,7 @@ template <bool ROLLOUT>
 static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) {
     // tuning knobs, read once: waiting-time weight of the vote and resident CTAs (x 2 warps) per SM.  Measured on B200 with
     // 102,400 rollouts: 10 CTAs of 64 lanes per SM and weight 0 are best.
-    static int sms = 0, lag_weight = 0, blocks_per_sm = 10;
+    static int sms = 0, lag_weight = 0, blocks_per_sm = 10, force_bps = 0, force_store_min = 0;
     if (sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -235,6 +249,8 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
         if (sms <= 0) sms = 148;
         if (const char *e = getenv("DIEE_LANE_LAG")) lag_weight = atoi(e);
         if (const char *e = getenv("DIEE_LANE_BLOCKS_PER_SM")) blocks_per_sm = atoi(e) > 0 ? atoi(e) : 10;
+        if (const char *e = getenv("DIEE_LANE_FORCE_BPS")) force_bps = atoi(e);
+        if (const char *e = getenv("DIEE_LANE_STORE_MIN")) force_store_min = atoi(e);
     }
     job.lag_weight = lag_weight;
     job.reps = 8;  // measured: 1 / 2 / 4 / 8 / 16 / 64 plies per vote -> 1.50 / 1.48 / 1.46 / 1.44 / 1.50 / 1.69 ms (C3 rollouts)
@@ -242,10 +258,10 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
     // runs at full occupancy and lanes are refilled from the queue (measured at 819,200 rollouts: 77.7 M simulations/s
     // with 10 CTAs per SM, 82.6 M with 16)
     const bool refilled = job.n_items > (long long)sms * blocks_per_sm * LANE_CTA * 5 / 4;
-    const int bps = refilled ? 16 : blocks_per_sm;
+    const int bps = force_bps > 0 ? force_bps : (refilled ? 16 : blocks_per_sm);
     // results are written / items taken once this many lanes wait (a quarter of the warp; three quarters when the queue
     // keeps every lane busy anyway: 81.8 M -> 85.2 M simulations/s at 8,192 games)
-    job.store_min = refilled ? 24 : 8;
+    job.store_min = force_store_min > 0 ? force_store_min : (refilled ? 24 : 8);
     long long blocks = (job.n_items + LANE_CTA - 1) / LANE_CTA;
     if (blocks > (long long)sms * bps) blocks = (long long)sms * bps;
     cudaError_t e = cudaMemsetAsync(job.next_item, 0, sizeof(unsigned long long), st);

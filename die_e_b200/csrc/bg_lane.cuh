@@ -900,7 +900,7 @@ LANE_HD LanePlay l_pick(const LaneBoard &g, const LaneGen &gen, const uint32_t *
 
 // Count and selection in one go for contact play, bar entries included (the masks are built once): returns U;
 // k >= 0 asks for the k-th play, k == -1 for the count only, k == -2 for the play at index_of(w, U) -- a rollout's
-// uniform choice.  pl.n == 0 on return when there is no play to report.
+// uniform choice --, k <= -3 for the play -k-2 from the end (-3: the last one, which Node::expand pops first).  pl.n == 0 on return when there is no play to report.
 LANE_HD int l_contact_select(const LaneBoard &g, const LaneMasks &m, int lo, int hi, int k, uint32_t w, LanePlay &pl) {
     const bool isplus = g.player > 0;
     pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
@@ -913,6 +913,7 @@ LANE_HD int l_contact_select(const LaneBoard &g, const LaneMasks &m, int lo, int
         l_bar(g, m, lo, hi, t);
         U = t.n0 + t.n1;
         if (k == -2 && U > 0) k = (int)l_index(w, (uint32_t)U);
+        else if (k < -2) k = k + U + 2 >= 0 ? k + U + 2 : -1;
         if (k >= 0 && k < U) {
             x = L_BAR;
             if (g.bar_own >= 2) {  // two entries (the second one is the bar's own bit), or the one that is possible
@@ -933,6 +934,7 @@ LANE_HD int l_contact_select(const LaneBoard &g, const LaneMasks &m, int lo, int
         l_dbl(m, lo, isplus, t);
         U = t.nR * (t.nR + 1) / 2 - l_popc(t.R & (t.R >> lo)) - l_popc(t.Lx) + l_popc(t.HIT) + l_popc(t.NEWRUN | t.NEWLEAPF) + l_popc(t.Z);
         if (k == -2 && U > 0) k = (int)l_index(w, (uint32_t)U);
+        else if (k < -2) k = k + U + 2 >= 0 ? k + U + 2 : -1;
         mode = 0;
         c.R = t.R; c.base = t.nR; c.tri = true;
         c.plus0 = t.HIT | t.NEWRUN | t.Z;                       // disjoint: a root without children neither runs on nor hits
@@ -946,6 +948,7 @@ LANE_HD int l_contact_select(const LaneBoard &g, const LaneMasks &m, int lo, int
         const int N0 = t.nR0 * t.nR1 - l_popc(t.L) + l_popc(t.G0) - l_popc(t.D0) + l_popc(t.Z0);
         U = N0 + l_popc(t.NR1) + l_popc(t.NL1) + l_popc(t.Z1);
         if (k == -2 && U > 0) k = (int)l_index(w, (uint32_t)U);
+        else if (k < -2) k = k + U + 2 >= 0 ? k + U + 2 : -1;
         c.tri = false;
         if (k < N0) {
             mode = 1;

@@ -23,6 +23,7 @@ namespace diee {
 
 constexpr int MCTS_WARPS_PER_CTA = 4;
 constexpr int NO_WINNER = 2;
+constexpr int ROOT_PLAYS = 128;               // cached plays of the root (a backgammon position has at most ~130)
 constexpr uint32_t NM_UNKNOWN = 0xFFFFFFFFu;  // a node whose legal moves have not been counted yet
 
 // ---------------- game policies ----------------
@@ -53,7 +54,8 @@ __device__ __forceinline__ void bg_to_planes(const BgWarp &g, lane::LaneBoard &b
 // the list cooperatively.  One out-of-line copy (the tree kernel calls it three times per iteration and is
 // instruction-fetch bound); everything travels BY VALUE in registers: a reference to the caller's board
 // would force it into local memory and every call would start with a round trip through it.
-// k >= 0: the k-th play; k == -1: count only; k == -2: the play at index_of(w, U) (a rollout's uniform choice).
+// k >= 0: the k-th play; k == -1: count only; k == -2: the play at index_of(w, U) (a rollout's uniform choice);
+// k <= -3: the play -k-2 from the end (-3 = the last one).  k may differ from lane to lane.
 __device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal, WarpSlab *slab, int lane, int k, uint32_t w,
                                                             const uint32_t *pb_index, const uint16_t *pb_plays) {
     BgWarp g;
@@ -80,12 +82,14 @@ __device__ __noinline__ unsigned long long bg_count_and_kth(int v, uint32_t scal
         const uint32_t e = __ldg(pb_index + lane::l_pb_key(b));
         const int U = (int)(e & 255u);
         if (k == -2 && U > 0) k = (int)index_of(w, (uint32_t)U);
+        else if (k < -2) k = k + U + 2 >= 0 ? k + U + 2 : -1;
         if (k >= 0 && k < U) seq = lane::l_play_to_seq(lane::l_pb_unpack(__ldg(pb_plays + (e >> 8) + k)), g.player);
         return ((unsigned long long)(uint32_t)U << 32) | seq;
     }
     bool ovf = false;
     const int U = bg_movegen(g, *slab, lane, ovf);
     if (k == -2 && U > 0) k = (int)index_of(w, (uint32_t)U);
+        else if (k < -2) k = k + U + 2 >= 0 ? k + U + 2 : -1;
     if (k >= 0 && k < U) seq = slab->raw[k];
     __syncwarp();
     return ((unsigned long long)ovf << 63) | ((unsigned long long)(uint32_t)U << 32) | seq;
@@ -103,7 +107,7 @@ struct BgGame {
                               ((uint32_t)(g.second ? 1 : 0) << 25);
         const unsigned long long r = bg_count_and_kth(g.v, scal, &slab, lane, k, 0u, pb_index, pb_plays);
         if (r >> 63) ovf = true;
-        if (k >= 0) seq = (uint32_t)r;
+        if (k >= 0 || k < -2) seq = (uint32_t)r;
         return (int)((r >> 32) & 0x7FFFFFFFu);
     }
     // the play a rollout makes: uniform over the legal plays with the word w (SEQ_EMPTY when there is none)
@@ -153,6 +157,7 @@ struct TttGame {  // tictactoe/mod.rs; the whole state is warp-uniform
     __device__ __forceinline__ int movegen(WarpSlab &, int, bool &) const { return __popc(~(xm | om) & 0x1FFu); }
     __device__ __forceinline__ int count_and_kth(WarpSlab &slab, int, bool &, int k, uint32_t &seq) const {
         const int U = __popc(~(xm | om) & 0x1FFu);
+        if (k < -2) k += U + 2;
         if (k >= 0 && k < U) seq = move_at(slab, k);
         return U;
     }
@@ -227,10 +232,14 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                    int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out, bool slab_in_smem,
                    bool fill_counts) {
     __shared__ WarpSlab slabs[MCTS_WARPS_PER_CTA];
+    // the root's plays, generated once, 32 per call (every lane asks for a different one): Node::expand pops them one
+    // by one over the first iterations of the search, and each pop would otherwise regenerate the root's move set
+    __shared__ uint32_t root_plays_all[MCTS_WARPS_PER_CTA][ROOT_PLAYS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gidx = blockIdx.x * MCTS_WARPS_PER_CTA + wib;
     if (gidx >= n) return;
     WarpSlab &slab = slabs[wib];
+    uint32_t *root_plays = root_plays_all[wib];
     const int cap = (int)cfg.iterations + 1;
     const size_t base = (size_t)gidx * cap;
     // The game's node slab.  While the kernel runs it lives in SHARED memory when it fits (the search is a
@@ -288,8 +297,9 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
         if (game.winner() == NO_WINNER) {  // simple_mcts.rs:12-14
             // root = add_node(state)  (Node::new computes the legal moves eagerly, node.rs:50)
             game.store(st, lane);
-            uint32_t unused = SEQ_EMPTY;
-            int U = game.count_and_kth(slab, lane, ovf, -1, unused);
+            uint32_t play = SEQ_EMPTY;
+            int U = game.count_and_kth(slab, lane, ovf, lane, play);
+            root_plays[lane] = play;
             if (U == 0 && pass_child) U = 1;
             if (lane == 0) {
                 parent[0] = -1; visits[0] = 0.f; value[0] = 0.f; action[0] = SEQ_EMPTY; nm[0] = ((uint32_t)U << 16) | (uint32_t)U;
@@ -323,9 +333,24 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
         }
     }
 
+    if (n_nodes > 0 && status == DIEE_OK) {
+        const int rootU = (int)(nm[0] >> 16), todo = min((int)(nm[0] & 0xFFFFu), ROOT_PLAYS);  // only untried plays are read
+        if (todo > (it_begin == 0 ? 32 : 0)) {
+            game.load(st, lane);
+            for (int c0 = it_begin == 0 ? 32 : 0; c0 < todo; c0 += 32) {
+                uint32_t play = SEQ_EMPTY;
+                game.count_and_kth(slab, lane, ovf, c0 + lane < rootU ? c0 + lane : -1, play);
+                root_plays[c0 + lane] = play;
+            }
+        }
+        __syncwarp();
+    }
+
     if (n_nodes > 0) {
         if (status == DIEE_OK)
         for (uint32_t it = it_begin; it < it_end; ++it) {
+            int counted_node = -1;            // the node whose plays were counted during this descent ...
+            uint32_t counted_last = SEQ_EMPTY;  // ... and its last play, which expand pops first
             // ---- select_leaf_node :88-94 ----
             int cur = 0;
             uint32_t nmv;
@@ -339,8 +364,9 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                     // the search comes back to the node, so it is taken here, on first arrival -- most nodes of a
                     // 100-iteration search are never reached again and never need it (a pool dump fills them in).
                     game.load(st + cur, lane);
-                    uint32_t unused = SEQ_EMPTY;
-                    int Uc = game.count_and_kth(slab, lane, ovf, -1, unused);
+                    counted_last = SEQ_EMPTY;
+                    int Uc = game.count_and_kth(slab, lane, ovf, -3, counted_last);
+                    counted_node = cur;
                     if (Uc == 0 && pass_child) Uc = 1;
                     nmv = ((uint32_t)Uc << 16) | (uint32_t)Uc;
                     if (lane == 0) nm[cur] = nmv;
@@ -396,7 +422,9 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                 if (nunt == 0) { status = DIEE_ERR_NO_MOVES_PANIC; break; }  // node.rs:119-121 (Q6)
                 // ---- Node::expand node.rs:118-137: pop the LAST untried move ----
                 uint32_t seq = SEQ_EMPTY;  // stays EMPTY_MOVE for the pass child of a no-move node
-                game.count_and_kth(slab, lane, ovf, nunt - 1, seq);
+                if (cur == 0 && nunt <= ROOT_PLAYS) seq = root_plays[nunt - 1];
+                else if (cur == counted_node) seq = counted_last;
+                else game.count_and_kth(slab, lane, ovf, nunt - 1, seq);
                 const int child = n_nodes;
                 uint32_t blk[4];
                 philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)child, gid, DIEE_STREAM_EXPAND, epoch, blk);
@@ -508,6 +536,9 @@ __global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32)
 rollout_kernel(int n_games, diee_mcts_cfg cfg, uint64_t seed, uint32_t first_game_id, uint32_t epoch, Pool pool,
                const int8_t *__restrict__ players, int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out) {
     __shared__ WarpSlab slabs[MCTS_WARPS_PER_CTA];
+    // the root's plays, generated once, 32 per call (every lane asks for a different one): Node::expand pops them one
+    // by one over the first iterations of the search, and each pop would otherwise regenerate the root's move set
+    __shared__ uint32_t root_plays_all[MCTS_WARPS_PER_CTA][ROOT_PLAYS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long pair = (long long)blockIdx.x * MCTS_WARPS_PER_CTA + wib;
     if (pair >= (long long)n_games * cfg.iterations) return;

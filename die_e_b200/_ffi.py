@@ -106,8 +106,26 @@ def dirichlet(seed, epoch, alpha, n=ACTION_SPACE):
 COMM_ID_BYTES = 128
 
 
+def _prefer_bundled_nccl():
+    """points DIEE_NCCL_LIB at the NCCL wheel next to torch (if there is one and nothing was chosen): whichever
+    libnccl.so.2 is mapped first is the one a later `import torch` gets, and the system's may be older than torch needs"""
+    if os.environ.get("DIEE_NCCL_LIB"):
+        return
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["DIEE_NCCL_LIB"] = cand
+            return
+
+
 def comm_unique_id():
     """the NCCL rendezvous id: rank 0 draws it and ships it to the other ranks (diee_comm_init)"""
+    _prefer_bundled_nccl()
     out = np.zeros(COMM_ID_BYTES, dtype=np.uint8)
     rc = lib().diee_comm_unique_id(_p(out))
     if rc != OK:
@@ -282,6 +300,7 @@ class Context:
 
     # ---- multi-GPU exchange over NCCL (one rank per context) ----
     def comm_init(self, nranks, rank, unique_id):
+        _prefer_bundled_nccl()
         uid = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
         assert len(uid) == COMM_ID_BYTES
         self._chk(lib().diee_comm_init(self._h, C.c_int32(nranks), C.c_int32(rank), _p(uid)))

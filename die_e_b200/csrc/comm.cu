@@ -4,10 +4,13 @@
 // tasks, versus.rs:303-316), so nothing else on the path communicates.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2), not at link time: the library must load on a box that has no
-// NCCL at all, and inside a process where torch has already loaded its own copy.
+// NCCL at all, and inside a process where torch has already loaded its own copy (that copy is reused; a process
+// that will import torch LATER should point DIEE_NCCL_LIB at torch's bundled libnccl.so.2 -- the Python host does
+// -- because the dynamic loader hands torch whichever libnccl.so.2 is already mapped).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -35,8 +38,12 @@ Nccl *nccl() {
     static bool tried = false;
     if (!tried) {
         tried = true;
-        n.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!n.h) n.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        // the copy the process already has (torch's bundled one, normally) wins; then DIEE_NCCL_LIB; then the
+        // system's.  Never RTLD_GLOBAL: symbols of an NCCL loaded here must not leak into libraries loaded later.
+        n.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL);
+        if (!n.h) { const char *path = getenv("DIEE_NCCL_LIB"); if (path && *path) n.h = dlopen(path, RTLD_NOW | RTLD_LOCAL); }
+        if (!n.h) n.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!n.h) n.h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
         if (n.h) {
             n.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(n.h, "ncclGetUniqueId");
             n.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(n.h, "ncclCommInitRank");
@@ -88,7 +95,7 @@ int32_t diee_comm_init(diee_ctx *ctx, int32_t nranks, int32_t rank, const uint8_
 
 int32_t diee_comm_destroy(diee_ctx *ctx) {
     if (!ctx) return DIEE_ERR_INVALID;
-    Nccl *N = nccl();
+    Nccl *N = ctx->comm ? nccl() : nullptr;  // a context that never joined a communicator must not load NCCL on its way out
     if (ctx->comm && N) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);

@@ -23,6 +23,7 @@ namespace diee {
 
 constexpr int MCTS_WARPS_PER_CTA = 4;
 constexpr int NO_WINNER = 2;
+constexpr int NODE_PLAYS = 4;                 // plays kept per node from the call that counted them (the ones expand pops first)
 constexpr int ROOT_PLAYS = 128;               // cached plays of the root (a backgammon position has at most ~130)
 constexpr uint32_t NM_UNKNOWN = 0xFFFFFFFFu;  // a node whose legal moves have not been counted yet
 
@@ -261,8 +262,11 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     // value / visits of every node, refreshed where the two change (back-propagation): select_ucb then needs one
     // IEEE division per child instead of two (same operands, same rounding, so the same bits)
     float *qv = nullptr;
+    // the last NODE_PLAYS plays of every node counted by this launch: a node of a 100-iteration search is expanded
+    // a handful of times, and each time would otherwise regenerate its move set to pop one play
+    uint32_t *nplays = nullptr;
     if (slab_in_smem) {
-        unsigned char *mine = slab_mem + (size_t)wib * cap * (sizeof(typename G::State) + 24);
+        unsigned char *mine = slab_mem + (size_t)wib * cap * (sizeof(typename G::State) + 24 + 4 * NODE_PLAYS);
         st = reinterpret_cast<typename G::State *>(mine);
         parent = reinterpret_cast<int32_t *>(mine + (size_t)cap * sizeof(typename G::State));
         visits = reinterpret_cast<float *>(parent + cap);
@@ -270,6 +274,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
         nm = reinterpret_cast<uint32_t *>(value + cap);
         crange = nm + cap;
         qv = reinterpret_cast<float *>(crange + cap);
+        nplays = reinterpret_cast<uint32_t *>(qv + cap);
     }
     uint32_t *action = pool.action + base;
     int32_t *sim_node = pool.sim_node + (size_t)gidx * cfg.iterations;
@@ -333,6 +338,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
         }
     }
 
+    const int first_cached = it_begin == 0 ? 1 : n_nodes;  // nodes created from here on are counted (and cached) by this launch
     if (n_nodes > 0 && status == DIEE_OK) {
         const int rootU = (int)(nm[0] >> 16), todo = min((int)(nm[0] & 0xFFFFu), ROOT_PLAYS);  // only untried plays are read
         if (todo > (it_begin == 0 ? 32 : 0)) {
@@ -364,8 +370,10 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                     // the search comes back to the node, so it is taken here, on first arrival -- most nodes of a
                     // 100-iteration search are never reached again and never need it (a pool dump fills them in).
                     game.load(st + cur, lane);
-                    counted_last = SEQ_EMPTY;
-                    int Uc = game.count_and_kth(slab, lane, ovf, -3, counted_last);
+                    uint32_t play = SEQ_EMPTY;  // lane j asks for the play j from the end
+                    int Uc = game.count_and_kth(slab, lane, ovf, lane < NODE_PLAYS ? -3 - lane : -1, play);
+                    if (nplays && lane < NODE_PLAYS) nplays[cur * NODE_PLAYS + lane] = play;
+                    counted_last = __shfl_sync(FULL, play, 0);
                     counted_node = cur;
                     if (Uc == 0 && pass_child) Uc = 1;
                     nmv = ((uint32_t)Uc << 16) | (uint32_t)Uc;
@@ -424,6 +432,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                 uint32_t seq = SEQ_EMPTY;  // stays EMPTY_MOVE for the pass child of a no-move node
                 if (cur == 0 && nunt <= ROOT_PLAYS) seq = root_plays[nunt - 1];
                 else if (cur == counted_node) seq = counted_last;
+                else if (nplays && cur >= first_cached && nmoves - nunt < NODE_PLAYS) seq = nplays[cur * NODE_PLAYS + (nmoves - nunt)];
                 else game.count_and_kth(slab, lane, ovf, nunt - 1, seq);
                 const int child = n_nodes;
                 uint32_t blk[4];
@@ -572,7 +581,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
     const typename G::State *r = static_cast<const typename G::State *>(roots);
     cudaError_t e;
     // node slabs of the CTA's games in shared memory when they fit
-    size_t slab_bytes = (size_t)MCTS_WARPS_PER_CTA * (cfg.iterations + 1) * (sizeof(typename G::State) + 24);
+    size_t slab_bytes = (size_t)MCTS_WARPS_PER_CTA * (cfg.iterations + 1) * (sizeof(typename G::State) + 24 + 4 * NODE_PLAYS);
     const bool in_smem = slab_bytes <= 160 * 1024;
     if (!in_smem) slab_bytes = 0;
     if (in_smem) {

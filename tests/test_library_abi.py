@@ -69,3 +69,15 @@ def test_arena_surface_matches_the_reference_cli():
     r = PlayResult(Agent.Mcts, Agent.Random, 3, 1, 5, None, None)
     assert r.draws == 1 and abs(r.winrate - 0.6) < 1e-12 and "Wins Player 1: 3" in str(r)
     assert Player(Agent.Random).model is None
+
+
+def test_nccl_loaded_through_the_library_does_not_break_a_later_torch_import():
+    """the dynamic loader hands torch whichever libnccl.so.2 is already mapped: the host side must map torch's own
+    (and a context that never joined a communicator must not map any on its way out)"""
+    import subprocess
+    import sys
+    code = ("from die_e_b200 import _ffi\n"
+            "try:\n    _ffi.comm_unique_id()\nexcept _ffi.DieeError:\n    pass\n"
+            "import torch\nprint('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]

@@ -407,9 +407,9 @@ def run_ours(args, rank, world):
             extra = {}
         traffic = None
         if args.workload == "mcts" and dominant and G == 1024 and args.iterations == 100 and args.round_limit == 400:
-            traffic = ncu_traffic("r01_lane_run_rollouts_v7_ncu_full_summary.txt")
+            traffic = ncu_traffic("r01_lane_run_rollouts_v8_ncu_full_summary.txt")
         if args.workload == "playout" and G == 65536 and args.round_limit == 400:
-            traffic = ncu_traffic("r01_lane_run_playouts_v7_ncu_full_summary.txt")
+            traffic = ncu_traffic("r01_lane_run_playouts_v8_ncu_full_summary.txt")
         avg_launch_ms = float(np.mean(kern_ms))
         achieved = alg_bytes / ((dominant[1] if dominant else avg_launch_ms) / 1e3) / 1e9
         roof = None

@@ -29,13 +29,13 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// activations: bf16 NHWC [n][4][6][C]; box = [64 ch][6][4][16 boards], 128B swizzle, OOB -> zero
-static bool make_act_map(CUtensorMap *m, const void *base, int n_boards, int C) {
+// activations: bf16 NHWC [n][4][6][C]; box = [64 ch][6][4][nb boards], 128B swizzle, OOB -> zero
+static bool make_act_map(CUtensorMap *m, const void *base, int n_boards, int C, int nb = 16) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
     cuuint64_t dims[4] = {(cuuint64_t)C, 6, 4, (cuuint64_t)n_boards};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 12, (cuuint64_t)C * 48};
-    cuuint32_t box[4] = {64, 6, 4, 16};
+    cuuint32_t box[4] = {64, 6, 4, (cuuint32_t)nb};
     cuuint32_t es[4] = {1, 1, 1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -72,6 +72,7 @@ struct ConvLayer {
     int c_in = 0, c_out = 0;
     float *bias = nullptr;       // [c_out_pad]
     CUtensorMap wmap, wmap3;
+    CUtensorMap wmap_n64, wmap_n32;  // the same weights through 64- and 32-row boxes: small batches run smaller CTA tiles
     int c_out_pad = 0, K = 0, ntaps = 9, chunks = 4, bn = 128;
 };
 
@@ -157,6 +158,8 @@ static int32_t build_conv(diee_ctx *ctx, ConvLayer &L, const float *w, const flo
     CU(cudaMemcpy(L.w, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (!make_w_map(&L.wmap, L.w, c_out_pad, K, bn)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed");
+    if (!make_w_map(&L.wmap_n32, L.w, c_out_pad, K, 32) || !make_w_map(&L.wmap_n64, L.w, c_out_pad, K, c_out_pad >= 64 ? 64 : 32))
+        return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed");
     int32_t rc = upload_split(ctx, L, wf);
     if (rc != DIEE_OK) return rc;
     if (!make_w_map(&L.wmap3, L.w3, c_out_pad, 3 * K, bn)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (split weights) failed");
@@ -227,6 +230,8 @@ int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *t,
         CU(cudaMemcpy(L.w, wp.data(), wp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(L.bias, bpv.data(), bpv.size() * sizeof(float), cudaMemcpyHostToDevice));
         if (!make_w_map(&L.wmap, L.w, F, K, 128)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed");
+        if (!make_w_map(&L.wmap_n32, L.w, F, K, 32) || !make_w_map(&L.wmap_n64, L.w, F, K, 64))
+            return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed");
         rc = upload_split(ctx, L, wf0);
         if (rc != DIEE_OK) return rc;
         rc = upload_f32(ctx, L, wf0, 6, F);
@@ -369,26 +374,46 @@ int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *
     RESERVE(net->actC, rows * F * 2);
     RESERVE(net->pfeat, rows * 32 * 2);
     RESERVE(net->vfeat, rows * 16 * 4);
-    CUtensorMap m_in, mA, mB, mC;
-    if (!make_act_map(&m_in, net->in0.p, n, 64) || !make_act_map(&mA, net->actA.p, n, F) || !make_act_map(&mB, net->actB.p, n, F) ||
-        !make_act_map(&mC, net->actC.p, n, F))
+    // The CTA tile of the tower: nb boards x bn output channels.  A CTA's time is set by the bytes it pulls through its
+    // own SM's L2 port (nb * 3 KB + bn * 128 B per K-block), so the smallest tile that still fits the whole layer in one
+    // wave of CTAs wins: 16 x 128 at 1,024 boards, 8 x 64 at 256, 4 x 32 at 64 -- the long tail of a self-play batch.
+    const char *force_tile = getenv("DIEE_CONV_TILE");  // "nb,bn" (experiments, tests)
+    int nb = 16, bn = 128;
+    {
+        static int sms = 0;
+        if (sms == 0) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device); if (sms <= 0) sms = 148; }
+        const int cand[5][2] = {{4, 32}, {8, 32}, {8, 64}, {8, 128}, {16, 128}};  // ascending bytes per K-block
+        for (int c = 0; c < 5; ++c) {
+            const int cnb = cand[c][0], cbn = cand[c][1];
+            if (F % cbn != 0) continue;
+            if ((long long)((n + cnb - 1) / cnb) * (F / cbn) <= sms) { nb = cnb; bn = cbn; break; }
+        }
+        if (force_tile) { int a = 0, b = 0; if (sscanf(force_tile, "%d,%d", &a, &b) == 2 && F % b == 0) { nb = a; bn = b; } }
+    }
+    CUtensorMap m_in, mA, mB, mC, m_head;
+    if (!make_act_map(&m_in, net->in0.p, n, 64, nb) || !make_act_map(&mA, net->actA.p, n, F, nb) || !make_act_map(&mB, net->actB.p, n, F, nb) ||
+        !make_act_map(&mC, net->actC.p, n, F, nb))
         return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (activations) failed");
     cudaStream_t st = ctx->stream;
     CU(launch_encode_im2col(st, states, n, net->in0.p));
+    auto wmap_of = [bn](const ConvLayer &L) -> const CUtensorMap & { return bn == 128 ? L.wmap : bn == 64 ? L.wmap_n64 : L.wmap_n32; };
     const ConvLayer &L0 = net->convs[0];
-    CU(launch_conv(st, L0.bn, m_in, L0.wmap, n, L0.ntaps, L0.chunks, L0.bias, nullptr, net->actA.p, 0, F, 1));
+    CU(launch_conv_tile(st, bn, nb, m_in, wmap_of(L0), n, L0.ntaps, L0.chunks, L0.bias, nullptr, net->actA.p, 0, F, 1));
     ctx->launches += 2;
     // x lives in A; y = relu(bn1(conv1(x))) -> B; x' = relu(bn2(conv2(y)) + x) -> C; rotate
     void *bx = net->actA.p, *by = net->actB.p, *bz = net->actC.p;
     CUtensorMap *mx = &mA, *my = &mB, *mz = &mC;
     for (int b = 0; b < net->blocks; ++b) {
         const ConvLayer &c1 = net->convs[1 + 2 * b], &c2 = net->convs[2 + 2 * b];
-        CU(launch_conv(st, c1.bn, *mx, c1.wmap, n, 9, c1.chunks, c1.bias, nullptr, by, 0, F, 1));
-        CU(launch_conv(st, c2.bn, *my, c2.wmap, n, 9, c2.chunks, c2.bias, bx, bz, 0, F, 1));
+        CU(launch_conv_tile(st, bn, nb, *mx, wmap_of(c1), n, 9, c1.chunks, c1.bias, nullptr, by, 0, F, 1));
+        CU(launch_conv_tile(st, bn, nb, *my, wmap_of(c2), n, 9, c2.chunks, c2.bias, bx, bz, 0, F, 1));
         ctx->launches += 2;
         void *tp = bx; bx = bz; bz = tp;
         CUtensorMap *tm = mx; mx = mz; mz = tm;
     }
+    // the two head convolutions keep 16-board tiles (their output tiles are 32 / 16 channels wide already)
+    if (!make_act_map(&m_head, bx, n, F, 16)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (activations) failed");
+    mx = &m_head;
     CU(launch_conv(st, net->pconv.bn, *mx, net->pconv.wmap, n, 9, net->pconv.chunks, net->pconv.bias, nullptr, net->pfeat.p, 0, 32, 1));
     CU(launch_conv(st, net->vconv.bn, *mx, net->vconv.wmap, n, 9, net->vconv.chunks, net->vconv.bias, nullptr, net->vfeat.p, 1, 16, 1));
     CUtensorMap m_pf;

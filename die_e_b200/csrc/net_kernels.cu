@@ -130,20 +130,27 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 }
 
 // ---------------------------------------------------------------- the convolution kernel
-constexpr int CONV_NB = 16;                      // boards per CTA tile
-constexpr int CONV_ROWS = CONV_NB * 24;          // 384 positions = 3 MMA M-tiles
-constexpr int CONV_MT = CONV_ROWS / 128;
-constexpr int CONV_A_BYTES = CONV_ROWS * 128;    // one K-block (64 bf16 channels) of the activation tile
 constexpr int CONV_THREADS = 192;
 
-template <int BN>
+// A CTA computes NB boards x BN output channels.  NB = 16 (384 positions = 3 MMA M-tiles) x BN = 128 is the shape for
+// big batches; smaller shapes exist because a CTA's time is set by the bytes it has to pull through ITS SM's L2 port
+// (~38 B/cycle measured: a layer takes the same 32 us at 16 boards as at 1,024), so a small batch is spread over as
+// many CTAs as there are SMs, each with a smaller tile (net.cu picks the shape per launch).
+template <int BN, int NB>
 struct ConvCfg {
+    static constexpr int ROWS = NB * 24;
+    static constexpr int MT = (ROWS + 127) / 128;          // the last M-tile may be partly padding (rows >= ROWS: never stored)
+    static constexpr int A_BYTES = ROWS * 128;             // one K-block (64 bf16 channels) of the activation tile
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = CONV_A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN >= 128) ? 3 : 4;
-    static constexpr int TMEM_COLS = (CONV_MT * BN <= 32) ? 32 : (CONV_MT * BN <= 64) ? 64 : (CONV_MT * BN <= 128) ? 128
-                                     : (CONV_MT * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES_RAW = (216 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SLACK = (ROWS % 128) ? 16 * 1024 : 0;  // a padded M-tile reads past its stage: keep that inside the allocation
+    static constexpr int TMEM_COLS = (MT * BN <= 32) ? 32 : (MT * BN <= 64) ? 64 : (MT * BN <= 128) ? 128 : (MT * BN <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/ + SLACK;
+    static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned (128B swizzle atoms)");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(MT * BN <= 512, "TMEM budget");
 };
 
 // out_mode: 0 = bf16 NHWC [rows][c_out_total], 1 = fp32 NHWC, 2 = three bf16 planes [rows][3][c_out_total]
@@ -154,13 +161,13 @@ struct ConvCfg {
 // accumulator -- so the K loop simply runs over (pair, tap, chunk): `pairs` packs up to eight (i, j) as 2+2
 // bits each, plane i of the activations starts a_plane channels further on, plane j of the weights b_plane
 // K-columns further on.  Plain bf16 is the one pair (0, 0).
-template <int BN>
+template <int BN, int NB>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int n_boards,
                   int ntaps, int chunks, const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual,
                   void *__restrict__ out, int out_mode, int c_out_total, int relu, int npairs, uint32_t pairs, int a_plane,
                   int b_plane) {
-    using Cfg = ConvCfg<BN>;
+    using Cfg = ConvCfg<BN, NB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *tail = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -171,7 +178,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     float *bias_smem = reinterpret_cast<float *>(tail + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int board0 = blockIdx.x * CONV_NB;
+    const int board0 = blockIdx.x * NB;
     const int n0 = blockIdx.y * BN;
     const int per_pair = ntaps * chunks;
     const int num_kb = per_pair * npairs;
@@ -198,7 +205,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 uint8_t *sa = smem + s * Cfg::STAGE_BYTES;
-                uint8_t *sb = sa + CONV_A_BYTES;
+                uint8_t *sb = sa + Cfg::A_BYTES;
                 mbar_expect_tx(&full_bar[s], (uint32_t)Cfg::STAGE_BYTES);
                 const int pr = kb / per_pair, kin = kb - pr * per_pair;
                 const int pi = (int)((pairs >> (4 * pr)) & 3u), pj = (int)((pairs >> (4 * pr + 2)) & 3u);
@@ -218,9 +225,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint32_t sb = sa + CONV_A_BYTES;
+                const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
-                for (int mt = 0; mt < CONV_MT; ++mt) {
+                for (int mt = 0; mt < Cfg::MT; ++mt) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzled row
                         const uint64_t ad = umma_desc_sw128(sa + mt * (128 * 128) + kk * 32);
@@ -240,9 +247,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const int q = warp & 3;  // TMEM lane quadrant this warp may read
         const long long total_rows = (long long)n_boards * 24;
 #pragma unroll 1
-        for (int mt = 0; mt < CONV_MT; ++mt) {
-            const long long grow = (long long)board0 * 24 + mt * 128 + q * 32 + lane;
-            const bool valid = grow < total_rows;
+        for (int mt = 0; mt < Cfg::MT; ++mt) {
+            const int trow = mt * 128 + q * 32 + lane;
+            const long long grow = (long long)board0 * 24 + trow;
+            const bool valid = trow < Cfg::ROWS && grow < total_rows;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
@@ -579,33 +587,48 @@ fc_f32_kernel(const float *__restrict__ feat, const float *__restrict__ wT, cons
 }
 
 // ---------------------------------------------------------------- launchers
-template <int BN>
+template <int BN, int NB>
 static cudaError_t launch_conv_bn(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,
                                   int chunks, const float *bias, const __nv_bfloat16 *residual, void *out, int out_mode,
                                   int c_out_total, int relu, int npairs, uint32_t pairs, int a_plane, int b_plane) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NB>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid((n_boards + CONV_NB - 1) / CONV_NB, c_out_total / BN);
-    conv3x3_tc_kernel<BN><<<grid, CONV_THREADS, ConvCfg<BN>::SMEM_BYTES, st>>>(ta, tb, n_boards, ntaps, chunks, bias, residual, out,
-                                                                              out_mode, c_out_total, relu, npairs, pairs, a_plane,
-                                                                              b_plane);
+    dim3 grid((n_boards + NB - 1) / NB, c_out_total / BN);
+    conv3x3_tc_kernel<BN, NB><<<grid, CONV_THREADS, ConvCfg<BN, NB>::SMEM_BYTES, st>>>(ta, tb, n_boards, ntaps, chunks, bias, residual, out,
+                                                                                      out_mode, c_out_total, relu, npairs, pairs, a_plane,
+                                                                                      b_plane);
     return cudaGetLastError();
+}
+
+// `ta` must have been encoded with a box of nb boards, `tb` with a box of bn rows
+cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,
+                             int chunks, const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
+                             int npairs, uint32_t pairs, int a_plane, int b_plane) {
+    const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(residual);
+#define DIEE_CONV_CASE(BN_, NB_)                                                                                                        \
+    if (bn == BN_ && nb == NB_)                                                                                                         \
+        return launch_conv_bn<BN_, NB_>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu, npairs, pairs, \
+                                        a_plane, b_plane);
+    DIEE_CONV_CASE(128, 16)
+    DIEE_CONV_CASE(32, 16)
+    DIEE_CONV_CASE(16, 16)
+    DIEE_CONV_CASE(128, 8)
+    DIEE_CONV_CASE(64, 8)
+    DIEE_CONV_CASE(32, 8)
+    DIEE_CONV_CASE(32, 4)
+#undef DIEE_CONV_CASE
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_conv(cudaStream_t st, int bn, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps, int chunks,
                         const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
                         int npairs, uint32_t pairs, int a_plane, int b_plane) {
-    const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(residual);
-    switch (bn) {
-        case 128: return launch_conv_bn<128>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu, npairs, pairs, a_plane, b_plane);
-        case 32: return launch_conv_bn<32>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu, npairs, pairs, a_plane, b_plane);
-        case 16: return launch_conv_bn<16>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu, npairs, pairs, a_plane, b_plane);
-        default: return cudaErrorInvalidValue;
-    }
+    return launch_conv_tile(st, bn, 16, ta, tb, n_boards, ntaps, chunks, bias, residual, out, out_mode, c_out_total, relu, npairs, pairs,
+                            a_plane, b_plane);
 }
 
 cudaError_t launch_encode_im2col(cudaStream_t st, const diee_bg_state *states, int n, void *out) {

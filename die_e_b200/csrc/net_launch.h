@@ -7,6 +7,10 @@
 #include "../../include/diee.h"
 
 namespace diee {
+// one convolution with an explicit CTA tile: nb boards x bn output channels (ta encoded with a box of nb boards, tb with bn rows)
+cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,
+                             int chunks, const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
+                             int npairs = 1, uint32_t pairs = 0, int a_plane = 0, int b_plane = 0);
 cudaError_t launch_conv(cudaStream_t st, int bn, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps, int chunks,
                         const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
                         int npairs = 1, uint32_t pairs = 0, int a_plane = 0, int b_plane = 0);

@@ -116,6 +116,26 @@ def test_batch_edges_and_determinism(ctx, oracle):
     net.close()
 
 
+def test_every_cta_tile_shape_gives_the_same_bits(ctx, oracle, monkeypatch):
+    """the tower picks its CTA tile (boards x output channels) from the batch size; every shape accumulates each
+    output element over the same K order, so all of them must agree bit for bit (incl. the padded last M-tile of the
+    8- and 4-board tiles and a batch that does not fill its last tile)"""
+    from die_e_b200 import _ffi, nnet
+    tens = nnet.synthetic_tensors(seed=11, filters=256, blocks=2, bn_stats="random")
+    net = _ffi.Net(ctx, tens)
+    states, _ = _inputs(oracle, 43, seed=5)
+    monkeypatch.setenv("DIEE_CONV_TILE", "16,128")
+    p_ref, v_ref = net.forward(states)
+    for tile in ("8,128", "8,64", "8,32", "4,32"):
+        monkeypatch.setenv("DIEE_CONV_TILE", tile)
+        p, v = net.forward(states)
+        assert (p == p_ref).all() and (v == v_ref).all(), tile
+    monkeypatch.delenv("DIEE_CONV_TILE")
+    p, v = net.forward(states)   # the automatic choice
+    assert (p == p_ref).all() and (v == v_ref).all()
+    net.close()
+
+
 def test_resnet_host_object(ctx, oracle, tmp_path):
     from die_e_b200 import nnet
     net = nnet.ResNet.new(seed=5, filters=128, blocks=1, bn_stats="random", ctx=ctx)

@@ -11,7 +11,7 @@ torch.cuda.set_stream(stream)
 ctx.set_stream(stream.cuda_stream)
 tens = nnet.synthetic_tensors(seed=1, filters=256, blocks=19)
 net = _ffi.Net(ctx, tens)
-for n in (1024, 4096, 16384):
+for n in [int(a) for a in sys.argv[1:]] or (1024, 4096, 16384):
     s = np.zeros(n, dtype=_ffi.BG_STATE)
     s["pts"][:] = [2, 0, 0, 0, 0, -5, 0, -3, 0, 0, 0, 5, -5, 0, 0, 0, 3, 0, 5, 0, 0, 0, 0, -2]
     s["player"] = -1

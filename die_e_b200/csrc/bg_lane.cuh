@@ -316,7 +316,10 @@ LANE_HD bool l_test_and_set(uint32_t &m, uint32_t bit) {  // true iff the bit wa
 // Counts the distinct plays of `g` root by root and parks, per root in reference order, the mask of its
 // NEW children in scr[slot * stride].  scr needs L_SCRATCH words (lane-strided).  Exact in every regime;
 // used where the closed form below does not apply (checkers on the bar, bearing off).
-LANE_HD void l_movegen_walk(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stride) {
+// BO_ONLY: the caller guarantees the bear-off regime (bar empty, at most one lone checker outside the home board) --
+// the lane kernels' walk path, which only ever sees such positions; the other cases then compile away.
+template <bool BO_ONLY>
+LANE_HD void l_movegen_walk_t(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stride) {
     const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;  // :406-409
     const bool dbl = hi == lo;
     const bool isplus = g.player > 0;
@@ -325,7 +328,7 @@ LANE_HD void l_movegen_walk(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int
     const uint32_t own_single = g.own[0] & ~o123;
     const uint32_t oppblot = g.opp[0] & ~p123;
     const uint32_t freem = ~p123 & L_M24;
-    const int bar = g.bar_own;
+    const int bar = BO_ONLY ? 0 : g.bar_own;
     gen.isplus = isplus;
     gen.closed = false;
     gen.U = 0;
@@ -337,7 +340,7 @@ LANE_HD void l_movegen_walk(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int
 
     // the side can bear off within this play: bar empty and at most one checker outside the home board
     const uint32_t outside = own1 & ~0x3Fu;
-    const bool bo_regime = bar == 0 && (outside & (outside - 1u)) == 0 && (outside & ~own_single) == 0;
+    const bool bo_regime = BO_ONLY || (bar == 0 && (outside & (outside - 1u)) == 0 && (outside & ~own_single) == 0);
     uint64_t H = 0;
     const bool opp_home = ((g.opp[0] | p123) & 0x3Fu) != 0;  // opposing checkers inside the mover's home board
     if (bo_regime && opp_home) {
@@ -370,7 +373,7 @@ LANE_HD void l_movegen_walk(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int
         while (r) {
             const int x = l_take(r, isplus);
             r &= ~(1u << x);
-            const bool frombar = x == L_BAR;
+            const bool frombar = !BO_ONLY && x == L_BAR;
             const int t1 = l_to(x, m1);
             // the board after the first sub-move, as masks
             uint32_t own1p = own1;
@@ -445,6 +448,7 @@ LANE_HD void l_movegen_walk(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int
     }
     gen.U = U;
 }
+LANE_HD void l_movegen_walk(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stride) { l_movegen_walk_t<false>(g, gen, scr, stride); }
 
 // the k-th distinct play (0 <= k < gen.U) in reference order, from the masks l_movegen_walk parked
 LANE_HD LanePlay l_pick_walk(const LaneGen &gen, const uint32_t *scr, int stride, int k) {

@@ -213,7 +213,7 @@ lane_run_kernel(LaneJob job) {
             }
         } else {
             LaneGen gen;
-            l_movegen_walk(g, gen, scr, LANE_CTA);
+            l_movegen_walk_t<true>(g, gen, scr, LANE_CTA);
             if (gen.U > 0) pl = l_pick_walk(gen, scr, LANE_CTA, (int)l_index(o[2], (uint32_t)gen.U));
         }
         l_step(g, pl, l_die(o[0]), l_die(o[1]));

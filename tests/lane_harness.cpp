@@ -62,6 +62,18 @@ static bool check_position(const orc_bg_state &s) {
         const uint32_t o123 = g.own[1] | g.own[2] | g.own[3];
         const uint32_t own1 = g.own[0] | o123, outside = own1 & ~0x3Fu;
         const bool bo = g.bar_own == 0 && (outside & (outside - 1u)) == 0 && (outside & ~(g.own[0] & ~o123)) == 0 && own1 != 0;
+        if (bo) {   // the walk as the lane kernels instantiate it (bear-off regime taken for granted)
+            uint32_t scr2[L_SCRATCH];
+            LaneGen gen2;
+            l_movegen_walk_t<true>(g, gen2, scr2, 1);
+            if (gen2.U != n) { fprintf(stderr, "bear-off walk count differs: %d vs %d\n", gen2.U, n); print_state(s); return false; }
+            for (int k = 0; k < n; ++k) {
+                const LanePlay pl = l_pick_walk(gen2, scr2, 1, k);
+                uint32_t o;
+                memcpy(&o, &mv[k], 4);
+                if (l_play_to_seq(pl, g.player) != o) { fprintf(stderr, "bear-off walk play %d differs\n", k); print_state(s); return false; }
+            }
+        }
         if (bo && n > 0) {
             ++n_boregime;
             if ((g.opp[0] | g.opp[1] | g.opp[2] | g.opp[3]) & 0x3Fu) ++n_bo_opp_home;

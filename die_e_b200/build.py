@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdiee_cuda.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = (["-DDIEE_LANE_STATS"] if os.environ.get("DIEE_LANE_STATS") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+FLAGS = (["-DDIEE_LANE_STATS"] if os.environ.get("DIEE_LANE_STATS") else []) + os.environ.get("DIEE_EXTRA_NVCC_FLAGS", "").split() + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--fmad=true"]
 
 

@@ -144,7 +144,10 @@ struct ConvCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES_RAW = (216 * 1024) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+#ifndef DIEE_CONV_MAX_STAGES
+#define DIEE_CONV_MAX_STAGES 8
+#endif
+    static constexpr int STAGES = STAGES_RAW > DIEE_CONV_MAX_STAGES ? DIEE_CONV_MAX_STAGES : STAGES_RAW;
     static constexpr int SLACK = (ROWS % 128) ? 16 * 1024 : 0;  // a padded M-tile reads past its stage: keep that inside the allocation
     static constexpr int TMEM_COLS = (MT * BN <= 32) ? 32 : (MT * BN <= 64) ? 64 : (MT * BN <= 128) ? 128 : (MT * BN <= 256) ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/ + SLACK;

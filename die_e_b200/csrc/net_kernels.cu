@@ -18,6 +18,7 @@
 // The first layer (6 -> F channels, K = 54) consumes a [positions][64] bf16 matrix that
 // encode_im2col_kernel builds directly from the packed 32-byte states (as_tensor,
 // backgammon_logic.rs:198-252, fused with the tap gather), through the same kernel with one tap.
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -133,25 +134,27 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 constexpr int CONV_THREADS = 192;
 
 // A CTA computes NB boards x BN output channels.  NB = 16 (384 positions = 3 MMA M-tiles) x BN = 128 is the shape for
-// big batches; smaller shapes exist because a CTA's time is set by the bytes it has to pull through ITS SM's L2 port
-// (~38 B/cycle measured: a layer takes the same 32 us at 16 boards as at 1,024), so a small batch is spread over as
-// many CTAs as there are SMs, each with a smaller tile (net.cu picks the shape per launch).
-template <int BN, int NB>
+// big batches.  What a K-block costs a CTA does not depend on how many CTAs run (a layer takes the same 32 us at 16
+// boards as at 1,024): about 0.2 us plus its MMAs at the rate their operands leave shared memory.  So a
+// small batch is spread over as many CTAs as there are SMs, each with a smaller tile (net.cu picks the shape per
+// launch), and the small tiles take KC = 2 chunks of 64 input channels per pipeline stage: half as many K-blocks.
+template <int BN, int NB, int KC = 1>
 struct ConvCfg {
     static constexpr int ROWS = NB * 24;
     static constexpr int MT = (ROWS + 127) / 128;          // the last M-tile may be partly padding (rows >= ROWS: never stored)
-    static constexpr int A_BYTES = ROWS * 128;             // one K-block (64 bf16 channels) of the activation tile
+    static constexpr int A_BYTES = ROWS * 128;             // one chunk (64 bf16 channels) of the activation tile
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = KC * (A_BYTES + B_BYTES);  // [A chunk 0 .. A chunk KC-1 | B chunk 0 .. B chunk KC-1]
     static constexpr int STAGES_RAW = (216 * 1024) / STAGE_BYTES;
 #ifndef DIEE_CONV_MAX_STAGES
 #define DIEE_CONV_MAX_STAGES 8
 #endif
     static constexpr int STAGES = STAGES_RAW > DIEE_CONV_MAX_STAGES ? DIEE_CONV_MAX_STAGES : STAGES_RAW;
-    static constexpr int SLACK = (ROWS % 128) ? 16 * 1024 : 0;  // a padded M-tile reads past its stage: keep that inside the allocation
+    static constexpr int SLACK = (ROWS % 128) ? 16 * 1024 : 0;  // a padded M-tile reads past its tile: keep that inside the allocation
     static constexpr int TMEM_COLS = (MT * BN <= 32) ? 32 : (MT * BN <= 64) ? 64 : (MT * BN <= 128) ? 128 : (MT * BN <= 256) ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/ + SLACK;
-    static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned (128B swizzle atoms)");
+    static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned (128B swizzle atoms)");
+    static_assert(STAGES >= 2, "pipeline depth");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(MT * BN <= 512, "TMEM budget");
 };
@@ -164,13 +167,13 @@ struct ConvCfg {
 // accumulator -- so the K loop simply runs over (pair, tap, chunk): `pairs` packs up to eight (i, j) as 2+2
 // bits each, plane i of the activations starts a_plane channels further on, plane j of the weights b_plane
 // K-columns further on.  Plain bf16 is the one pair (0, 0).
-template <int BN, int NB>
+template <int BN, int NB, int KC>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int n_boards,
                   int ntaps, int chunks, const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual,
                   void *__restrict__ out, int out_mode, int c_out_total, int relu, int npairs, uint32_t pairs, int a_plane,
                   int b_plane) {
-    using Cfg = ConvCfg<BN, NB>;
+    using Cfg = ConvCfg<BN, NB, KC>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *tail = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -184,7 +187,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int board0 = blockIdx.x * NB;
     const int n0 = blockIdx.y * BN;
     const int per_pair = ntaps * chunks;
-    const int num_kb = per_pair * npairs;
+    const int num_kb = per_pair * npairs / KC;  // pipeline steps: KC consecutive chunks of one tap each (chunks % KC == 0)
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmapA);
@@ -208,14 +211,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 uint8_t *sa = smem + s * Cfg::STAGE_BYTES;
-                uint8_t *sb = sa + Cfg::A_BYTES;
+                uint8_t *sb = sa + KC * Cfg::A_BYTES;
                 mbar_expect_tx(&full_bar[s], (uint32_t)Cfg::STAGE_BYTES);
-                const int pr = kb / per_pair, kin = kb - pr * per_pair;
+                const int k0 = kb * KC;
+                const int pr = k0 / per_pair, kin = k0 - pr * per_pair;
                 const int pi = (int)((pairs >> (4 * pr)) & 3u), pj = (int)((pairs >> (4 * pr + 2)) & 3u);
                 const int tap = kin / chunks, chunk = kin - tap * chunks;
                 const int kh = ntaps == 9 ? tap / 3 : 1, kw = ntaps == 9 ? tap - (tap / 3) * 3 : 1;
-                tma_load_4d(sa, &tmapA, &full_bar[s], pi * a_plane + chunk * 64, kw - 1, kh - 1, board0);
-                tma_load_2d(sb, &tmapB, &full_bar[s], pj * b_plane + kin * 64, n0);
+#pragma unroll
+                for (int h = 0; h < KC; ++h) {
+                    tma_load_4d(sa + h * Cfg::A_BYTES, &tmapA, &full_bar[s], pi * a_plane + (chunk + h) * 64, kw - 1, kh - 1, board0);
+                    tma_load_2d(sb + h * Cfg::B_BYTES, &tmapB, &full_bar[s], pj * b_plane + (kin + h) * 64, n0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -228,14 +235,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint32_t sb = sa + Cfg::A_BYTES;
+                const uint32_t sb = sa + KC * Cfg::A_BYTES;
 #pragma unroll
-                for (int mt = 0; mt < Cfg::MT; ++mt) {
+                for (int h = 0; h < KC; ++h) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzled row
-                        const uint64_t ad = umma_desc_sw128(sa + mt * (128 * 128) + kk * 32);
-                        const uint64_t bd = umma_desc_sw128(sb + kk * 32);
-                        umma_bf16(tmem_base + (uint32_t)(mt * BN), ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
+                    for (int mt = 0; mt < Cfg::MT; ++mt) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzled row
+                            const uint64_t ad = umma_desc_sw128(sa + h * Cfg::A_BYTES + mt * (128 * 128) + kk * 32);
+                            const uint64_t bd = umma_desc_sw128(sb + h * Cfg::B_BYTES + kk * 32);
+                            umma_bf16(tmem_base + (uint32_t)(mt * BN), ad, bd, idesc, (kb | h | kk) != 0 ? 1u : 0u);
+                        }
                     }
                 }
                 umma_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
@@ -590,20 +600,20 @@ fc_f32_kernel(const float *__restrict__ feat, const float *__restrict__ wT, cons
 }
 
 // ---------------------------------------------------------------- launchers
-template <int BN, int NB>
+template <int BN, int NB, int KC>
 static cudaError_t launch_conv_bn(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,
                                   int chunks, const float *bias, const __nv_bfloat16 *residual, void *out, int out_mode,
                                   int c_out_total, int relu, int npairs, uint32_t pairs, int a_plane, int b_plane) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NB>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, NB, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NB, KC>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     dim3 grid((n_boards + NB - 1) / NB, c_out_total / BN);
-    conv3x3_tc_kernel<BN, NB><<<grid, CONV_THREADS, ConvCfg<BN, NB>::SMEM_BYTES, st>>>(ta, tb, n_boards, ntaps, chunks, bias, residual, out,
-                                                                                      out_mode, c_out_total, relu, npairs, pairs, a_plane,
-                                                                                      b_plane);
+    conv3x3_tc_kernel<BN, NB, KC><<<grid, CONV_THREADS, ConvCfg<BN, NB, KC>::SMEM_BYTES, st>>>(ta, tb, n_boards, ntaps, chunks, bias, residual,
+                                                                                              out, out_mode, c_out_total, relu, npairs, pairs,
+                                                                                              a_plane, b_plane);
     return cudaGetLastError();
 }
 
@@ -612,17 +622,25 @@ cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap 
                              int chunks, const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
                              int npairs, uint32_t pairs, int a_plane, int b_plane) {
     const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(residual);
-#define DIEE_CONV_CASE(BN_, NB_)                                                                                                        \
-    if (bn == BN_ && nb == NB_)                                                                                                         \
-        return launch_conv_bn<BN_, NB_>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu, npairs, pairs, \
-                                        a_plane, b_plane);
-    DIEE_CONV_CASE(128, 16)
-    DIEE_CONV_CASE(32, 16)
-    DIEE_CONV_CASE(16, 16)
-    DIEE_CONV_CASE(128, 8)
-    DIEE_CONV_CASE(64, 8)
-    DIEE_CONV_CASE(32, 8)
-    DIEE_CONV_CASE(32, 4)
+    // several chunks per pipeline stage where the tile is small enough for >= 3 such stages and the layer's chunk count
+    // divides (DIEE_CONV_KC=n caps it; 1 keeps one chunk per stage everywhere)
+    static const bool one_chunk = getenv("DIEE_CONV_KC") && atoi(getenv("DIEE_CONV_KC")) == 1;
+    const int max_kc = one_chunk ? 1 : (getenv("DIEE_CONV_KC") ? atoi(getenv("DIEE_CONV_KC")) : 4);
+#define DIEE_CONV_CASE(BN_, NB_, KC_)                                                                                                        \
+    if (bn == BN_ && nb == NB_ && KC_ <= max_kc && chunks % KC_ == 0)                                                                                    \
+        return launch_conv_bn<BN_, NB_, KC_>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu, npairs, pairs, \
+                                             a_plane, b_plane);
+    DIEE_CONV_CASE(128, 16, 1)
+    DIEE_CONV_CASE(32, 16, 1)
+    DIEE_CONV_CASE(16, 16, 1)
+    DIEE_CONV_CASE(128, 8, 1)
+    DIEE_CONV_CASE(64, 8, 2)
+    DIEE_CONV_CASE(64, 8, 1)
+    DIEE_CONV_CASE(32, 8, 2)
+    DIEE_CONV_CASE(32, 8, 1)
+    DIEE_CONV_CASE(32, 4, 4)
+    DIEE_CONV_CASE(32, 4, 2)
+    DIEE_CONV_CASE(32, 4, 1)
 #undef DIEE_CONV_CASE
     return cudaErrorInvalidValue;
 }

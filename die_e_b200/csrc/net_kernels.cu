@@ -633,6 +633,7 @@ cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap 
     DIEE_CONV_CASE(128, 16, 1)
     DIEE_CONV_CASE(32, 16, 1)
     DIEE_CONV_CASE(16, 16, 1)
+    DIEE_CONV_CASE(128, 8, 2)
     DIEE_CONV_CASE(128, 8, 1)
     DIEE_CONV_CASE(64, 8, 2)
     DIEE_CONV_CASE(64, 8, 1)

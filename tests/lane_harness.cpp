@@ -106,6 +106,24 @@ static bool check_position(const orc_bg_state &s) {
                 }
             }
         }
+        {   // ... and asked from the end (k = -3 - j: play n-1-j, none when j >= n), as the tree kernel does when it counts a node
+            const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;
+            LaneMasks mm;
+            const bool closed = l_closed_applies(g, mm, lo, hi);
+            if (g.bar_own > 0 || closed) {
+                for (int j = 0; j < 5; ++j) {
+                    LanePlay pl;
+                    if (l_contact_select(g, mm, lo, hi, -3 - j, 0u, pl) != n) { fprintf(stderr, "select from the end: count differs\n"); print_state(s); return false; }
+                    if (j >= n) {
+                        if (pl.n != 0) { fprintf(stderr, "select from the end: a play past the first one\n"); print_state(s); return false; }
+                        continue;
+                    }
+                    uint32_t o;
+                    memcpy(&o, &mv[n - 1 - j], 4);
+                    if (l_play_to_seq(pl, g.player) != o) { fprintf(stderr, "select from the end: play %d differs\n", j); print_state(s); return false; }
+                }
+            }
+        }
         if (l_pure_bearoff(g) && n > 0) ++n_pb;
         if (l_pure_bearoff(g)) {  // the play table the kernels use for these positions
             const uint32_t e = pb_index[l_pb_key(g)];

@@ -253,7 +253,8 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
         if (const char *e = getenv("DIEE_LANE_STORE_MIN")) force_store_min = atoi(e);
     }
     job.lag_weight = lag_weight;
-    job.reps = 8;  // measured: 1 / 2 / 4 / 8 / 16 / 64 plies per vote -> 1.50 / 1.48 / 1.46 / 1.44 / 1.50 / 1.69 ms (C3 rollouts)
+    static const int reps_env = getenv("DIEE_LANE_REPS") ? atoi(getenv("DIEE_LANE_REPS")) : 0;
+    job.reps = reps_env > 0 ? reps_env : 8;  // measured: 1 / 2 / 4 / 8 / 16 / 64 plies per vote -> 1.50 / 1.48 / 1.46 / 1.44 / 1.50 / 1.69 ms (C3 rollouts)
     // one item per lane as long as the job fits ~10 CTAs per SM (the C2 / C3 sizes: fewer, fuller warps); a bigger job
     // runs at full occupancy and lanes are refilled from the queue (measured at 819,200 rollouts: 77.7 M simulations/s
     // with 10 CTAs per SM, 82.6 M with 16)

@@ -4,14 +4,15 @@
 // Every 3x3 convolution over the 4x6 board is an implicit GEMM on the 5th-generation tensor
 // cores:  M = boards*24 positions, N = output channels, K = 9 taps * C_in.
 //   * activations live in HBM as NHWC bf16 ([board][h][w][c]); a 4-D TMA tensor map
-//     (c, w, h, board) with a box of [64 ch][6][4][16 boards] loads, for tap (kh,kw), the box
+//     (c, w, h, board) with a box of [64 ch][6][4][NB boards] (NB = 16, 8 or 4) loads, for tap (kh,kw), the box
 //     shifted by (kw-1, kh-1): the out-of-bounds halo is ZERO-FILLED by TMA, so the 3x3 padding
 //     costs nothing and no im2col matrix is ever materialised;
 //   * weights are pre-packed [c_out][tap][c_in] bf16 with BatchNorm folded in (eval mode), loaded
 //     by a 2-D tensor map; both operands land in shared memory in the 128-byte swizzle that
 //     tcgen05 smem descriptors expect;
 //   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM accumulators
-//     (3 M-tiles x BN fp32 columns for a 16-board tile); tcgen05.commit releases smem stages and
+//     (3 M-tiles x BN fp32 columns for a 16-board tile; the tile shape is picked per launch, see ConvCfg);
+//     tcgen05.commit releases smem stages and
 //     finally signals the epilogue warps, which read TMEM with tcgen05.ld, add the folded bias
 //     (+ residual), apply ReLU and store bf16 NHWC (or fp32 for the two head convolutions).
 //   * warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue.

@@ -825,6 +825,9 @@ LANE_HD LanePlay l_pb_unpack(uint32_t w) {
 }
 
 // Counts the distinct plays of `g`.  Contact play is counted in closed form; otherwise root by root.
+// (l_movegen / l_pick are the two-pass form -- count, then pick -- of every regime.  The kernels call the fused
+// l_contact_select, the bear-off table and l_movegen_walk_t<true> directly; the two-pass form stays as what
+// tests/lane_harness.cpp checks them against, position by position, and as the generator of the table.)
 LANE_HD void l_movegen(const LaneBoard &g, LaneGen &gen, uint32_t *scr, int stride) {
     const int hi = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo = g.roll0 > g.roll1 ? g.roll1 : g.roll0;
     LaneMasks m;

@@ -80,3 +80,38 @@ def test_training_data_files_round_trip(tmp_path):
     assert len(back) == 7
     for a, b in zip(data, back):
         assert a.outcome == b.outcome and (a.ps == b.ps).all() and (a.state == b.state).all() and b.state.shape == (1, 6, 4, 6)
+
+
+def test_reference_mcts_test_invariants(oracle):
+    """tests/mcts_test.rs of the reference (its only two tests on the search path), on the oracle twins:
+    :17-33  turn_policy_to_probs_tensor_parallel -- with a RANDOM policy every row of masked, renormalised priors sums
+            to 1 (here: the priors of every root's children, one root per game, and of every expanded node);
+    :41-59  get_prob_tensor_parallel -- a root whose children all have 10 visits gives a row that sums to 1."""
+    import positions
+    rng = np.random.default_rng(7)
+
+    def random_eval(states):
+        n = len(states)
+        return rng.random((n, 1352), dtype=np.float32), np.zeros(n, dtype=np.float32)
+    states = positions.midgame_positions(seed=9, n=10, max_adv=60)
+    cfg = oracle.mcts_cfg(iterations=12, c=2.0, limit=400, alpha=0.3, eps=0.0)
+    nodes, n_nodes, status = oracle.alpha_mcts_parallel(states, np.arange(10), cfg, 3, 0, oracle.make_eval(random_eval), 1 + 13 * 130)
+    assert (status == 0).all()
+    rows = 0
+    for g in range(10):
+        t = nodes[g, :n_nodes[g]]
+        for nd in t:
+            nc = int(nd["n_children"])
+            if nc:
+                ch = t[nd["first_child"]:nd["first_child"] + nc]
+                assert abs(float(ch["prior"].astype(np.float64).sum()) - 1.0) <= 1e-5
+                rows += 1
+    assert rows >= 10
+    # get_prob_tensor_parallel: children with 10 visits each
+    t = nodes[0, :n_nodes[0]].copy()
+    nc = int(t[0]["n_children"])
+    assert nc > 0
+    t["visits"][t[0]["first_child"]:t[0]["first_child"] + nc] = 10.0
+    ids, pi = oracle.root_pi(t, 1.0)
+    assert len(ids) == nc and abs(float(pi.astype(np.float64).sum()) - 1.0) <= 1e-5
+    assert np.allclose(pi, 1.0 / nc, rtol=1e-6)

@@ -1,7 +1,8 @@
 """The reference's own tests (transcribed, tests/golden/) run against the CPU oracle.
 
 This is the oracle's pin: every vector in tests/backgammon_test.rs, tests/tictactoe_test.rs
-and tests/encoding_test.rs of alibasaran/die-e.
+and tests/encoding_test.rs of alibasaran/die-e.  (The reference's fourth test file, tests/mcts_test.rs, holds two
+normalisation invariants and no vectors; they run on the oracle in tests/test_alpha_host.py.)
 """
 import json
 import os

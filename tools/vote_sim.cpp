@@ -31,7 +31,7 @@ static const char *SUB_NAME[S_COUNT] = {"two dice", "doubles", "bar", "bear-off 
 // warp instructions per executed sub-case and per step (profiles/r01_lane_run_rollouts_v8_ncu_full_summary.txt, rounded)
 static int COST[S_COUNT] = {230, 210, 100, 40, 20, 1000, 1000};  // (the walk: 22 % of the instructions at ~14 % of the ply steps)
 static int COST_SHARED = 270;  // Philox, apply, turn change, next path, loop
-static int COST_VOTE = 40, COST_STORE = 300;
+static int COST_VOTE = 150, COST_STORE = 300;  // (vote: calibrated on the measured plies-per-vote sweep, 8 best)
 
 static Sub classify(const LaneBoard &g) {
     const uint32_t o123 = g.own[1] | g.own[2] | g.own[3];
@@ -121,7 +121,7 @@ static Result simulate_fine(const std::vector<std::vector<uint8_t>> &seqs, int r
 // fold_walk: 0 = both kinds of walk are the voted walk path, 1 = the all-home kind runs on the closed path at walk_cost
 // (the one-outside kind stays voted), 2 = both on the closed path
 static Result simulate(const std::vector<std::vector<uint8_t>> &seqs, int games_per_lane, int fold_walk, int walk_cost, int reps,
-                       int store_min, int waves = 1) {
+                       int store_min, int waves = 1, double walk_weight = 1.0) {
     Result r;
     const int per_warp = 32 * games_per_lane;
     const int n = (int)seqs.size();
@@ -148,7 +148,7 @@ static Result simulate(const std::vector<std::vector<uint8_t>> &seqs, int games_
                 for (int k = 0; k < games_per_lane; ++k) { const int nd = need(slot[l * games_per_lane + k]); if (nd >= 0) has[nd] = true; }
                 for (int p = 0; p < 3; ++p) cnt[p] += has[p];
             }
-            int best = cnt[0] >= cnt[1] ? 0 : 1;
+            int best = (double)cnt[0] >= walk_weight * cnt[1] ? 0 : 1;  // walk_weight < 1: the walk must gather more lanes to win
             if (cnt[best] == 0) best = 2;
             if (cnt[2] >= store_min && cnt[2] > 0) best = 2;
             ++r.steps[best];
@@ -240,11 +240,26 @@ int main(int argc, char **argv) {
     report("C  two games per lane", simulate(seqs, 2, 0, COST[S_WALK], 8, 16));
     report("C' four games per lane", simulate(seqs, 4, 0, COST[S_WALK], 8, 32));
     report("D  one vote path per sub-case", simulate_fine(seqs, 8, 8));
+    for (int reps : {1, 4, 8, 16, 64}) {
+        char name[64];
+        snprintf(name, sizeof name, "A  with %d plies per vote (GPU: 8 is best)", reps);
+        report(name, simulate(seqs, 1, 0, COST[S_WALK], reps, 8));
+    }
+    for (double ww : {0.25, 0.5, 0.75, 1.5, 3.0}) {
+        char name[64];
+        snprintf(name, sizeof name, "A  walk lanes weighted %.2f in the vote", ww);
+        report(name, simulate(seqs, 1, 0, COST[S_WALK], 8, 8, 1, ww));
+    }
     printf("-- a job six times the machine, lanes refilled from the queue (store batch 24) --\n");
     report("A  as built", simulate(seqs, 1, 0, COST[S_WALK], 8, 24, 6));
     report("B' walk folded into the closed path at a third of its cost", simulate(seqs, 1, 2, COST[S_WALK] / 3, 8, 24, 6));
     report("B\" ... at table cost", simulate(seqs, 1, 2, COST[S_PB], 8, 24, 6));
     report("E  only the all-home walk folded, at table cost (GPU: -11 %)", simulate(seqs, 1, 1, COST[S_PB], 8, 24, 6));
+    for (double ww : {0.25, 0.5, 0.75, 1.5}) {
+        char name[64];
+        snprintf(name, sizeof name, "A  walk lanes weighted %.2f in the vote", ww);
+        report(name, simulate(seqs, 1, 0, COST[S_WALK], 8, 24, 6, ww));
+    }
     report("C  two games per lane", simulate(seqs, 2, 0, COST[S_WALK], 8, 24, 3));
     report("C' four games per lane", simulate(seqs, 4, 0, COST[S_WALK], 8, 24, 2));
     return 0;

@@ -14,7 +14,8 @@
 //   A  the kernel as it is (one game per lane),
 //   B  the bear-off walk folded into the closed path at a given cost (what a cheaper generator would buy),
 //   C  two games per lane (a lane takes a step with whichever of its games waits for the voted path),
-//   D  one vote path per sub-case (measured on the GPU: 1.9x slower -- the model's sanity check).
+//   D  one vote path per sub-case (measured on the GPU: 1.9x slower -- the model's sanity check),
+//   F  a CTA that re-packs its games by sub-case every ply (full, nearly homogeneous warps at the price of an exchange).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -190,6 +191,51 @@ static Result simulate(const std::vector<std::vector<uint8_t>> &seqs, int games_
     return r;
 }
 
+// F: a CTA of W warps re-packs its 32*W games every ply: sorted by sub-case, consecutive 32-game chunks go to the warps,
+// so a warp is full and sees one or two sub-cases.  Cost per warp and ply: shared + its chunk's sub-cases + `exchange`
+// (state through shared memory, counting sort, two block barriers).  Finished games are replaced from the queue
+// (`waves` shares) at COST_STORE per 32.
+static Result simulate_sorted(const std::vector<std::vector<uint8_t>> &seqs, int W, int exchange, int waves) {
+    Result r;
+    const int per_cta = 32 * W, n = (int)seqs.size(), share = per_cta * waves;
+    for (int base = 0; base < n; base += share) {
+        std::vector<int> item(per_cta), pos(per_cta, 0);
+        int next = base + per_cta;
+        const int end = std::min(n, base + share);
+        int live = 0;
+        for (int i = 0; i < per_cta; ++i) { item[i] = base + i < end ? base + i : -1; if (item[i] >= 0) ++live; }
+        long long stored = 0;
+        while (live > 0) {
+            // finished games leave (and are replaced)
+            for (int i = 0; i < per_cta; ++i)
+                if (item[i] >= 0 && pos[i] >= (int)seqs[item[i]].size()) {
+                    ++stored;
+                    if (next < end) { item[i] = next++; pos[i] = 0; }
+                    else { item[i] = -1; --live; }
+                }
+            if (live == 0) break;
+            // sort the live games by sub-case
+            std::vector<std::pair<int, int>> order;  // (sub-case, slot)
+            for (int i = 0; i < per_cta; ++i)
+                if (item[i] >= 0 && pos[i] < (int)seqs[item[i]].size()) order.push_back({seqs[item[i]][pos[i]], i});
+            if (order.empty()) continue;
+            std::sort(order.begin(), order.end());
+            for (size_t c0 = 0; c0 < order.size(); c0 += 32) {
+                bool present[S_COUNT] = {false};
+                const size_t c1 = std::min(order.size(), c0 + 32);
+                for (size_t j = c0; j < c1; ++j) { present[order[j].first] = true; ++pos[order[j].second]; }
+                ++r.exec;
+                r.exec_lanes += (long long)(c1 - c0);
+                r.plies += (long long)(c1 - c0);
+                r.cost += COST_SHARED + exchange;
+                for (int c = 0; c < S_COUNT; ++c) if (present[c]) r.cost += COST[c];
+            }
+        }
+        r.cost += stored * COST_STORE / 32;
+    }
+    return r;
+}
+
 static void report(const char *name, const Result &r) {
     printf("%-58s steps closed/walk/store %8lld %8lld %7lld  lanes/step %5.1f %5.1f %5.1f | ply steps %8lld at %5.1f lanes | %6.1f instr per played ply\n",
            name, r.steps[0], r.steps[1], r.steps[2], r.steps[0] ? (double)r.lanes[0] / r.steps[0] : 0.0,
@@ -250,6 +296,12 @@ int main(int argc, char **argv) {
         snprintf(name, sizeof name, "A  walk lanes weighted %.2f in the vote", ww);
         report(name, simulate(seqs, 1, 0, COST[S_WALK], 8, 8, 1, ww));
     }
+    for (int W : {2, 4, 8}) {
+        char name[80];
+        snprintf(name, sizeof name, "F  CTA of %d warps re-packed by sub-case every ply (+150)", W);
+        report(name, simulate_sorted(seqs, W, 150, 1));
+    }
+    report("F  ... 4 warps, exchange at 300", simulate_sorted(seqs, 4, 300, 1));
     printf("-- a job six times the machine, lanes refilled from the queue (store batch 24) --\n");
     report("A  as built", simulate(seqs, 1, 0, COST[S_WALK], 8, 24, 6));
     report("B' walk folded into the closed path at a third of its cost", simulate(seqs, 1, 2, COST[S_WALK] / 3, 8, 24, 6));
@@ -260,6 +312,12 @@ int main(int argc, char **argv) {
         snprintf(name, sizeof name, "A  walk lanes weighted %.2f in the vote", ww);
         report(name, simulate(seqs, 1, 0, COST[S_WALK], 8, 24, 6, ww));
     }
+    for (int W : {2, 4, 8}) {
+        char name[80];
+        snprintf(name, sizeof name, "F  CTA of %d warps re-packed by sub-case every ply (+150)", W);
+        report(name, simulate_sorted(seqs, W, 150, 6));
+    }
+    report("F  ... 4 warps, exchange at 300", simulate_sorted(seqs, 4, 300, 6));
     report("C  two games per lane", simulate(seqs, 2, 0, COST[S_WALK], 8, 24, 3));
     report("C' four games per lane", simulate(seqs, 4, 0, COST[S_WALK], 8, 24, 2));
     return 0;

@@ -69,7 +69,10 @@ static void start_state(LaneBoard &g, int game, int adv) {
     }
 }
 
-struct Result { long long steps[3] = {0, 0, 0}, lanes[3] = {0, 0, 0}, plies = 0, exec = 0, exec_lanes = 0, cost = 0; };
+struct Result {
+    long long steps[3] = {0, 0, 0}, lanes[3] = {0, 0, 0}, plies = 0, exec = 0, exec_lanes = 0, cost = 0;
+    long long chain = 0;  // the longest dependent chain of any warp (or CTA, design F): what bounds a job that fits one wave
+};
 
 // D: one vote path per sub-case (what DESIGN.md section 4 reports as measured: 1.19 -> 2.21 ms)
 static Result simulate_fine(const std::vector<std::vector<uint8_t>> &seqs, int reps, int store_min) {
@@ -134,6 +137,7 @@ static Result simulate(const std::vector<std::vector<uint8_t>> &seqs, int games_
         int next = base + per_warp;
         const int end = std::min(n, base + share);
         for (int i = 0; i < per_warp; ++i) { slot[i] = {base + i < end ? base + i : -1, 0}; if (slot[i].item >= 0) ++live; }
+        const long long cost_at_start = r.cost;
         auto need = [&](const Slot &s) -> int {  // 0 closed, 1 walk, 2 store, -1 nothing
             if (s.item < 0) return -1;
             const auto &q = seqs[s.item];
@@ -187,6 +191,7 @@ static Result simulate(const std::vector<std::vector<uint8_t>> &seqs, int games_
                     if (present[c]) r.cost += ((c == S_WALK && fold_walk) || (c == S_WALK1 && fold_walk == 2)) ? walk_cost : COST[c];
             }
         }
+        r.chain = std::max(r.chain, r.cost - cost_at_start);
     }
     return r;
 }
@@ -204,7 +209,7 @@ static Result simulate_sorted(const std::vector<std::vector<uint8_t>> &seqs, int
         const int end = std::min(n, base + share);
         int live = 0;
         for (int i = 0; i < per_cta; ++i) { item[i] = base + i < end ? base + i : -1; if (item[i] >= 0) ++live; }
-        long long stored = 0;
+        long long stored = 0, chain = 0;
         while (live > 0) {
             // finished games leave (and are replaced)
             for (int i = 0; i < per_cta; ++i)
@@ -220,6 +225,7 @@ static Result simulate_sorted(const std::vector<std::vector<uint8_t>> &seqs, int
                 if (item[i] >= 0 && pos[i] < (int)seqs[item[i]].size()) order.push_back({seqs[item[i]][pos[i]], i});
             if (order.empty()) continue;
             std::sort(order.begin(), order.end());
+            long long slowest = 0;
             for (size_t c0 = 0; c0 < order.size(); c0 += 32) {
                 bool present[S_COUNT] = {false};
                 const size_t c1 = std::min(order.size(), c0 + 32);
@@ -227,20 +233,24 @@ static Result simulate_sorted(const std::vector<std::vector<uint8_t>> &seqs, int
                 ++r.exec;
                 r.exec_lanes += (long long)(c1 - c0);
                 r.plies += (long long)(c1 - c0);
-                r.cost += COST_SHARED + exchange;
-                for (int c = 0; c < S_COUNT; ++c) if (present[c]) r.cost += COST[c];
+                long long wc = COST_SHARED + exchange;
+                for (int c = 0; c < S_COUNT; ++c) if (present[c]) wc += COST[c];
+                r.cost += wc;
+                slowest = std::max(slowest, wc);
             }
+            chain += slowest;  // the warps of a CTA meet at a barrier every ply
         }
         r.cost += stored * COST_STORE / 32;
+        r.chain = std::max(r.chain, chain);
     }
     return r;
 }
 
 static void report(const char *name, const Result &r) {
-    printf("%-58s steps closed/walk/store %8lld %8lld %7lld  lanes/step %5.1f %5.1f %5.1f | ply steps %8lld at %5.1f lanes | %6.1f instr per played ply\n",
+    printf("%-58s steps closed/walk/store %8lld %8lld %7lld  lanes/step %5.1f %5.1f %5.1f | ply steps %8lld at %5.1f lanes | %6.1f instr per played ply | longest chain %7lld\n",
            name, r.steps[0], r.steps[1], r.steps[2], r.steps[0] ? (double)r.lanes[0] / r.steps[0] : 0.0,
            r.steps[1] ? (double)r.lanes[1] / r.steps[1] : 0.0, r.steps[2] ? (double)r.lanes[2] / r.steps[2] : 0.0, r.exec,
-           r.exec ? (double)r.exec_lanes / r.exec : 0.0, r.plies ? (double)r.cost / r.plies : 0.0);
+           r.exec ? (double)r.exec_lanes / r.exec : 0.0, r.plies ? (double)r.cost / r.plies : 0.0, r.chain);
 }
 
 int main(int argc, char **argv) {

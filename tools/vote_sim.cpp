@@ -306,6 +306,15 @@ int main(int argc, char **argv) {
         snprintf(name, sizeof name, "A  walk lanes weighted %.2f in the vote", ww);
         report(name, simulate(seqs, 1, 0, COST[S_WALK], 8, 8, 1, ww));
     }
+    for (int fill : {16, 8}) {  // thinner warps: only `fill` of the 32 lanes get a rollout (shorter chains, more warps)
+        std::vector<std::vector<uint8_t>> thin;
+        for (size_t i = 0; i < seqs.size(); i += (size_t)fill) {
+            for (int l = 0; l < 32; ++l) thin.push_back(l < fill && i + l < seqs.size() ? seqs[i + l] : std::vector<uint8_t>());
+        }
+        char name[80];
+        snprintf(name, sizeof name, "G  %d rollouts per warp (plies counted incl. empty lanes: x%d warps)", fill, 32 / fill);
+        report(name, simulate(thin, 1, 0, COST[S_WALK], 8, 8));
+    }
     for (int W : {2, 4, 8}) {
         char name[80];
         snprintf(name, sizeof name, "F  CTA of %d warps re-packed by sub-case every ply (+150)", W);

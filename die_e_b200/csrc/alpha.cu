@@ -114,6 +114,12 @@ static int32_t check_alpha_args(diee_ctx *ctx, diee_net *net, int n, const diee_
     if (!ctx) return DIEE_ERR_INVALID;
     if (!net || !cfg || n < 0) return fail(ctx, DIEE_ERR_INVALID, "alpha_search: bad argument");
     if (cfg->iterations == 0 || cfg->iterations > 65534u) return fail(ctx, DIEE_ERR_INVALID, "alpha_search: iterations must be in 1..65534");
+    // Dirichlet::new(&vec![alpha; n]).unwrap() panics for alpha <= 0 (noise.rs:29); here: an error, never a hang in the
+    // Gamma rejection loop or a silent NaN prior.  epsilon mixes two distributions, so it must lie in [0, 1].
+    if (!(cfg->dirichlet_alpha > 0.f) || !std::isfinite(cfg->dirichlet_alpha))
+        return fail(ctx, DIEE_ERR_INVALID, "alpha_search: dirichlet_alpha must be a finite number > 0");
+    if (!(cfg->dirichlet_epsilon >= 0.f && cfg->dirichlet_epsilon <= 1.f))
+        return fail(ctx, DIEE_ERR_INVALID, "alpha_search: dirichlet_epsilon must be in [0, 1]");
     (void)epoch;
     return DIEE_OK;
 }
@@ -121,7 +127,7 @@ static int32_t check_alpha_args(diee_ctx *ctx, diee_net *net, int n, const diee_
 extern "C" {
 
 int32_t diee_dirichlet(uint64_t seed, uint32_t epoch, float alpha, int32_t n, float *out) {
-    if (!out || n <= 0 || !(alpha > 0.f)) return DIEE_ERR_INVALID;
+    if (!out || n <= 0 || !(alpha > 0.f) || !std::isfinite(alpha)) return DIEE_ERR_INVALID;
     dirichlet_sample(seed, epoch, alpha, n, out);
     return DIEE_OK;
 }

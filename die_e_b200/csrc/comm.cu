@@ -86,6 +86,9 @@ int32_t diee_comm_init(diee_ctx *ctx, int32_t nranks, int32_t rank, const uint8_
     ncclUniqueId uid;
     memcpy(&uid, id, DIEE_COMM_ID_BYTES);
     ncclComm_t c = nullptr;
+    // scratch of the counts / status gathers of diee_traj_allgather: allocated HERE so that nothing rank-local can
+    // fail between entering that call and its first collective
+    RESERVE(ctx->c_counts, sizeof(long long) * 6 * (size_t)(nranks + 2));
     NC(N->CommInitRank(&c, nranks, uid, rank));
     ctx->comm = c;
     ctx->comm_ranks = nranks;
@@ -108,52 +111,83 @@ int32_t diee_comm_destroy(diee_ctx *ctx) {
 
 // Ragged sizes: the counts first, then slabs padded to the largest contribution; the host keeps each rank's valid prefix,
 // rank-major, and rebases pi_offset into the concatenated pi arrays.
+//
+// Every decision between the collectives is COLLECTIVE: caps, output pointers and local failures are rank-local
+// facts, and a rank that bailed out alone would leave the others inside the next ncclAllGather forever.  So each rank
+// contributes (n_rec, n_pi, rec_cap, pi_cap, outputs present) to the first gather and all of them derive the same
+// verdict from the same table; a rank whose staging (allocation, H2D copy) fails still takes part in a one-word
+// status gather and in nothing after it, and every rank returns an error in that case.
 int32_t diee_traj_allgather(diee_ctx *ctx, const diee_traj_record *rec, int32_t n_rec, const uint16_t *pi_ids, const float *pi_vals,
                             int32_t n_pi, diee_traj_record *rec_out, int32_t rec_cap, uint16_t *pi_ids_out, float *pi_vals_out,
                             int32_t pi_cap, int32_t *n_rec_out, int32_t *n_pi_out) {
-    if (!ctx || n_rec < 0 || n_pi < 0 || !n_rec_out || !n_pi_out || (n_rec && !rec) || (n_pi && (!pi_ids || !pi_vals)))
-        return fail(ctx, DIEE_ERR_INVALID, "traj_allgather: bad argument");
+    if (!ctx) return DIEE_ERR_INVALID;
     Nccl *N = nccl();
     if (!N || !ctx->comm) return fail(ctx, DIEE_ERR_INVALID, "traj_allgather: diee_comm_init has not been called on this context");
+    // a locally invalid call still enters the first gather (with the `bad` flag up) so that nobody waits for it
+    const bool bad_in = n_rec < 0 || n_pi < 0 || !n_rec_out || !n_pi_out || (n_rec > 0 && !rec) || (n_pi > 0 && (!pi_ids || !pi_vals)) ||
+                        rec_cap < 0 || pi_cap < 0;
     CU(cudaSetDevice(ctx->device));
     ncclComm_t comm = (ncclComm_t)ctx->comm;
     const int W = ctx->comm_ranks;
     cudaStream_t st = ctx->stream;
-    // counts
-    RESERVE(ctx->c_counts, sizeof(long long) * 2 * (size_t)(W + 1));
-    long long mine[2] = {n_rec, n_pi};
-    long long *d_mine = (long long *)ctx->c_counts.p, *d_all = d_mine + 2;
-    CU(cudaMemcpyAsync(d_mine, mine, sizeof mine, cudaMemcpyHostToDevice, st));
-    NC(N->AllGather(d_mine, d_all, 2, ncclInt64, comm, st));
-    std::vector<long long> all(2 * (size_t)W);
-    CU(cudaMemcpyAsync(all.data(), d_all, sizeof(long long) * 2 * W, cudaMemcpyDeviceToHost, st));
+    constexpr int F = 6;  // n_rec, n_pi, rec_cap, pi_cap, has rec_out, has pi outputs (all -1 in a row = bad call on that rank)
+    // (the buffers below are allocated by diee_comm_init, so nothing here can fail before the first collective)
+    if (ctx->c_counts.cap < sizeof(long long) * F * (size_t)(W + 2)) return fail(ctx, DIEE_ERR_INVALID, "traj_allgather: communicator scratch missing");
+    long long mine[F] = {n_rec, n_pi, rec_cap, pi_cap, rec_out ? 1 : 0, (pi_ids_out && pi_vals_out) ? 1 : 0};
+    if (bad_in) for (int i = 0; i < F; ++i) mine[i] = -1;
+    long long *d_mine = (long long *)ctx->c_counts.p, *d_all = d_mine + F;
+    std::vector<long long> all((size_t)F * W);
+    int local_err = 0;
+    if (cudaMemcpyAsync(d_mine, mine, sizeof mine, cudaMemcpyHostToDevice, st) != cudaSuccess) local_err = 1;
+    NC(N->AllGather(d_mine, d_all, F, ncclInt64, comm, st));
+    CU(cudaMemcpyAsync(all.data(), d_all, sizeof(long long) * F * W, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     long long max_rec = 1, max_pi = 1, tot_rec = 0, tot_pi = 0;
+    int bad_rank = -1;
     for (int r = 0; r < W; ++r) {
-        max_rec = all[2 * r] > max_rec ? all[2 * r] : max_rec;
-        max_pi = all[2 * r + 1] > max_pi ? all[2 * r + 1] : max_pi;
-        tot_rec += all[2 * r];
-        tot_pi += all[2 * r + 1];
+        const long long *a = &all[(size_t)F * r];
+        if (a[0] < 0) { if (bad_rank < 0) bad_rank = r; continue; }
+        max_rec = a[0] > max_rec ? a[0] : max_rec;
+        max_pi = a[1] > max_pi ? a[1] : max_pi;
+        tot_rec += a[0];
+        tot_pi += a[1];
     }
+    if (bad_rank >= 0) return fail(ctx, DIEE_ERR_INVALID, "traj_allgather: bad argument on rank %d", bad_rank);
     *n_rec_out = (int32_t)tot_rec;
     *n_pi_out = (int32_t)tot_pi;
-    if (tot_rec > rec_cap || tot_pi > pi_cap) return fail(ctx, DIEE_ERR_OVERFLOW, "traj_allgather: %lld records / %lld pi entries do not fit", tot_rec, tot_pi);
-    if ((tot_rec && !rec_out) || (tot_pi && (!pi_ids_out || !pi_vals_out))) return fail(ctx, DIEE_ERR_INVALID, "traj_allgather: null output");
-    // slabs: [records | ids | values] of one rank, padded
+    // the same table on every rank -> the same verdict on every rank
+    for (int r = 0; r < W; ++r) {
+        const long long *a = &all[(size_t)F * r];
+        if (tot_rec > a[2] || tot_pi > a[3])
+            return fail(ctx, DIEE_ERR_OVERFLOW, "traj_allgather: %lld records / %lld pi entries do not fit rank %d's buffers (%lld / %lld)",
+                        tot_rec, tot_pi, r, a[2], a[3]);
+        if ((tot_rec && !a[4]) || (tot_pi && !a[5])) return fail(ctx, DIEE_ERR_INVALID, "traj_allgather: null output on rank %d", r);
+    }
+    // slabs: [records | ids | values] of one rank, padded.  Staging may fail locally (allocation): gather one status
+    // word before the payload so that all ranks skip it together.
     const size_t b_rec = sizeof(diee_traj_record) * (size_t)max_rec, b_ids = (2 * (size_t)max_pi + 3) & ~(size_t)3, b_val = 4 * (size_t)max_pi;
     const size_t slab = b_rec + b_ids + b_val;
-    RESERVE(ctx->c_send, slab);
-    RESERVE(ctx->c_recv, slab * (size_t)W);
+    if (!local_err && (reserve(ctx, ctx->c_send, slab) != DIEE_OK || reserve(ctx, ctx->c_recv, slab * (size_t)W) != DIEE_OK)) local_err = 1;
     unsigned char *d_send = (unsigned char *)ctx->c_send.p, *d_recv = (unsigned char *)ctx->c_recv.p;
-    if (n_rec) CU(cudaMemcpyAsync(d_send, rec, sizeof(diee_traj_record) * (size_t)n_rec, cudaMemcpyHostToDevice, st));
-    if (n_pi) {
-        CU(cudaMemcpyAsync(d_send + b_rec, pi_ids, 2 * (size_t)n_pi, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(d_send + b_rec + b_ids, pi_vals, 4 * (size_t)n_pi, cudaMemcpyHostToDevice, st));
+    if (!local_err) {
+        if (n_rec && cudaMemcpyAsync(d_send, rec, sizeof(diee_traj_record) * (size_t)n_rec, cudaMemcpyHostToDevice, st) != cudaSuccess) local_err = 1;
+        if (n_pi && (cudaMemcpyAsync(d_send + b_rec, pi_ids, 2 * (size_t)n_pi, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                     cudaMemcpyAsync(d_send + b_rec + b_ids, pi_vals, 4 * (size_t)n_pi, cudaMemcpyHostToDevice, st) != cudaSuccess)) local_err = 1;
     }
+    long long flag = local_err;
+    long long *d_flag = d_all + (size_t)F * W, *d_flags = d_mine;  // d_mine..d_all is free again: W <= F*W words
+    std::vector<long long> flags((size_t)W);
+    CU(cudaMemcpyAsync(d_flag, &flag, sizeof flag, cudaMemcpyHostToDevice, st));
+    // (gathers into the first W words of the scratch; the per-rank table was already copied to the host)
+    NC(N->AllGather(d_flag, d_flags, 1, ncclInt64, comm, st));
+    CU(cudaMemcpyAsync(flags.data(), d_flags, sizeof(long long) * W, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int r = 0; r < W; ++r)
+        if (flags[r]) return fail(ctx, DIEE_ERR_CUDA, "traj_allgather: staging failed on rank %d (device memory?)", r);
     NC(N->AllGather(d_send, d_recv, slab, ncclChar, comm, st));
     long long o_rec = 0, o_pi = 0;
     for (int r = 0; r < W; ++r) {
-        const long long nr = all[2 * r], np = all[2 * r + 1];
+        const long long nr = all[(size_t)F * r], np = all[(size_t)F * r + 1];
         const unsigned char *src = d_recv + slab * (size_t)r;
         if (nr) CU(cudaMemcpyAsync(rec_out + o_rec, src, sizeof(diee_traj_record) * (size_t)nr, cudaMemcpyDeviceToHost, st));
         if (np) {
@@ -166,9 +200,9 @@ int32_t diee_traj_allgather(diee_ctx *ctx, const diee_traj_record *rec, int32_t 
     CU(cudaStreamSynchronize(st));
     o_rec = 0; o_pi = 0;
     for (int r = 0; r < W; ++r) {  // pi_offset of rank r's records now counts from the start of the concatenated arrays
-        for (long long i = 0; i < all[2 * r]; ++i) rec_out[o_rec + i].pi_offset += (uint32_t)o_pi;
-        o_rec += all[2 * r];
-        o_pi += all[2 * r + 1];
+        for (long long i = 0; i < all[(size_t)F * r]; ++i) rec_out[o_rec + i].pi_offset += (uint32_t)o_pi;
+        o_rec += all[(size_t)F * r];
+        o_pi += all[(size_t)F * r + 1];
     }
     return DIEE_OK;
 }

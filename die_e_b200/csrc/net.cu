@@ -166,6 +166,8 @@ static int32_t build_conv(diee_ctx *ctx, ConvLayer &L, const float *w, const flo
     return upload_f32(ctx, L, wf, c_in, c_out);
 }
 
+static int32_t net_build(diee_ctx *ctx, diee_net *net, const float *const *t, int blocks, int F);
+
 extern "C" {
 
 int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *t, const int64_t *numels, int32_t n_tensors,
@@ -202,11 +204,30 @@ int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *t,
     diee_net *net = new diee_net();
     net->filters = F; net->blocks = blocks;
     for (int i = 0; i < n_tensors; ++i) net->param_count += numels[i];
+    // Every layer is built IN PLACE inside the net (the vector never reallocates), so each device buffer belongs to the
+    // net from the moment it exists and one diee_net_destroy cleans up after a failure anywhere below.
+    net->convs.reserve((size_t)1 + 2 * (size_t)blocks);
+    const int32_t rc_build = net_build(ctx, net, t, blocks, F);
+    if (rc_build != DIEE_OK) {
+        const std::string why = ctx->err;  // destroy does not touch it, but keep the first message anyway
+        diee_net_destroy(ctx, net);
+        ctx->err = why;
+        return rc_build;
+    }
+    *out = net;
+    return DIEE_OK;
+}
+
+}  // extern "C"
+
+static int32_t net_build(diee_ctx *ctx, diee_net *net, const float *const *t, int blocks, int F) {
     int32_t rc;
+    int idx;
     // init conv: C_in = 6, K = 54 padded to 64, one "tap" over the im2col operand
     {
         // repack [F][6][3][3] -> build_conv's [co][tap][ci] with c_in = 6, then pad K to 64
-        ConvLayer L;
+        net->convs.emplace_back();
+        ConvLayer &L = net->convs.back();
         std::vector<float> w6((size_t)F * 54);
         memcpy(w6.data(), t[0], sizeof(float) * w6.size());
         // build with k_pad = 64: K index = tap*6 + ci (< 54)
@@ -237,17 +258,15 @@ int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *t,
         rc = upload_f32(ctx, L, wf0, 6, F);
         if (rc != DIEE_OK) return rc;
         if (!make_w_map(&L.wmap3, L.w3, F, 3 * K, 128)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (split weights) failed");
-        net->convs.push_back(L);
     }
     idx = 6;
     for (int b = 0; b < blocks; ++b) {  // ResBlock::new registers conv1, conv2, bn1, bn2 (nnet.rs:37-44)
-        ConvLayer c1, c2;
-        rc = build_conv(ctx, c1, t[idx], t[idx + 1], t[idx + 4], t[idx + 5], t[idx + 6], t[idx + 7], F, F, F, 0, 128);
+        net->convs.emplace_back();
+        rc = build_conv(ctx, net->convs.back(), t[idx], t[idx + 1], t[idx + 4], t[idx + 5], t[idx + 6], t[idx + 7], F, F, F, 0, 128);
         if (rc != DIEE_OK) return rc;
-        rc = build_conv(ctx, c2, t[idx + 2], t[idx + 3], t[idx + 8], t[idx + 9], t[idx + 10], t[idx + 11], F, F, F, 0, 128);
+        net->convs.emplace_back();
+        rc = build_conv(ctx, net->convs.back(), t[idx + 2], t[idx + 3], t[idx + 8], t[idx + 9], t[idx + 10], t[idx + 11], F, F, F, 0, 128);
         if (rc != DIEE_OK) return rc;
-        net->convs.push_back(c1);
-        net->convs.push_back(c2);
         idx += 12;
     }
     rc = build_conv(ctx, net->pconv, t[idx], t[idx + 1], t[idx + 2], t[idx + 3], t[idx + 4], t[idx + 5], 32, F, 32, 0, 32);
@@ -281,9 +300,10 @@ int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *t,
         net->bv = t[idx + 15][0];
     }
     (void)bf16_round;
-    *out = net;
     return DIEE_OK;
 }
+
+extern "C" {
 
 int32_t diee_net_destroy(diee_ctx *ctx, diee_net *net) {
     if (!ctx || !net) return DIEE_ERR_INVALID;

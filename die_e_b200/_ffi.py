@@ -32,7 +32,11 @@ ANODE = np.dtype([("parent", "i4"), ("first_child", "i4"), ("n_children", "i4"),
                   ("prior", "f4"), ("action", MOVE), ("state", BG_STATE)])
 TRAJ = np.dtype([("state", BG_STATE), ("game_id", "u4"), ("ply", "u2"), ("outcome", "i1"), ("pad", "u1"),
                  ("n_pi", "u2"), ("pad2", "u2"), ("pi_offset", "u4")])
-assert ANODE.itemsize == 60 and TRAJ.itemsize == 48
+SELFPLAY_OPTS = np.dtype([("flags", "u4"), ("max_waves", "i4"), ("leaves_per_game", "i4"), ("target_games", "i4"),
+                          ("virtual_loss", "f4"), ("pad", "u4")])
+SELFPLAY_REPORT = np.dtype([("waves", "i4"), ("games_finished", "i4"), ("games_cut", "i4"), ("pad", "i4"), ("game_moves", "u8")])
+SP_REFILL = 1
+assert ANODE.itemsize == 60 and TRAJ.itemsize == 48 and SELFPLAY_OPTS.itemsize == 24 and SELFPLAY_REPORT.itemsize == 24
 assert SEARCH_STATS.itemsize == 24
 assert BG_STATE.itemsize == 32 and MOVE.itemsize == 4 and TTT_STATE.itemsize == 16 and NODE.itemsize == 24
 
@@ -44,8 +48,8 @@ SYMBOLS = [
     "diee_bg_playout", "diee_bg_playout_dev", "diee_bg_encode_moves", "diee_bg_decode_moves",
     "diee_bg_encode_states", "diee_bg_encode_states_dev", "diee_mcts_search", "diee_mcts_search_dev",
     "diee_net_create", "diee_net_destroy", "diee_net_set_precision", "diee_net_param_count", "diee_net_forward", "diee_net_forward_dev",
-    "diee_search_timing", "diee_comm_unique_id", "diee_comm_init", "diee_comm_destroy", "diee_traj_allgather",
-    "diee_net_broadcast", "diee_dirichlet", "diee_alpha_search", "diee_alpha_search_dev", "diee_selfplay_run", "diee_net_eval_count",
+    "diee_search_timing", "diee_search_work", "diee_comm_unique_id", "diee_comm_init", "diee_comm_destroy", "diee_traj_allgather",
+    "diee_net_broadcast", "diee_dirichlet", "diee_alpha_search", "diee_alpha_search_dev", "diee_selfplay_run", "diee_selfplay_run_ex", "diee_net_eval_count",
 ]
 
 
@@ -180,6 +184,12 @@ class Context:
         self._chk(lib().diee_search_timing(self._h, C.byref(a), C.byref(b)))
         return float(a.value), float(b.value)
 
+    def search_work(self):
+        """plies the rollouts of the last backgammon search actually played (closed-form tails excluded)"""
+        n = C.c_uint64(0)
+        self._chk(lib().diee_search_work(self._h, C.byref(n)))
+        return int(n.value)
+
     # ---- env, host buffers ----
     def bg_valid_moves(self, states, want_ids=False):
         states = np.ascontiguousarray(states, dtype=BG_STATE).reshape(-1)
@@ -283,6 +293,26 @@ class Context:
         self._chk(lib().diee_alpha_search_dev(self._h, net._h, _p(d_states), C.c_int32(n), _p(d_ids), _p(cfg), C.c_uint64(seed),
                                               C.c_uint32(epoch), C.c_int32(max_nodes), _p(d_root_ids), _p(d_root_moves),
                                               _p(d_root_visits), _p(d_root_counts), _p(d_status)))
+
+    def selfplay_run_ex(self, net, n_games, cfg, temperature, seed, first_game_id=0, max_nodes=0, rec_cap=None, pi_cap=None,
+                        max_waves=0, flags=0, leaves_per_game=0, target_games=0, virtual_loss=0.0):
+        """diee_selfplay_run_ex: (records, pi ids, pi values, report); see include/diee.h for the options"""
+        cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]
+        limit = int(cfg["simulate_round_limit"][0])
+        opts = np.zeros(1, dtype=SELFPLAY_OPTS)
+        opts[0] = (flags, max_waves, leaves_per_game, target_games, virtual_loss, 0)
+        rec_cap = rec_cap or max(n_games, target_games) * (2 * limit + 4)
+        pi_cap = pi_cap or rec_cap * 48
+        rec = np.zeros(rec_cap, dtype=TRAJ)
+        pi_ids = np.zeros(pi_cap, dtype=np.uint16)
+        pi_vals = np.zeros(pi_cap, dtype=np.float32)
+        rep = np.zeros(1, dtype=SELFPLAY_REPORT)
+        n_rec, n_pi, n_waves = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._chk(lib().diee_selfplay_run_ex(self._h, net._h, C.c_int32(n_games), _p(cfg), C.c_float(temperature), C.c_uint64(seed),
+                                             C.c_uint32(first_game_id), C.c_int32(max_nodes), _p(opts), _p(rec), C.c_int32(rec_cap),
+                                             _p(pi_ids), _p(pi_vals), C.c_int32(pi_cap), C.byref(n_rec), C.byref(n_pi),
+                                             C.byref(n_waves), _p(rep)))
+        return rec[: n_rec.value], pi_ids[: n_pi.value], pi_vals[: n_pi.value], rep[0]
 
     def selfplay_run(self, net, n_games, cfg, temperature, seed, first_game_id=0, max_nodes=0, rec_cap=None, pi_cap=None):
         cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]

@@ -226,8 +226,21 @@ int32_t diee_selfplay_run(diee_ctx *ctx, diee_net *net, int32_t n_games, const d
                           uint64_t seed, uint32_t first_game_id, int32_t max_nodes, diee_traj_record *rec_out, int32_t rec_cap,
                           uint16_t *pi_ids_out, float *pi_vals_out, int32_t pi_cap, int32_t *n_rec_out, int32_t *n_pi_out,
                           int32_t *n_waves_out) {
+    return diee_selfplay_run_ex(ctx, net, n_games, cfg, temperature, seed, first_game_id, max_nodes, nullptr, rec_out, rec_cap,
+                                pi_ids_out, pi_vals_out, pi_cap, n_rec_out, n_pi_out, n_waves_out, nullptr);
+}
+
+int32_t diee_selfplay_run_ex(diee_ctx *ctx, diee_net *net, int32_t n_games, const diee_mcts_cfg *cfg, float temperature,
+                             uint64_t seed, uint32_t first_game_id, int32_t max_nodes, const diee_selfplay_opts *opts,
+                             diee_traj_record *rec_out, int32_t rec_cap, uint16_t *pi_ids_out, float *pi_vals_out, int32_t pi_cap,
+                             int32_t *n_rec_out, int32_t *n_pi_out, int32_t *n_waves_out, diee_selfplay_report *report_out) {
     int32_t rc = check_alpha_args(ctx, net, n_games, cfg, 0);
     if (rc != DIEE_OK) return rc;
+    diee_selfplay_opts o{};
+    if (opts) o = *opts;
+    if (o.max_waves < 0 || o.flags != 0 || o.leaves_per_game > 1 || o.target_games != 0)
+        return fail(ctx, DIEE_ERR_INVALID, "selfplay_run_ex: unsupported option");
+    diee_selfplay_report rep{};
     if (!rec_out || !pi_ids_out || !pi_vals_out || !n_rec_out || !n_pi_out || !(temperature > 0.f))
         return fail(ctx, DIEE_ERR_INVALID, "selfplay_run: bad argument");
     *n_rec_out = 0; *n_pi_out = 0;
@@ -292,6 +305,17 @@ int32_t diee_selfplay_run(diee_ctx *ctx, diee_net *net, int32_t n_games, const d
         for (int g = 0; g < N; ++g)
             if (alive[g]) { live[nl] = state[g]; ids[nl] = first_game_id + (uint32_t)g; idx_of[nl] = g; ++nl; }
         if (nl == 0) break;
+        if (o.max_waves > 0 && waves >= o.max_waves) {
+            // time box: the games still running hand over what they have recorded so far, outcome 0 (not a reference
+            // behaviour: a bounded sample of the same work for benchmarks)
+            for (int g = 0; g < N; ++g)
+                if (alive[g]) {
+                    if (!emit(g, false, 0, (int)mem[g].size())) return fail(ctx, DIEE_ERR_OVERFLOW, "selfplay_run: record buffers too small");
+                    rep.games_cut += 1;
+                }
+            break;
+        }
+        rep.game_moves += (uint64_t)nl;
         CU(cudaMemcpyAsync(ctx->a_states_in.p, live.data(), sizeof(diee_bg_state) * (size_t)nl, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ctx->a_ids_in.p, ids.data(), 4 * (size_t)nl, cudaMemcpyHostToDevice, st));
         AlphaPool P;
@@ -386,11 +410,14 @@ int32_t diee_selfplay_run(diee_ctx *ctx, diee_net *net, int32_t n_games, const d
             if (win != 0) {  // :215-223
                 if (!emit(g, true, win, (int)mem[g].size())) return fail(ctx, DIEE_ERR_OVERFLOW, "selfplay_run: record buffers too small");
                 alive[g] = 0;
+                rep.games_finished += 1;
             }
         }
     }
     *n_rec_out = n_rec; *n_pi_out = n_pi;
     if (n_waves_out) *n_waves_out = waves;
+    rep.waves = waves;
+    if (report_out) *report_out = rep;
     return DIEE_OK;
 }
 

@@ -117,6 +117,19 @@ int32_t diee_search_timing(diee_ctx *ctx, float *tree_ms, float *rollout_ms) {
     return DIEE_OK;
 }
 
+// plies the rollouts of the last split backgammon search actually PLAYED (lane_run_kernel counts them; the plies a
+// reference-exact rollout spends passing after both sides have collected everything are resolved in closed form)
+int32_t diee_search_work(diee_ctx *ctx, uint64_t *rollout_plies_played) {
+    if (!ctx || !rollout_plies_played) return DIEE_ERR_INVALID;
+    if (!ctx->q_head.p) return fail(ctx, DIEE_ERR_INVALID, "search_work: no search has run on this context");
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long h[8];
+    CU(cudaMemcpyAsync(h, ctx->q_head.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *rollout_plies_played = h[1] + h[3] + h[5] + h[7];
+    return DIEE_OK;
+}
+
 const char *diee_last_error(const diee_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 int64_t diee_launch_count(const diee_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
@@ -367,6 +380,7 @@ static int32_t mcts_search_dev_impl(diee_ctx *ctx, int32_t game_kind, const void
                 (int32_t *)ctx->p_simnode.p, ctx->p_finals.p,
                 PbTable{(const uint32_t *)ctx->pb_index.p, (const uint16_t *)ctx->pb_plays.p}};
     RESERVE(ctx->q_head, sizeof(unsigned long long) * 8);
+    CU(cudaMemsetAsync(ctx->q_head.p, 0, sizeof(unsigned long long) * 8, ctx->stream));
     SearchPipe pipe;
     for (int i = 0; i < SEARCH_SLICES; ++i) { pipe.side[i] = ctx->side[i]; pipe.tree_done[i] = ctx->ev_tree[i]; pipe.roll_done[i] = ctx->ev_roll[i]; }
     pipe.queue_heads = (unsigned long long *)ctx->q_head.p;

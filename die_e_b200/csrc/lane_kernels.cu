@@ -51,7 +51,7 @@ struct LaneJob {
     int reps;                      // scheduling: plies a lane may play on one vote while it stays on the same path
     int store_min;                 // scheduling: lanes that must wait to write a result / take an item before it happens
     int lag_weight;                // scheduling: how much one step of waiting counts against one more waiting lane
-    unsigned long long *next_item; // job queue head (zeroed before the launch)
+    unsigned long long *next_item; // job queue head (zeroed before the launch); next_item[1] counts the plies PLAYED
     PbTable pb;                    // pure bear-off play table
     const diee_bg_state *states;   // PLAYOUT: starts[n]; ROLLOUT: node pool states
     const int32_t *sim_node;       // ROLLOUT: node each simulation rolls out from, or -1
@@ -170,6 +170,11 @@ lane_run_kernel(LaneJob job) {
         if (need != best) { ++age; continue; }
         age = 0;
         if (best == PATH_STORE) {
+            {   // plies this job actually played (the closed-form tail below is not work): one atomic per storing batch
+                const uint32_t act = __activemask();
+                const uint32_t sum = __reduce_add_sync(act, k);
+                if (lane == (int)(__ffs(act) - 1)) atomicAdd(job.next_item + 1, (unsigned long long)sum);
+            }
             if (ROLLOUT) {
                 if (k < job.limit) {
                     // both sides have collected everything: the remaining plies are skip_turns, i.e. the side to
@@ -265,7 +270,7 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
     job.store_min = force_store_min > 0 ? force_store_min : (refilled ? 24 : 8);
     long long blocks = (job.n_items + LANE_CTA - 1) / LANE_CTA;
     if (blocks > (long long)sms * bps) blocks = (long long)sms * bps;
-    cudaError_t e = cudaMemsetAsync(job.next_item, 0, sizeof(unsigned long long), st);
+    cudaError_t e = cudaMemsetAsync(job.next_item, 0, 2 * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     lane_run_kernel<ROLLOUT><<<(unsigned)blocks, LANE_CTA, 0, st>>>(job);
     if (launches) *launches += 1;

@@ -627,7 +627,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if ((e = cudaEventRecord(pipe.tree_done[s], st)) != cudaSuccess) return e;
             if ((e = cudaStreamWaitEvent(pipe.side[s], pipe.tree_done[s], 0)) != cudaSuccess) return e;
-            if ((e = launch_bg_rollouts(pipe.side[s], n, cfg, a, b, seed, first_game_id, epoch, pp, pipe.queue_heads + s, launches)) != cudaSuccess) return e;
+            if ((e = launch_bg_rollouts(pipe.side[s], n, cfg, a, b, seed, first_game_id, epoch, pp, pipe.queue_heads + 2 * s, launches)) != cudaSuccess) return e;
             if ((e = cudaEventRecord(pipe.roll_done[s], pipe.side[s])) != cudaSuccess) return e;
         }
         for (uint32_t s = 0; s < slices; ++s)

@@ -204,6 +204,10 @@ int32_t diee_mcts_search_dev(diee_ctx *ctx, int32_t game_kind, const void *state
 /* CUDA-event durations of the two kernels of the last reference-exact backgammon search on this context
  * (tree kernel | all rollouts), for the roofline line of bench.py.  Waits for that search to finish. */
 int32_t diee_search_timing(diee_ctx *ctx, float *tree_ms, float *rollout_ms);
+/* plies the rollouts of the last backgammon search on this context actually PLAYED.  (A reference-exact rollout runs
+ * `simulate_round_limit` plies whatever happens -- quirk Q5 --, but once both sides have collected all 15 checkers the rest
+ * are forced passes and the final state is written in closed form: those plies are not executed and not counted.) */
+int32_t diee_search_work(diee_ctx *ctx, uint64_t *rollout_plies_played);
 
 /* ---- policy/value net: ResNet (alphazero/nnet.rs:57-155), inference only ----
  * Architecture (backgammon): conv3x3(6->F)+BN+ReLU, `blocks` x [conv+BN+ReLU+conv+BN+add+ReLU],
@@ -281,6 +285,27 @@ int32_t diee_selfplay_run(diee_ctx *ctx, diee_net *net, int32_t n_games, const d
                           uint64_t seed, uint32_t first_game_id, int32_t max_nodes, diee_traj_record *rec_out, int32_t rec_cap,
                           uint16_t *pi_ids_out, float *pi_vals_out, int32_t pi_cap, int32_t *n_rec_out, int32_t *n_pi_out,
                           int32_t *n_waves_out);
+/* The same driver with options (all zero / NULL = diee_selfplay_run).  max_waves > 0 time-boxes the run: after that
+ * many game-move waves the games still running emit what they have recorded with outcome 0 (a bounded sample of the
+ * same work for benchmarks; not a reference behaviour).  The other fields select the NON-PARITY throughput modes of
+ * SURVEY 8(f)4 and must be 0 unless the library says it supports them (DIEE_ERR_INVALID otherwise). */
+typedef struct {
+    uint32_t flags;          /* DIEE_SP_* */
+    int32_t max_waves;       /* 0 = until every game has ended */
+    int32_t leaves_per_game; /* 0/1 = one leaf per game and iteration, as the reference (alpha_mcts.rs:149-201) */
+    int32_t target_games;    /* DIEE_SP_REFILL: stop once this many games have finished */
+    float virtual_loss;      /* leaves_per_game > 1 */
+    uint32_t pad;
+} diee_selfplay_opts;
+#define DIEE_SP_REFILL 1u /* a finished game's slot starts a new game, so the forward batch stays at n_games */
+typedef struct {
+    int32_t waves, games_finished, games_cut, pad;
+    uint64_t game_moves; /* searches run: one per live game and wave */
+} diee_selfplay_report;
+int32_t diee_selfplay_run_ex(diee_ctx *ctx, diee_net *net, int32_t n_games, const diee_mcts_cfg *cfg, float temperature,
+                             uint64_t seed, uint32_t first_game_id, int32_t max_nodes, const diee_selfplay_opts *opts,
+                             diee_traj_record *rec_out, int32_t rec_cap, uint16_t *pi_ids_out, float *pi_vals_out, int32_t pi_cap,
+                             int32_t *n_rec_out, int32_t *n_pi_out, int32_t *n_waves_out, diee_selfplay_report *report_out);
 uint64_t diee_net_eval_count(const diee_ctx *ctx);
 
 /* ---- multi-GPU: the one exchange step of the path ----

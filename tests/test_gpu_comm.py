@@ -53,6 +53,15 @@ def _worker(rank, world, uid, q):
             raise AssertionError("expected an overflow")
         except _ffi.DieeError as err:
             assert err.code == _ffi.ERR_OVERFLOW
+        # the verdict is COLLECTIVE: only rank 0's buffers are too small, yet BOTH ranks get the overflow and nobody is left
+        # waiting inside the payload all-gather (round-1 advisor finding); the communicator stays usable afterwards
+        try:
+            ctx.traj_allgather(rec, ids, vals, rec_cap=10 if rank == 0 else 100, pi_cap=1000)
+            raise AssertionError("expected an overflow on both ranks")
+        except _ffi.DieeError as err:
+            assert err.code == _ffi.ERR_OVERFLOW
+        again = ctx.traj_allgather(rec, ids, vals, rec_cap=100, pi_cap=1000)
+        assert len(again[0]) == sum(sizes)
         # weights: everybody ends up with rank 1's tensors
         tens = [np.full(7, float(rank), np.float32), np.arange(12, dtype=np.float32).reshape(3, 4) * (rank + 1)]
         ctx.net_broadcast(tens, root=1)

@@ -130,7 +130,7 @@ def initial_states(ffi, first_gid, n):
 
 def midgame_states(ctx, ffi, first_gid, n):
     """SURVEY 8(d) M-inputs: game g advanced k plies of random play, k = 10*(g % 9) in 0..80 (made with
-    the product's own playout kernel; never terminal this early -- the shortest game is ~40 plies).
+    the product's own playout kernel); the few games per thousand that are already over by then keep their opening roll.
     host_states_for_reference() makes the same states with the oracle; parity_check compares the two."""
     s = initial_states(ffi, first_gid, n)
     out = s.copy()
@@ -159,11 +159,13 @@ def host_states_for_reference(args, first_gid=0, n=None, midgame=None):
         w = orc.philox(SEED, 0, first_gid + g, orc.STREAM_INIT, 0)
         s["roll"][g] = (orc.die(w[0]), orc.die(w[1]))
     if (args.workload in ("mcts", "alpha", "selfplay")) if midgame is None else midgame:
+        start = s.copy()
         for g in range(G):
             for ply in range(10 * ((first_gid + g) % 9)):
-                if orc.bg_check_winner(s[g:g + 1]) is not None:
-                    break
                 orc.bg_random_ply(s[g:g + 1], orc.philox(SEED, ply, first_gid + g, orc.STREAM_GAME, 0))
+                if orc.bg_check_winner(s[g:g + 1]) is not None:
+                    s[g] = start[g]  # a game that is over this early (a few per thousand) searches from its opening roll instead
+                    break
     return s
 
 

@@ -69,7 +69,7 @@ int32_t diee_ctx_destroy(diee_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->s_states, &ctx->s_moves, &ctx->s_counts, &ctx->s_ids, &ctx->s_aux, &ctx->s_out,
                       &ctx->s_players, &ctx->s_best, &ctx->s_status, &ctx->s_plies, &ctx->p_states, &ctx->p_parent,
-                      &ctx->p_visits, &ctx->p_value, &ctx->p_action, &ctx->p_nmoves, &ctx->p_nnodes, &ctx->p_simnode, &ctx->p_finals,
+                      &ctx->p_visits, &ctx->p_value, &ctx->p_action, &ctx->p_nmoves, &ctx->p_nnodes, &ctx->p_simnode, &ctx->p_finals, &ctx->p_result,
                       &ctx->ln_table, &ctx->a_state, &ctx->a_parent, &ctx->a_first, &ctx->a_nchild, &ctx->a_visits, &ctx->a_value,
                       &ctx->a_prior, &ctx->a_action, &ctx->a_nnodes, &ctx->a_selg, &ctx->a_seln, &ctx->a_status, &ctx->a_any,
                       &ctx->a_batch, &ctx->a_policy, &ctx->a_valueout, &ctx->a_dir, &ctx->a_states_in, &ctx->a_ids_in,
@@ -234,6 +234,7 @@ int32_t diee_bg_playout_dev(diee_ctx *ctx, const diee_bg_state *starts, int32_t 
     if (n == 0) return DIEE_OK;
     int nl = 0;
     RESERVE(ctx->q_head, sizeof(unsigned long long) * 8);
+    CU(cudaMemsetAsync(ctx->q_head.p, 0, sizeof(unsigned long long) * 8, ctx->stream));
     CU(launch_bg_playout(ctx->stream, starts, n, seed, first_game_id, round_limit, winners_out, plies_out, finals_out,
                          (unsigned long long *)ctx->q_head.p, PbTable{(const uint32_t *)ctx->pb_index.p, (const uint16_t *)ctx->pb_plays.p}, &nl));
     ctx->launches += nl;
@@ -339,6 +340,7 @@ static int32_t ensure_pool(diee_ctx *ctx, int game_kind, int n, const diee_mcts_
     RESERVE(ctx->p_nnodes, sizeof(int32_t) * (size_t)n);
     RESERVE(ctx->p_simnode, sizeof(int32_t) * (size_t)cfg->iterations * (size_t)n);
     RESERVE(ctx->p_finals, state_size(game_kind) * (size_t)cfg->iterations * (size_t)n);
+    RESERVE(ctx->p_result, sizeof(float) * (size_t)n);
     if (ctx->ln_table_n < cfg->iterations + 2) {
         // ln of every possible (integer-valued) visit count, correctly rounded from double:
         // the contract's replacement for f32::ln (node.rs:91)
@@ -378,7 +380,7 @@ static int32_t mcts_search_dev_impl(diee_ctx *ctx, int32_t game_kind, const void
     PoolPtrs pp{ctx->p_states.p, (int32_t *)ctx->p_parent.p, (float *)ctx->p_visits.p, (float *)ctx->p_value.p,
                 (uint32_t *)ctx->p_action.p, (uint32_t *)ctx->p_nmoves.p, (int32_t *)ctx->p_nnodes.p,
                 (int32_t *)ctx->p_simnode.p, ctx->p_finals.p,
-                PbTable{(const uint32_t *)ctx->pb_index.p, (const uint16_t *)ctx->pb_plays.p}};
+                PbTable{(const uint32_t *)ctx->pb_index.p, (const uint16_t *)ctx->pb_plays.p}, (float *)ctx->p_result.p};
     RESERVE(ctx->q_head, sizeof(unsigned long long) * 8);
     CU(cudaMemsetAsync(ctx->q_head.p, 0, sizeof(unsigned long long) * 8, ctx->stream));
     SearchPipe pipe;

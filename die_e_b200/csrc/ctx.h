@@ -23,7 +23,7 @@ struct diee_ctx {
     // scratch for host-buffer entry points
     DevBuf s_states, s_moves, s_counts, s_ids, s_aux, s_out, s_players, s_best, s_status, s_plies;
     // pure-MCTS node pool (HBM resident, reused between searches)
-    DevBuf p_states, p_parent, p_visits, p_value, p_action, p_nmoves, p_nnodes, p_simnode, p_finals, ln_table;
+    DevBuf p_states, p_parent, p_visits, p_value, p_action, p_nmoves, p_nnodes, p_simnode, p_finals, p_result, ln_table;
     uint32_t ln_table_n = 0;
     DevBuf pb_index, pb_plays;  // pure bear-off play table (bg_pb_table.h)
     DevBuf q_head;  // job queue heads of the persistent lane kernel (lane_kernels.cu)

@@ -1,8 +1,11 @@
 // lane_kernels.cu -- one LANE per game: the throughput kernels of the path.
 //
-//   lane_run_kernel<false>   C2: whole random-vs-random games
-//   lane_run_kernel<true>    T4: every deferred Node::simulate of a split search (node.rs:176-196),
-//                            one lane per (game, iteration)
+//   lane_run_kernel<LANE_PLAYOUT>   C2: whole random-vs-random games
+//   lane_run_kernel<LANE_ROLLOUT>   T4: every deferred Node::simulate of a split search (node.rs:176-196),
+//                                   one lane per (game, iteration); reference-exact rollouts (quirk Q5)
+//   lane_run_kernel<LANE_ROLLOUT_CC> T4 with DIEE_MODE_ROLLOUT_CHECK_CURRENT: the rollouts of ONE iteration of a lock-step
+//                                   search, one lane per game; the rollout stops at a winner and its result goes back
+//                                   to the tree kernel of the next iteration
 //
 // A ply is get_valid_moves -> uniform choice -> apply_move | skip_turn.  The board lives in the lane's
 // registers as bit planes (bg_lane.cuh).  Contact plies touch no memory at all (closed forms); pure bear-off
@@ -40,6 +43,8 @@ __device__ __forceinline__ void lane_store_state(const LaneBoard &g, diee_bg_sta
 __device__ unsigned long long g_lane_stats[16];  // [p] = steps executed on path p, [8+p] = lanes advanced
 #endif
 
+enum { LANE_PLAYOUT = 0, LANE_ROLLOUT = 1, LANE_ROLLOUT_CC = 2 };
+
 struct LaneJob {
     // PLAYOUT (C2): item = game index; ROLLOUT (T4): item = game * iterations + iteration
     long long n_items;
@@ -58,6 +63,11 @@ struct LaneJob {
     diee_bg_state *finals;         // PLAYOUT: nullable
     int8_t *winners;               // PLAYOUT
     int32_t *plies;                // PLAYOUT
+    // ROLLOUT_CC (lock-step search): item = game (first_item + item), one iteration per launch
+    uint32_t first_item;           // first game of this launch's group
+    const int8_t *players;         // the player each game's search counts the value for
+    float *results;                // [game]: Node::simulate's return value (node.rs:182-185,195)
+    diee_search_stats *stats;      // [game]: rollout_plies += plies played (nullable)
 };
 
 // The code path the next ply of a game needs.  A warp runs ONE path per step, for all its lanes that
@@ -90,9 +100,11 @@ __device__ __forceinline__ int lane_path(const LaneBoard &g) {
 // wins, lanes that have waited long counting extra so that nobody starves; the warp executes THAT path
 // once, for the lanes waiting on it, and they move on to their next ply.  Divergence between code paths
 // is thereby turned into batching.
-template <bool ROLLOUT>
+template <int MODE>
 __global__ void __launch_bounds__(LANE_CTA)
 lane_run_kernel(LaneJob job) {
+    constexpr bool ROLLOUT = MODE != LANE_PLAYOUT;   // plays on the ROLLOUT stream from a node of the pool
+    constexpr bool CC = MODE == LANE_ROLLOUT_CC;     // stops at a winner (of the rolled-out state) and reports the result
     __shared__ uint32_t scratch[L_SCRATCH][LANE_CTA];
     uint32_t *scr = &scratch[0][threadIdx.x];
     const int lane = threadIdx.x & 31;
@@ -118,7 +130,16 @@ lane_run_kernel(LaneJob job) {
                 if (item >= job.n_items) item = -1;
                 if (item >= 0) {
                     k = 0;
-                    if (ROLLOUT) {
+                    if (CC) {
+                        const uint32_t gm = job.first_item + (uint32_t)item;
+                        item = (long long)gm * job.iterations + job.it_begin;
+                        const int node = job.sim_node[item];
+                        if (node >= 0) {  // node < 0: nothing was deferred for this game in this iteration
+                            lane_load_state(g, job.states + (size_t)gm * (job.iterations + 1) + node);
+                            gid = job.first_game_id + gm; c3 = (job.epoch << 16) | (job.it_begin & 0xFFFFu);
+                            need = (l_winner(g) != 0 || job.limit == 0) ? PATH_STORE : lane_path(g);
+                        }
+                    } else if (ROLLOUT) {
                         const uint32_t gm = (uint32_t)(item / job.it_count);
                         const uint32_t it = job.it_begin + (uint32_t)(item - (long long)gm * job.it_count);
                         item = (long long)gm * job.iterations + it;  // from here on: the (game, iteration) pair
@@ -175,7 +196,15 @@ lane_run_kernel(LaneJob job) {
                 const uint32_t sum = __reduce_add_sync(act, k);
                 if (lane == (int)(__ffs(act) - 1)) atomicAdd(job.next_item + 1, (unsigned long long)sum);
             }
-            if (ROLLOUT) {
+            if (CC) {
+                // node.rs:181-185 on the rolled-out state: a winner met BEFORE ply `limit` decides; at the cap the
+                // result is 0 whatever the last ply did (the loop ends without another test)
+                const uint32_t gm = (uint32_t)(item / job.iterations);
+                const int w = k < job.limit ? l_winner(g) : 0, pl = job.players[gm];
+                job.results[gm] = w == 0 ? 0.f : (w == pl ? 1.f : (w == -pl ? -1.f : 0.f));
+                if (job.stats) job.stats[gm].rollout_plies += k;
+                lane_store_state(g, job.finals + item);
+            } else if (ROLLOUT) {
                 if (k < job.limit) {
                     // both sides have collected everything: the remaining plies are skip_turns, i.e. the side to
                     // move alternates and the dice shown at the end are those of the last ply
@@ -225,7 +254,7 @@ lane_run_kernel(LaneJob job) {
         ++k;
 
         // ---- what next ----
-        if (ROLLOUT) need = (k == job.limit || (g.off_own == 15 && g.off_opp == 15)) ? PATH_STORE : lane_path(g);
+        if (ROLLOUT && !CC) need = (k == job.limit || (g.off_own == 15 && g.off_opp == 15)) ? PATH_STORE : lane_path(g);
         else need = (k == job.limit || l_winner(g) != 0) ? PATH_STORE : lane_path(g);
         if (need != best) break;
         }
@@ -242,7 +271,7 @@ __global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32
     stats_out[gm].rollout_plies += c;
 }
 
-template <bool ROLLOUT>
+template <int MODE>
 static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) {
     // tuning knobs, read once: waiting-time weight of the vote and resident CTAs (x 2 warps) per SM.  Measured on B200 with
     // 102,400 rollouts: 10 CTAs of 64 lanes per SM and weight 0 are best.
@@ -270,9 +299,10 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
     job.store_min = force_store_min > 0 ? force_store_min : (refilled ? 24 : 8);
     long long blocks = (job.n_items + LANE_CTA - 1) / LANE_CTA;
     if (blocks > (long long)sms * bps) blocks = (long long)sms * bps;
-    cudaError_t e = cudaMemsetAsync(job.next_item, 0, 2 * sizeof(unsigned long long), st);
+    // (the head only: next_item[1], the played-plies counter, is zeroed once per search / playout call by the caller)
+    cudaError_t e = cudaMemsetAsync(job.next_item, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    lane_run_kernel<ROLLOUT><<<(unsigned)blocks, LANE_CTA, 0, st>>>(job);
+    lane_run_kernel<MODE><<<(unsigned)blocks, LANE_CTA, 0, st>>>(job);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -286,7 +316,7 @@ cudaError_t launch_bg_playout(cudaStream_t st, const diee_bg_state *starts, int 
     job.pb = pb;
     job.n_items = n; job.limit = (uint32_t)round_limit; job.seed = seed; job.first_game_id = first_game_id;
     job.states = starts; job.finals = finals_out; job.winners = winners_out; job.plies = plies_out;
-    return launch_lane_job<false>(st, job, launches);
+    return launch_lane_job<LANE_PLAYOUT>(st, job, launches);
 }
 
 cudaError_t launch_bg_rollouts(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, uint32_t it_begin, uint32_t it_end,
@@ -301,7 +331,23 @@ cudaError_t launch_bg_rollouts(cudaStream_t st, int n_games, const diee_mcts_cfg
     job.finals = static_cast<diee_bg_state *>(pp.finals);
     job.next_item = queue_head;
     job.pb = pp.pb;
-    return launch_lane_job<true>(st, job, launches);
+    return launch_lane_job<LANE_ROLLOUT>(st, job, launches);
+}
+
+// the rollouts of iteration `it` of a lock-step search (DIEE_MODE_ROLLOUT_CHECK_CURRENT) for games [g0, g0 + n_games)
+cudaError_t launch_bg_rollouts_cc(cudaStream_t st, int g0, int n_games, const diee_mcts_cfg &cfg, uint32_t it, uint64_t seed,
+                                  uint32_t first_game_id, uint32_t epoch, const PoolPtrs &pp, const int8_t *players, float *results,
+                                  diee_search_stats *stats, unsigned long long *queue_head, int *launches) {
+    if (n_games <= 0 || cfg.simulate_round_limit == 0) return cudaSuccess;
+    LaneJob job{};
+    job.n_items = n_games; job.iterations = cfg.iterations; job.it_begin = it; job.it_count = 1;
+    job.limit = cfg.simulate_round_limit; job.seed = seed; job.first_game_id = first_game_id; job.epoch = epoch;
+    job.states = static_cast<const diee_bg_state *>(pp.states); job.sim_node = pp.sim_node;
+    job.finals = static_cast<diee_bg_state *>(pp.finals);
+    job.next_item = queue_head;
+    job.pb = pp.pb;
+    job.first_item = (uint32_t)g0; job.players = players; job.results = results; job.stats = stats;
+    return launch_lane_job<LANE_ROLLOUT_CC>(st, job, launches);
 }
 
 cudaError_t launch_bg_rollout_count(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, const PoolPtrs &pp,

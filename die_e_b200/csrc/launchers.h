@@ -23,6 +23,7 @@ struct PoolPtrs {
     int32_t *sim_node;
     void *finals;
     PbTable pb;
+    float *roll_result;  // [game]: result of the game's pending rollout (lock-step search)
 };
 
 // side streams of a split search: rollouts of one slice of iterations run beside the tree kernel of the next
@@ -45,6 +46,10 @@ cudaError_t launch_bg_playout(cudaStream_t st, const diee_bg_state *starts, int 
 cudaError_t launch_bg_rollouts(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, uint32_t it_begin, uint32_t it_end,
                                uint64_t seed, uint32_t first_game_id, uint32_t epoch, const PoolPtrs &pp,
                                unsigned long long *queue_head, int *launches);
+// lock-step search (rollouts that test the rolled-out state): the rollouts of ONE iteration, one lane per game
+cudaError_t launch_bg_rollouts_cc(cudaStream_t st, int g0, int n_games, const diee_mcts_cfg &cfg, uint32_t it, uint64_t seed,
+                                  uint32_t first_game_id, uint32_t epoch, const PoolPtrs &pp, const int8_t *players, float *results,
+                                  diee_search_stats *stats, unsigned long long *queue_head, int *launches);
 cudaError_t launch_bg_rollout_count(cudaStream_t st, int n_games, const diee_mcts_cfg &cfg, const PoolPtrs &pp,
                                     diee_search_stats *stats_out, int *launches);
 cudaError_t launch_bg_encode_moves(cudaStream_t st, const diee_bg_state *states, const diee_move *moves, int n, uint16_t *ids_out);

@@ -190,7 +190,16 @@ struct Pool {
     int32_t *sim_node; // [game][iteration]: node whose rollout the rollout kernel still has to run, or -1
     void *finals;      // [game][iteration]: state each simulation's rollout ended in (zero = no rollout)
     PbTable pb;        // pure bear-off play table (backgammon)
+    float *roll_result; // [game]: result of the rollout the game is waiting for (lock-step search)
 };
+
+// lock-step search: did this iteration defer its rollout (warp-uniform; sim_node[it] was just written by lane 0)
+__device__ __forceinline__ bool sim_node_deferred(const int32_t *sim_node, uint32_t it, int lane) {
+    __syncwarp();
+    int v = 0;
+    if (lane == 0) v = sim_node[it];
+    return __shfl_sync(FULL, v, 0) >= 0;
+}
 
 __device__ __forceinline__ float outcome(int winner, int player) {  // simple_mcts.rs:26-28
     return winner == player ? 1.0f : (winner == -player ? -1.0f : 0.0f);
@@ -225,9 +234,15 @@ __device__ __forceinline__ float rollout_plies(G &game, WarpSlab &slab, int lane
 // tree never depends on it.  The tree kernel then only records which node each simulation rolls
 // out from, and rollout_kernel runs all games x iterations rollouts concurrently (same stream
 // coordinates, so every rollout plays the same plies as in the fused form).
-template <class G, bool SPLIT>
+//
+// LOCK = lock-step search (DIEE_MODE_ROLLOUT_CHECK_CURRENT on the lane engine): the rollout DOES feed the tree, so the
+// search runs as one launch per iteration for all games -- this kernel does back-propagation of the previous
+// iteration's rollout result (pool.roll_result, written by lane_run_kernel<LANE_ROLLOUT_CC>), select and expand, and
+// defers the new rollout to the lane kernel that follows it on the stream; a last launch with it_begin == it_end ==
+// iterations back-propagates the last result and picks the move.  The pool stays in HBM / L2 between launches.
+template <class G, bool SPLIT, bool LOCK = false>
 __global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32)
-mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int8_t *__restrict__ players,
+mcts_search_kernel(const typename G::State *__restrict__ roots, int g0, int n, const int8_t *__restrict__ players,
                    diee_mcts_cfg cfg, uint32_t it_begin, uint32_t it_end, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
                    Pool pool, const float *__restrict__ ln_table, uint32_t *__restrict__ best_out,
                    int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out, bool slab_in_smem,
@@ -237,7 +252,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     // by one over the first iterations of the search, and each pop would otherwise regenerate the root's move set
     __shared__ uint32_t root_plays_all[MCTS_WARPS_PER_CTA][ROOT_PLAYS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int gidx = blockIdx.x * MCTS_WARPS_PER_CTA + wib;
+    const int gidx = g0 + blockIdx.x * MCTS_WARPS_PER_CTA + wib;  // this launch covers games [g0, n)
     if (gidx >= n) return;
     WarpSlab &slab = slabs[wib];
     uint32_t *root_plays = root_plays_all[wib];
@@ -295,7 +310,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
     unsigned long long plies = 0;
     uint32_t sel_levels = 0, sel_children = 0, terminal_leaves = 0;
     bool ovf = false;
-    const bool last_slice = it_end >= cfg.iterations;
+    const bool last_slice = LOCK ? it_begin >= cfg.iterations : it_end >= cfg.iterations;
 
     if (it_begin == 0) {
         game.load(roots + gidx, lane);
@@ -338,8 +353,23 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
         }
     }
 
+    if (LOCK && it_begin > 0 && n_nodes > 0 && status == DIEE_OK) {
+        // ---- backpropagate :96-103 for the rollout the previous launch deferred ----
+        const int leaf = sim_node[it_begin - 1];
+        if (leaf >= 0) {
+            if (lane == 0) {
+                const float result = pool.roll_result[gidx];
+                for (int i = leaf; i >= 0; i = parent[i]) {
+                    visits[i] = __fadd_rn(visits[i], 1.0f);
+                    value[i] = __fadd_rn(value[i], result);
+                }
+            }
+            __syncwarp();
+        }
+    }
     const int first_cached = it_begin == 0 ? 1 : n_nodes;  // nodes created from here on are counted (and cached) by this launch
-    if (n_nodes > 0 && status == DIEE_OK) {
+    const bool root_cache = !LOCK;  // a one-iteration launch pops at most one play of the root
+    if (root_cache && n_nodes > 0 && status == DIEE_OK) {
         const int rootU = (int)(nm[0] >> 16), todo = min((int)(nm[0] & 0xFFFFu), ROOT_PLAYS);  // only untried plays are read
         if (todo > (it_begin == 0 ? 32 : 0)) {
             game.load(st, lane);
@@ -430,7 +460,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                 if (nunt == 0) { status = DIEE_ERR_NO_MOVES_PANIC; break; }  // node.rs:119-121 (Q6)
                 // ---- Node::expand node.rs:118-137: pop the LAST untried move ----
                 uint32_t seq = SEQ_EMPTY;  // stays EMPTY_MOVE for the pass child of a no-move node
-                if (cur == 0 && nunt <= ROOT_PLAYS) seq = root_plays[nunt - 1];
+                if (root_cache && cur == 0 && nunt <= ROOT_PLAYS) seq = root_plays[nunt - 1];
                 else if (cur == counted_node) seq = counted_last;
                 else if (nplays && cur >= first_cached && nmoves - nunt < NODE_PLAYS) seq = nplays[cur * NODE_PLAYS + (nmoves - nunt)];
                 else game.count_and_kth(slab, lane, ovf, nunt - 1, seq);
@@ -457,7 +487,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                 bool deferred = false;
                 if (cfg.simulate_round_limit > 0 && w0 != NO_WINNER) {
                     result = outcome(w0, player);
-                } else if (SPLIT) {
+                } else if (SPLIT || LOCK) {
                     deferred = cfg.simulate_round_limit > 0;
                 } else {
                     result = rollout_plies<G>(game, slab, lane, ovf, cfg, check_current, player, seed, gid,
@@ -466,6 +496,7 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int n, const int
                 if (lane == 0) sim_node[it] = deferred ? child : -1;
                 if (!deferred) game.store(finals + it, lane);  // where the rollout ended
             }
+            if (LOCK && sim_node_deferred(sim_node, it, lane)) { __syncwarp(); continue; }  // back-propagated by the next launch
             // ---- backpropagate :96-103 (no sign flip) ----
             // the path root .. cur was recorded during select, one node per lane; the new child (if any) joins it
             if (leaf != cur) { if (lane == depth) my_path_node = leaf; ++depth; }
@@ -588,9 +619,52 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         if ((e = cudaFuncSetAttribute(mcts_search_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(mcts_search_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
     }
+    if constexpr (std::is_same<G, BgGame>::value) {
+        // Rollouts that test the rolled-out state feed the tree, so they cannot run after it.  Lock-step instead: per
+        // iteration one tree launch for all games (back-propagate the previous result, select, expand) and one lane-engine
+        // launch for their rollouts (lane_run_kernel<LANE_ROLLOUT_CC>, one lane per game).  The games are cut into groups
+        // on side streams so that one group's tree step runs beside another group's rollouts; what bounds a group is its
+        // longest rollout, iteration after iteration, so throughput comes from the batch size.
+        // DIEE_CC_FUSED=1 keeps the round-1 form (the whole search in one launch, warp-per-game rollouts) for comparison.
+        static const bool fused = getenv("DIEE_CC_FUSED") && atoi(getenv("DIEE_CC_FUSED")) != 0;
+        if (!split && !fused && cfg.simulate_round_limit > 0) {
+            int groups = n >= 8192 ? 4 : (n >= 2048 ? 2 : 1);
+            if (const char *ev = getenv("DIEE_CC_GROUPS")) groups = atoi(ev);
+            if (groups < 1) groups = 1;
+            if (groups > SEARCH_SLICES) groups = SEARCH_SLICES;
+            *pipe.timed = false;
+            if (groups > 1) {
+                if ((e = cudaEventRecord(pipe.tree_done[0], st)) != cudaSuccess) return e;
+                for (int gr = 0; gr < groups; ++gr)
+                    if ((e = cudaStreamWaitEvent(pipe.side[gr], pipe.tree_done[0], 0)) != cudaSuccess) return e;
+            }
+            for (uint32_t it = 0; it <= cfg.iterations; ++it) {  // the last pass only back-propagates and picks the moves
+                for (int gr = 0; gr < groups; ++gr) {
+                    const int lo = (int)((long long)n * gr / groups), hi = (int)((long long)n * (gr + 1) / groups);
+                    if (hi <= lo) continue;
+                    cudaStream_t sg = groups > 1 ? pipe.side[gr] : st;
+                    const uint32_t it_end = it < cfg.iterations ? it + 1 : it;
+                    mcts_search_kernel<G, false, true><<<mcts_grid(hi - lo), MCTS_WARPS_PER_CTA * 32, 0, sg>>>(
+                        r, lo, hi, players, cfg, it, it_end, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, false, dump);
+                    *launches += 1;
+                    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+                    if (it < cfg.iterations &&
+                        (e = launch_bg_rollouts_cc(sg, lo, hi - lo, cfg, it, seed, first_game_id, epoch, pp, players, pp.roll_result, stats_out,
+                                                   pipe.queue_heads + 2 * gr, launches)) != cudaSuccess)
+                        return e;
+                }
+            }
+            if (groups > 1)
+                for (int gr = 0; gr < groups; ++gr) {
+                    if ((e = cudaEventRecord(pipe.roll_done[gr], pipe.side[gr])) != cudaSuccess) return e;
+                    if ((e = cudaStreamWaitEvent(st, pipe.roll_done[gr], 0)) != cudaSuccess) return e;
+                }
+            return cudaSuccess;
+        }
+    }
     if (!split) {
         mcts_search_kernel<G, false><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
-            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
+            r, 0, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
         *launches = 1;
         return cudaGetLastError();
     }
@@ -610,7 +684,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         if (slices == 1) {  // everything on the caller's stream, with timing marks around the two kernels
             if ((e = cudaEventRecord(pipe.t_begin, st)) != cudaSuccess) return e;
             mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
-                r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
+                r, 0, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
             *launches += 1;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if ((e = cudaEventRecord(pipe.t_tree, st)) != cudaSuccess) return e;
@@ -622,7 +696,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         for (uint32_t s = 0; s < slices; ++s) {
             const uint32_t a = (uint32_t)((uint64_t)cfg.iterations * s / slices), b = (uint32_t)((uint64_t)cfg.iterations * (s + 1) / slices);
             mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
-                r, n, players, cfg, a, b, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
+                r, 0, n, players, cfg, a, b, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
             *launches += 1;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if ((e = cudaEventRecord(pipe.tree_done[s], st)) != cudaSuccess) return e;
@@ -635,7 +709,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         return launch_bg_rollout_count(st, n, cfg, pp, stats_out, launches);
     } else {
         mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
-            r, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
+            r, 0, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
         const long long pairs = (long long)n * cfg.iterations;
         const long long blocks = (pairs + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA;
         rollout_kernel<G><<<(unsigned)blocks, MCTS_WARPS_PER_CTA * 32, 0, st>>>(n, cfg, seed, first_game_id, epoch, pool, players,
@@ -651,7 +725,7 @@ cudaError_t launch_mcts_search(cudaStream_t st, int game_kind, const void *roots
                                int32_t *status_out, diee_search_stats *stats_out, bool dump, int *launches) {
     *launches = 0;
     if (n <= 0) return cudaSuccess;
-    Pool pool{pp.states, pp.parent, pp.visits, pp.value, pp.action, pp.nmoves, pp.n_nodes, pp.sim_node, pp.finals, pp.pb};
+    Pool pool{pp.states, pp.parent, pp.visits, pp.value, pp.action, pp.nmoves, pp.n_nodes, pp.sim_node, pp.finals, pp.pb, pp.roll_result};
     if (game_kind == DIEE_GAME_BACKGAMMON)
         return launch_typed<BgGame>(st, roots, n, players, cfg, seed, first_game_id, epoch, pool, pp, pipe, ln_table, best_out,
                                     status_out, stats_out, dump, launches);

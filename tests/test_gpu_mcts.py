@@ -136,3 +136,23 @@ def test_sliced_search_is_the_same_search(ctx, oracle, monkeypatch):
         for a, b in zip(ref, got):
             assert np.asarray(a).tobytes() == np.asarray(b).tobytes()
     monkeypatch.delenv("DIEE_SEARCH_SLICES")
+
+
+def test_lockstep_check_current_groups_and_fused_form_agree(ctx, oracle, monkeypatch):
+    """DIEE_MODE_ROLLOUT_CHECK_CURRENT runs lock-step on the lane engine (one tree launch + one rollout launch per
+    iteration, games cut into groups on side streams).  Any number of groups, and the round-1 fused form
+    (DIEE_CC_FUSED=1: one launch, warp-per-game rollouts), must give the same pool, moves and rollout end states."""
+    from die_e_b200 import _ffi
+    states = positions.midgame_positions(seed=29, n=70, max_adv=110)
+    players = states["player"].copy()
+    cfg = oracle.mcts_cfg(iterations=25, c=2.0, limit=400, mode=_ffi.MODE_PASS_CHILD | _ffi.MODE_ROLLOUT_CHECK_CURRENT)
+    ref = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
+    assert (ref[1] == 0).all() and int(ref[2]["rollout_plies"].sum()) > 0
+    for env, val in (("DIEE_CC_GROUPS", "3"), ("DIEE_CC_GROUPS", "4"), ("DIEE_CC_FUSED", "1")):
+        monkeypatch.setenv(env, val)
+        got = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
+        monkeypatch.delenv(env)
+        for k, (a, b) in enumerate(zip(ref, got)):
+            assert np.asarray(a).tobytes() == np.asarray(b).tobytes(), (env, val, k)
+    # and against the oracle, game by game, with the full rollout cap
+    _cmp_trees(oracle, _ffi, ctx, _ffi.GAME_BACKGAMMON, states[:24], players[:24], cfg, 5, 100, 3)

@@ -512,12 +512,16 @@ def run_ours(args, rank, world):
         # Not the headline (`value` is BASELINE configs[2], 1,024 games per GPU); it shows how far the 1,024-game figure
         # is bound by the latency of one game's 100 sequential iterations rather than by issue slots.
         detail["large_batch"] = sub_mcts(ctx, ffi, torch, dev, stream, rank, world, 8192, cfg, reduce_max)
+        detail["large_batch_32768"] = sub_mcts(ctx, ffi, torch, dev, stream, rank, world, 32768, cfg, reduce_max, reps=2)
         # (2) rollouts that test the rolled-out state (the evident intent of node.rs:181, quirk Q5): the mode in which the
         # rollouts decide the search
         cc = np.zeros(1, dtype=ffi.MCTS_CFG)
         cc[0] = (args.iterations, 2.0, args.round_limit, 0.3, 0.25, ffi.MODE_PASS_CHILD | ffi.MODE_ROLLOUT_CHECK_CURRENT)
         detail["check_current"] = {"1024_games": sub_mcts(ctx, ffi, torch, dev, stream, rank, world, 1024, cc, reduce_max, reps=2),
-                                   "16384_games": sub_mcts(ctx, ffi, torch, dev, stream, rank, world, 16384, cc, reduce_max, reps=1)}
+                                   "16384_games": sub_mcts(ctx, ffi, torch, dev, stream, rank, world, 16384, cc, reduce_max, reps=1),
+                                   "65536_games": sub_mcts(ctx, ffi, torch, dev, stream, rank, world, 65536, cc, reduce_max, reps=1),
+                                   "note": "1,024 games: the whole search fused in one launch (warp per game); 16,384 and 65,536 games: "
+                                           "lock-step on the lane engine, one tree launch + one rollout launch per iteration"}
         # (3) configs[3]: AlphaZero search + time-boxed self-play, per net precision that fits the time budget
         detail["alphazero"] = sub_alpha(ctx, ffi, torch, dev, stream, rank, world, args, h_states, reduce_max, reduce_sum, barrier,
                                         dist if world > 1 else None)

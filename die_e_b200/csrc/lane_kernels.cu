@@ -100,8 +100,11 @@ __device__ __forceinline__ int lane_path(const LaneBoard &g) {
 // wins, lanes that have waited long counting extra so that nobody starves; the warp executes THAT path
 // once, for the lanes waiting on it, and they move on to their next ply.  Divergence between code paths
 // is thereby turned into batching.
+#ifndef DIEE_LANE_MIN_BLOCKS
+#define DIEE_LANE_MIN_BLOCKS 1
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(LANE_CTA)
+__global__ void __launch_bounds__(LANE_CTA, DIEE_LANE_MIN_BLOCKS)
 lane_run_kernel(LaneJob job) {
     constexpr bool ROLLOUT = MODE != LANE_PLAYOUT;   // plays on the ROLLOUT stream from a node of the pool
     constexpr bool CC = MODE == LANE_ROLLOUT_CC;     // stops at a winner (of the rolled-out state) and reports the result

@@ -240,8 +240,11 @@ __device__ __forceinline__ float rollout_plies(G &game, WarpSlab &slab, int lane
 // iteration's rollout result (pool.roll_result, written by lane_run_kernel<LANE_ROLLOUT_CC>), select and expand, and
 // defers the new rollout to the lane kernel that follows it on the stream; a last launch with it_begin == it_end ==
 // iterations back-propagates the last result and picks the move.  The pool stays in HBM / L2 between launches.
-template <class G, bool SPLIT, bool LOCK = false>
-__global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32)
+// MINB = resident CTAs per SM the register allocation must allow.  The kernel is latency-bound, so a batch of many
+// waves gains from 5 CTAs per SM (102 registers, a few spilled words: 8,192 games 1.25 -> 1.13 ms, 32,768 games 4.08 ->
+// 3.62 ms), while the one-wave BASELINE batch is a little faster with the full 126 (0.466 vs 0.478 ms).
+template <class G, bool SPLIT, bool LOCK = false, int MINB = 1>
+__global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32, MINB)
 mcts_search_kernel(const typename G::State *__restrict__ roots, int g0, int n, const int8_t *__restrict__ players,
                    diee_mcts_cfg cfg, uint32_t it_begin, uint32_t it_end, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
                    Pool pool, const float *__restrict__ ln_table, uint32_t *__restrict__ best_out,
@@ -626,7 +629,11 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         // on side streams so that one group's tree step runs beside another group's rollouts; what bounds a group is its
         // longest rollout, iteration after iteration, so throughput comes from the batch size.
         // DIEE_CC_FUSED=1 keeps the round-1 form (the whole search in one launch, warp-per-game rollouts) for comparison.
-        static const bool fused = getenv("DIEE_CC_FUSED") && atoi(getenv("DIEE_CC_FUSED")) != 0;
+        // Which form: a lock-step search takes ~0.6 ms per iteration whatever the batch (the longest rollout of the
+        // iteration, ~2 us per ply in a thinned-out warp), the fused form grows with it -- measured on B200, 100
+        // iterations: 1,024 games 18.8 ms fused / 60 ms lock-step; 16,384 games 110 / 70.6 ms; 65,536 games: 125 ms lock-step.
+        const char *fenv = getenv("DIEE_CC_FUSED");
+        const bool fused = fenv ? atoi(fenv) != 0 : n < 12288;
         if (!split && !fused && cfg.simulate_round_limit > 0) {
             int groups = n >= 8192 ? 4 : (n >= 2048 ? 2 : 1);
             if (const char *ev = getenv("DIEE_CC_GROUPS")) groups = atoi(ev);
@@ -683,6 +690,11 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         *pipe.timed = false;
         if (slices == 1) {  // everything on the caller's stream, with timing marks around the two kernels
             if ((e = cudaEventRecord(pipe.t_begin, st)) != cudaSuccess) return e;
+            if (n >= 4096 && in_smem) {
+                if ((e = cudaFuncSetAttribute(mcts_search_kernel<G, true, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+                mcts_search_kernel<G, true, false, 5><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
+                    r, 0, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
+            } else
             mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
                 r, 0, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
             *launches += 1;

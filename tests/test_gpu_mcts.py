@@ -146,13 +146,15 @@ def test_lockstep_check_current_groups_and_fused_form_agree(ctx, oracle, monkeyp
     states = positions.midgame_positions(seed=29, n=70, max_adv=110)
     players = states["player"].copy()
     cfg = oracle.mcts_cfg(iterations=25, c=2.0, limit=400, mode=_ffi.MODE_PASS_CHILD | _ffi.MODE_ROLLOUT_CHECK_CURRENT)
+    monkeypatch.setenv("DIEE_CC_FUSED", "0")   # (small batches default to the fused form)
     ref = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
     assert (ref[1] == 0).all() and int(ref[2]["rollout_plies"].sum()) > 0
     for env, val in (("DIEE_CC_GROUPS", "3"), ("DIEE_CC_GROUPS", "4"), ("DIEE_CC_FUSED", "1")):
         monkeypatch.setenv(env, val)
         got = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
-        monkeypatch.delenv(env)
+        monkeypatch.delenv(env) if env != "DIEE_CC_FUSED" else monkeypatch.setenv("DIEE_CC_FUSED", "0")
         for k, (a, b) in enumerate(zip(ref, got)):
             assert np.asarray(a).tobytes() == np.asarray(b).tobytes(), (env, val, k)
     # and against the oracle, game by game, with the full rollout cap
     _cmp_trees(oracle, _ffi, ctx, _ffi.GAME_BACKGAMMON, states[:24], players[:24], cfg, 5, 100, 3)
+    monkeypatch.delenv("DIEE_CC_FUSED")

@@ -67,7 +67,8 @@ static bool make_kmajor_map(CUtensorMap *m, const void *base, long long rows, in
 
 struct ConvLayer {
     __nv_bfloat16 *w = nullptr;  // [c_out_pad][K]
-    __nv_bfloat16 *w3 = nullptr; // split precision: [c_out_pad][3 planes][K], w = w3[0] + w3[1] + w3[2] to 24 bits
+    __nv_bfloat16 *w3 = nullptr; // split precision: [c_out_pad][3 planes][K] = (s0, r1, r2) in units of wscale[co] (net_kernels.cu)
+    float *wscale = nullptr;     // split precision: [c_out_pad], the power-of-two unit of output channel co's planes
     float *wf32 = nullptr;       // fp32 mode: [9][c_in][c_out] (BatchNorm folded)
     int c_in = 0, c_out = 0;
     float *bias = nullptr;       // [c_out_pad]
@@ -76,18 +77,19 @@ struct ConvLayer {
     int c_out_pad = 0, K = 0, ntaps = 9, chunks = 4, bn = 128;
 };
 
-// the plane pairs (i, j), i + j <= 2, of a split-precision product, packed 2+2 bits each; smallest terms first
-static constexpr uint32_t PAIRS6 = (2u << 0 | 0u << 2) | (0u << 4 | 2u << 6) | (1u << 8 | 1u << 10) | (1u << 12 | 0u << 14) |
-                                   (0u << 16 | 1u << 18) | (0u << 20 | 0u << 22);
-// exact bf16 activations (the first layer's integers): activation plane 0 against the three weight planes
-static constexpr uint32_t PAIRS3 = (0u << 0 | 2u << 2) | (0u << 4 | 1u << 6) | (0u << 8 | 0u << 10);
+// Split precision: the plane pairs (i, j) of activations x weights, packed 2+2 bits each.  The big pair (0, 0) --
+// integer digits, accumulated EXACTLY -- is its own launch; the five small ones run before it, smallest terms first.
+static constexpr uint32_t PAIRS_SMALL5 = (2u << 0 | 0u << 2) | (0u << 4 | 2u << 6) | (1u << 8 | 1u << 10) | (1u << 12 | 0u << 14) |
+                                         (0u << 16 | 1u << 18);
+static constexpr uint32_t PAIRS_BIG = 0u;  // (0, 0)
+// the first layer's activations are small integers (one exact plane): plane 0 against the weights' r2, r1
+static constexpr uint32_t PAIRS_SMALL2 = (0u << 0 | 2u << 2) | (0u << 4 | 1u << 6);
 
-static void split3(float v, __nv_bfloat16 out[3]) {
-    out[0] = __float2bfloat16(v);
-    const float r1 = v - __bfloat162float(out[0]);
-    out[1] = __float2bfloat16(r1);
-    const float r2 = r1 - __bfloat162float(out[1]);
-    out[2] = __float2bfloat16(r2);
+// Digit width of plane 0: |s0| <= 2^sb.  9 * C_in products of two digits must stay below 2^24 for the sum to be exact.
+static int split_digit_bits(int K) {
+    int sb = 6;
+    while (sb > 1 && (double)K * std::ldexp(1.0, 2 * sb) >= 16777216.0) --sb;
+    return sb;
 }
 
 // fp32 mode weights from the packed fp32 matrix wf [c_out_pad][K], K index = tap * c_in + ci
@@ -103,16 +105,33 @@ static int32_t upload_f32(diee_ctx *ctx, ConvLayer &L, const std::vector<float> 
 }
 
 static int32_t upload_split(diee_ctx *ctx, ConvLayer &L, const std::vector<float> &wf) {
-    // wf: [c_out_pad][K] fp32 (BatchNorm already folded)
+    // wf: [c_out_pad][K] fp32 (BatchNorm already folded).  Per output channel: unit = 2^(e - sb) with 2^e > max |w|,
+    // s0 = rint(w / unit) (an integer, |s0| <= 2^sb), r1 and r2 the bf16 roundings of the remainder.
+    const int sb = split_digit_bits(L.K);
     std::vector<__nv_bfloat16> w3((size_t)L.c_out_pad * 3 * L.K);
-    for (int co = 0; co < L.c_out_pad; ++co)
+    std::vector<float> ws((size_t)L.c_out_pad, 1.f);
+    for (int co = 0; co < L.c_out_pad; ++co) {
+        float mx = 0.f;
+        for (int k = 0; k < L.K; ++k) mx = std::fmax(mx, std::fabs(wf[(size_t)co * L.K + k]));
+        int e = 0;
+        if (mx > 0.f) std::frexp(mx, &e);
+        const float unit = std::ldexp(1.f, e - sb), inv = std::ldexp(1.f, sb - e);
+        ws[co] = unit;
         for (int k = 0; k < L.K; ++k) {
-            __nv_bfloat16 p[3];
-            split3(wf[(size_t)co * L.K + k], p);
-            for (int pl = 0; pl < 3; ++pl) w3[((size_t)co * 3 + pl) * L.K + k] = p[pl];
+            const float u = wf[(size_t)co * L.K + k] * inv;
+            const float s0 = std::nearbyint(u);
+            const float d1 = u - s0;
+            const __nv_bfloat16 r1 = __float2bfloat16(d1);
+            const __nv_bfloat16 r2 = __float2bfloat16(d1 - __bfloat162float(r1));
+            w3[((size_t)co * 3 + 0) * L.K + k] = __float2bfloat16(s0);
+            w3[((size_t)co * 3 + 1) * L.K + k] = r1;
+            w3[((size_t)co * 3 + 2) * L.K + k] = r2;
         }
+    }
     CU(cudaMalloc(&L.w3, w3.size() * sizeof(__nv_bfloat16)));
     CU(cudaMemcpy(L.w3, w3.data(), w3.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&L.wscale, ws.size() * sizeof(float)));
+    CU(cudaMemcpy(L.wscale, ws.data(), ws.size() * sizeof(float), cudaMemcpyHostToDevice));
     return DIEE_OK;
 }
 
@@ -126,8 +145,9 @@ struct diee_net {
     float bv = 0.f;
     // activation scratch (grown on demand)
     float *wpT = nullptr;  // split precision: policy Linear weight fp32 [768][1352], same K order
-    int precision = DIEE_NET_BF16;
+    int precision = DIEE_NET_SPLIT3;  // inside the reference's fp32 tolerance; bf16 is the explicit fast mode
     DevBuf in0, actA, actB, actC, pfeat, vfeat, s_states, s_policy, s_value;
+    DevBuf planes, small, board_max, row_scale;  // split precision: operand planes, the small pairs' sum, per-board maxima / units
     int64_t param_count = 0;
 };
 
@@ -309,11 +329,12 @@ int32_t diee_net_destroy(diee_ctx *ctx, diee_net *net) {
     if (!ctx || !net) return DIEE_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (ConvLayer &L : net->convs) { cudaFree(L.w); cudaFree(L.w3); cudaFree(L.wf32); cudaFree(L.bias); }
-    cudaFree(net->pconv.w); cudaFree(net->pconv.w3); cudaFree(net->pconv.wf32); cudaFree(net->pconv.bias);
-    cudaFree(net->vconv.w); cudaFree(net->vconv.w3); cudaFree(net->vconv.wf32); cudaFree(net->vconv.bias);
+    for (ConvLayer &L : net->convs) { cudaFree(L.w); cudaFree(L.w3); cudaFree(L.wscale); cudaFree(L.wf32); cudaFree(L.bias); }
+    cudaFree(net->pconv.w); cudaFree(net->pconv.w3); cudaFree(net->pconv.wscale); cudaFree(net->pconv.wf32); cudaFree(net->pconv.bias);
+    cudaFree(net->vconv.w); cudaFree(net->vconv.w3); cudaFree(net->vconv.wscale); cudaFree(net->vconv.wf32); cudaFree(net->vconv.bias);
     cudaFree(net->wp); cudaFree(net->wpT); cudaFree(net->bp); cudaFree(net->wv);
-    DevBuf *bufs[] = {&net->in0, &net->actA, &net->actB, &net->actC, &net->pfeat, &net->vfeat, &net->s_states, &net->s_policy, &net->s_value};
+    DevBuf *bufs[] = {&net->in0, &net->actA, &net->actB, &net->actC, &net->pfeat, &net->vfeat, &net->s_states, &net->s_policy, &net->s_value,
+                      &net->planes, &net->small, &net->board_max, &net->row_scale};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete net;
@@ -355,37 +376,61 @@ int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *
         return DIEE_OK;
     }
     if (net->precision == DIEE_NET_SPLIT3) {
-        // fp32-parity mode: activations and weights as three bf16 planes, six tensor-core products per
-        // K-block, fp32 everywhere else (bias, residual, heads)
+        // the tensor-core mode inside the fp32 tolerance (net_kernels.cu, ConvEpi): per convolution one launch for the
+        // five small plane pairs (fp32 scratch), one for the exact integer pair whose epilogue finishes the layer in fp32,
+        // then the planes of the new activations; heads in fp32
+        const int sb = split_digit_bits(9 * F);
         RESERVE(net->in0, rows * 64 * 2);
-        RESERVE(net->actA, rows * F * 6);
-        RESERVE(net->actB, rows * F * 6);
-        RESERVE(net->actC, rows * F * 6);
+        RESERVE(net->actA, rows * F * 4);
+        RESERVE(net->actB, rows * F * 4);
+        RESERVE(net->actC, rows * F * 4);
+        RESERVE(net->small, rows * F * 4);
+        RESERVE(net->planes, rows * F * 6);
         RESERVE(net->pfeat, rows * 32 * 4);
         RESERVE(net->vfeat, rows * 16 * 4);
-        CUtensorMap m_in, mA, mB, mC;
-        if (!make_act_map(&m_in, net->in0.p, n, 64) || !make_act_map(&mA, net->actA.p, n, 3 * F) ||
-            !make_act_map(&mB, net->actB.p, n, 3 * F) || !make_act_map(&mC, net->actC.p, n, 3 * F))
+        if (net->board_max.cap < (size_t)n * 4) {
+            RESERVE(net->board_max, (size_t)n * 4);
+            CU(cudaMemsetAsync(net->board_max.p, 0, net->board_max.cap, ctx->stream));  // (split_planes_kernel leaves it zeroed)
+        }
+        RESERVE(net->row_scale, (size_t)n * 4);
+        CUtensorMap m_in, mP;
+        if (!make_act_map(&m_in, net->in0.p, n, 64) || !make_act_map(&mP, net->planes.p, n, 3 * F))
             return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (activations) failed");
         cudaStream_t st = ctx->stream;
+        float *small = (float *)net->small.p, *rscale = (float *)net->row_scale.p;
+        unsigned int *bmax = (unsigned int *)net->board_max.p;
+        // one convolution: x planes (map mx) * w planes -> fp32 `out` [rows][c_out]; first = the im2col layer (one exact plane, unit 1)
+        auto conv = [&](const CUtensorMap &mx, const ConvLayer &L, bool first, const float *residual, float *out, int c_out, bool want_max) -> int32_t {
+            CU(launch_conv(st, L.bn, mx, L.wmap3, n, L.ntaps, L.chunks, nullptr, nullptr, small, 1, c_out, 0, first ? 2 : 5,
+                           first ? PAIRS_SMALL2 : PAIRS_SMALL5, first ? 0 : F, L.K));
+            SplitEpilogue sp{small, first ? nullptr : rscale, L.wscale, residual, want_max ? bmax : nullptr};
+            CU(launch_conv(st, L.bn, mx, L.wmap3, n, L.ntaps, L.chunks, L.bias, nullptr, out, 2, c_out, 1, 1, PAIRS_BIG, first ? 0 : F, L.K, &sp));
+            ctx->launches += 2;
+            return DIEE_OK;
+        };
+        auto planes_of = [&](const float *y) -> int32_t {
+            CU(launch_split_planes(st, y, bmax, n, F, sb, net->planes.p, rscale));
+            ctx->launches += 1;
+            return DIEE_OK;
+        };
         CU(launch_encode_im2col(st, states, n, net->in0.p));
-        const ConvLayer &L0 = net->convs[0];
-        CU(launch_conv(st, L0.bn, m_in, L0.wmap3, n, L0.ntaps, L0.chunks, L0.bias, nullptr, net->actA.p, 2, F, 1, 3, PAIRS3, 0, L0.K));
-        ctx->launches += 2;
-        void *bx = net->actA.p, *by = net->actB.p, *bz = net->actC.p;
-        CUtensorMap *mx = &mA, *my = &mB, *mz = &mC;
+        ctx->launches += 1;
+        float *bx = (float *)net->actA.p, *by = (float *)net->actB.p, *bz = (float *)net->actC.p;
+        int32_t rc = conv(m_in, net->convs[0], true, nullptr, bx, F, true);
+        if (rc != DIEE_OK) return rc;
         for (int b = 0; b < net->blocks; ++b) {
             const ConvLayer &c1 = net->convs[1 + 2 * b], &c2 = net->convs[2 + 2 * b];
-            CU(launch_conv(st, c1.bn, *mx, c1.wmap3, n, 9, c1.chunks, c1.bias, nullptr, by, 2, F, 1, 6, PAIRS6, F, c1.K));
-            CU(launch_conv(st, c2.bn, *my, c2.wmap3, n, 9, c2.chunks, c2.bias, bx, bz, 2, F, 1, 6, PAIRS6, F, c2.K));
-            ctx->launches += 2;
-            void *tp = bx; bx = bz; bz = tp;
-            CUtensorMap *tm = mx; mx = mz; mz = tm;
+            if ((rc = planes_of(bx)) != DIEE_OK) return rc;
+            if ((rc = conv(mP, c1, false, nullptr, by, F, true)) != DIEE_OK) return rc;
+            if ((rc = planes_of(by)) != DIEE_OK) return rc;
+            if ((rc = conv(mP, c2, false, bx, bz, F, true)) != DIEE_OK) return rc;
+            float *tp = bx; bx = bz; bz = tp;
         }
-        CU(launch_conv(st, net->pconv.bn, *mx, net->pconv.wmap3, n, 9, net->pconv.chunks, net->pconv.bias, nullptr, net->pfeat.p, 1, 32, 1, 6, PAIRS6, F, net->pconv.K));
-        CU(launch_conv(st, net->vconv.bn, *mx, net->vconv.wmap3, n, 9, net->vconv.chunks, net->vconv.bias, nullptr, net->vfeat.p, 1, 16, 1, 6, PAIRS6, F, net->vconv.K));
+        if ((rc = planes_of(bx)) != DIEE_OK) return rc;
+        if ((rc = conv(mP, net->pconv, false, nullptr, (float *)net->pfeat.p, 32, false)) != DIEE_OK) return rc;
+        if ((rc = conv(mP, net->vconv, false, nullptr, (float *)net->vfeat.p, 16, false)) != DIEE_OK) return rc;
         CU(launch_heads_f32(st, (const float *)net->pfeat.p, net->wpT, net->bp, (const float *)net->vfeat.p, net->wv, net->bv, n, policy_out, value_out));
-        ctx->launches += 4;
+        ctx->launches += 2;
         return DIEE_OK;
     }
     RESERVE(net->in0, rows * 64 * 2);

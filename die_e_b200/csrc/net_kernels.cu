@@ -160,20 +160,36 @@ struct ConvCfg {
     static_assert(MT * BN <= 512, "TMEM budget");
 };
 
-// out_mode: 0 = bf16 NHWC [rows][c_out_total], 1 = fp32 NHWC, 2 = three bf16 planes [rows][3][c_out_total]
+// out_mode: 0 = bf16 NHWC [rows][c_out_total], 1 = fp32 NHWC, 2 = fp32 NHWC through the split-precision epilogue (ConvEpi)
 //
-// Split precision (the fp32-parity mode of the net): an fp32 value is carried as three bf16 planes
-// x = x0 + x1 + x2 (each the bf16 rounding of what the previous ones left over, 24 mantissa bits in all).
-// A product then needs the plane pairs (i, j) with i + j <= 2 -- six bf16 MMAs accumulated in the fp32 TMEM
-// accumulator -- so the K loop simply runs over (pair, tap, chunk): `pairs` packs up to eight (i, j) as 2+2
-// bits each, plane i of the activations starts a_plane channels further on, plane j of the weights b_plane
-// K-columns further on.  Plain bf16 is the one pair (0, 0).
+// Split precision (DIEE_NET_SPLIT3, the tensor-core mode inside the fp32 tolerance): an fp32 operand is carried as
+// three bf16 planes.  The K loop runs over (pair, tap, chunk): `pairs` packs up to eight plane pairs (i, j) as 2+2 bits
+// each, plane i of the activations starts a_plane channels further on, plane j of the weights b_plane K-columns further
+// on.  Plain bf16 is the one pair (0, 0).
+//
+// What makes it accurate is WHICH planes (net.cu, split_planes_kernel): the tensor core's fp32 accumulation truncates
+// on every MMA, a systematic shrink of ~0.5 ulp per instruction that 144 accumulations of full-size products turn into
+// ~3e-6 per layer (measured round 1: 2.2e-4 through 39 layers).  So plane 0 is a 7-bit signed INTEGER digit: every
+// board (and every output channel of the weights) is scaled by a power of two so that |x| <= 64 units, s0 = rint(x),
+// and planes 1, 2 are the bf16 roundings of what is left (x = s0 + r1 + r2 to 2^-24 of the board's largest value).
+// The products s0_x * s0_w are integers <= 4096 and a sum of 9 * C_in <= 2304 of them stays below 2^24: every partial
+// sum is exactly representable, so the accumulation of the big pair (0, 0) is EXACT whatever the hardware rounds.
+// It runs as its own launch; the five small pairs (2^-7 and below) run before it into an fp32 scratch (their
+// truncation costs 2^-7 of the above), and the epilogue of the (0, 0) launch adds the two, applies the two power-of-two
+// scales, bias, the fp32 residual and ReLU, stores fp32 and records every board's maximum for the next layer's planes.
+struct ConvEpi {
+    const float *addend;        // fp32 [rows][c_out_total]: the small pairs' sum, same units as the accumulator (nullable)
+    const float *row_scale;     // [board]: units of this layer's activation planes (nullable = 1)
+    const float *col_scale;     // [c_out_total]: units of the weight planes per output channel (nullable = 1)
+    const float *residual_f32;  // fp32 [rows][c_out_total] (nullable)
+    unsigned int *board_max;    // [board]: max of the (post-ReLU, >= 0) outputs as float bits, atomicMax (nullable)
+};
 template <int BN, int NB, int KC>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int n_boards,
                   int ntaps, int chunks, const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual,
                   void *__restrict__ out, int out_mode, int c_out_total, int relu, int npairs, uint32_t pairs, int a_plane,
-                  int b_plane) {
+                  int b_plane, ConvEpi epi) {
     using Cfg = ConvCfg<BN, NB, KC>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -198,7 +214,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    for (int i = threadIdx.x; i < BN; i += CONV_THREADS) bias_smem[i] = bias[n0 + i];
+    for (int i = threadIdx.x; i < BN; i += CONV_THREADS) bias_smem[i] = bias ? bias[n0 + i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -272,62 +288,69 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 const int ncol = (BN - c0) >= 32 ? 32 : 16;
                 if (ncol == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
                 tmem_ld_wait();
-                if (valid) {
-                    float f[32], rsum[32];
+                if (valid && out_mode == 2) {
+                    // split-precision epilogue: (acc + small pairs) * 2^(e_board + e_channel) + bias (+ residual), ReLU, fp32
+                    const size_t off = (size_t)grow * c_out_total + n0 + c0;
+                    const float rs = epi.row_scale ? epi.row_scale[grow / 24] : 1.f;
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = j < ncol ? __uint_as_float(v[j]) : 0.f;
+                    if (epi.addend) {
+                        const float4 *ap = reinterpret_cast<const float4 *>(epi.addend + off);
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4)
+                            if (g4 * 4 < ncol) {
+                                const float4 a = ap[g4];
+                                f[g4 * 4] += a.x; f[g4 * 4 + 1] += a.y; f[g4 * 4 + 2] += a.z; f[g4 * 4 + 3] += a.w;
+                            }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncol) f[j] = f[j] * (rs * (epi.col_scale ? epi.col_scale[n0 + c0 + j] : 1.f)) + bias_smem[c0 + j];
+                    if (epi.residual_f32) {
+                        const float4 *rp = reinterpret_cast<const float4 *>(epi.residual_f32 + off);
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4)
+                            if (g4 * 4 < ncol) {
+                                const float4 a = rp[g4];
+                                f[g4 * 4] += a.x; f[g4 * 4 + 1] += a.y; f[g4 * 4 + 2] += a.z; f[g4 * 4 + 3] += a.w;
+                            }
+                    }
+                    float mx = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (relu) f[j] = fmaxf(f[j], 0.f);
+                        mx = fmaxf(mx, fabsf(f[j]));
+                    }
+                    float4 *op = reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + off);
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4)
+                        if (g4 * 4 < ncol) op[g4] = make_float4(f[g4 * 4], f[g4 * 4 + 1], f[g4 * 4 + 2], f[g4 * 4 + 3]);
+                    if (epi.board_max) atomicMax(epi.board_max + grow / 24, __float_as_uint(mx));  // mx >= 0: bit order = value order
+                } else if (valid) {
+                    float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = j < ncol ? __uint_as_float(v[j]) + bias_smem[c0 + j] : 0.f;
-                    const int nplanes = out_mode == 2 ? 3 : 1;
-                    const size_t off = (size_t)grow * c_out_total * nplanes + n0 + c0;
-                    if (residual) {
-                        // the skip connection: in split precision the residual is the sum of its three planes,
-                        // smallest first (exact: they do not overlap)
-                        for (int pl = nplanes - 1; pl >= 0; --pl) {
-                            const uint4 *rp = reinterpret_cast<const uint4 *>(residual + off + (size_t)pl * c_out_total);
-                            float r32[32];
+                    const size_t off = (size_t)grow * c_out_total + n0 + c0;
+                    if (residual) {  // the skip connection (bf16 NHWC)
+                        const uint4 *rp = reinterpret_cast<const uint4 *>(residual + off);
 #pragma unroll
-                            for (int g4 = 0; g4 < 4; ++g4) {
-                                const uint4 r = rp[g4];
-                                const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            const uint4 r = rp[g4];
+                            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-                                for (int h = 0; h < 4; ++h) {
-                                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[h]);
-                                    r32[g4 * 8 + h * 2] = __bfloat162float(b2.x);
-                                    r32[g4 * 8 + h * 2 + 1] = __bfloat162float(b2.y);
-                                }
-                            }
-                            if (pl == nplanes - 1) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) rsum[j] = r32[j];
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) rsum[j] += r32[j];
+                            for (int h = 0; h < 4; ++h) {
+                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[h]);
+                                f[g4 * 8 + h * 2] += __bfloat162float(b2.x);
+                                f[g4 * 8 + h * 2 + 1] += __bfloat162float(b2.y);
                             }
                         }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] += rsum[j];
                     }
                     if (relu) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
                     }
-                    if (out_mode == 2) {
-                        // three bf16 planes: each is the bf16 rounding of what the previous ones left over
-                        for (int pl = 0; pl < 3; ++pl) {
-                            uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(out) + off + (size_t)pl * c_out_total);
-#pragma unroll
-                            for (int g4 = 0; g4 < 4; ++g4) {
-                                uint32_t w[4];
-#pragma unroll
-                                for (int h = 0; h < 4; ++h) {
-                                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g4 * 8 + h * 2], f[g4 * 8 + h * 2 + 1]);
-                                    w[h] = *reinterpret_cast<const uint32_t *>(&b2);
-                                    f[g4 * 8 + h * 2] -= __bfloat162float(b2.x);
-                                    f[g4 * 8 + h * 2 + 1] -= __bfloat162float(b2.y);
-                                }
-                                if (g4 * 8 < ncol) op[g4] = make_uint4(w[0], w[1], w[2], w[3]);
-                            }
-                        }
-                    } else if (out_mode == 0) {
+                    if (out_mode == 0) {
                         uint4 *op = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(out) + off);
 #pragma unroll
                         for (int g4 = 0; g4 < 4; ++g4) {
@@ -385,6 +408,42 @@ __global__ void encode_im2col_kernel(const diee_bg_state *__restrict__ states, i
         }
         out[idx] = __float2bfloat16(val);
     }
+}
+
+// ---------------------------------------------------------------- split-precision operand planes
+// One CTA per board: y fp32 [24][C] -> planes bf16 [24][3][C] = (s0, r1, r2) in units of 2^(e - sb), 2^e >= the board's
+// largest |y| (board_max, as float bits; reset to 0 here for the next layer); scale_out[board] = 2^(e - sb).
+// s0 = rint(y / unit) is an integer with |s0| <= 2^sb; r1, r2 = bf16 roundings of the remainder.
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float *__restrict__ y, unsigned int *__restrict__ board_max, int C, int sb, __nv_bfloat16 *__restrict__ planes,
+                    float *__restrict__ scale_out) {
+    const int b = blockIdx.x;
+    const float mx = __uint_as_float(board_max[b]);
+    int e = 0;
+    if (mx > 0.f) frexpf(mx, &e);  // mx = m * 2^e, m in [0.5, 1): 2^e > mx
+    const float unit = ldexpf(1.f, e - sb), inv = ldexpf(1.f, sb - e);  // powers of two: exact
+    const float *yb = y + (size_t)b * 24 * C;
+    __nv_bfloat16 *pb = planes + (size_t)b * 24 * 3 * C;
+    for (int i = threadIdx.x; i < 24 * C; i += 256) {
+        const int pos = i / C, c = i - pos * C;
+        const float u = yb[i] * inv;
+        const float s0 = rintf(u);
+        const float d1 = u - s0;  // exact: |u| <= 2^sb, the difference of two nearby floats
+        const __nv_bfloat16 r1 = __float2bfloat16(d1);
+        const __nv_bfloat16 r2 = __float2bfloat16(d1 - __bfloat162float(r1));
+        __nv_bfloat16 *o = pb + (size_t)pos * 3 * C + c;
+        o[0] = __float2bfloat16(s0);  // |s0| <= 64: exact in bf16
+        o[C] = r1;
+        o[2 * C] = r2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { scale_out[b] = unit; board_max[b] = 0u; }
+}
+
+cudaError_t launch_split_planes(cudaStream_t st, const float *y, unsigned int *board_max, int n, int C, int sb, void *planes, float *scale_out) {
+    if (n <= 0) return cudaSuccess;
+    split_planes_kernel<<<(unsigned)n, 256, 0, st>>>(y, board_max, C, sb, static_cast<__nv_bfloat16 *>(planes), scale_out);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- heads
@@ -604,7 +663,7 @@ fc_f32_kernel(const float *__restrict__ feat, const float *__restrict__ wT, cons
 template <int BN, int NB, int KC>
 static cudaError_t launch_conv_bn(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,
                                   int chunks, const float *bias, const __nv_bfloat16 *residual, void *out, int out_mode,
-                                  int c_out_total, int relu, int npairs, uint32_t pairs, int a_plane, int b_plane) {
+                                  int c_out_total, int relu, int npairs, uint32_t pairs, int a_plane, int b_plane, const ConvEpi &epi) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, NB, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NB, KC>::SMEM_BYTES);
@@ -614,15 +673,17 @@ static cudaError_t launch_conv_bn(cudaStream_t st, const CUtensorMap &ta, const 
     dim3 grid((n_boards + NB - 1) / NB, c_out_total / BN);
     conv3x3_tc_kernel<BN, NB, KC><<<grid, CONV_THREADS, ConvCfg<BN, NB, KC>::SMEM_BYTES, st>>>(ta, tb, n_boards, ntaps, chunks, bias, residual,
                                                                                               out, out_mode, c_out_total, relu, npairs, pairs,
-                                                                                              a_plane, b_plane);
+                                                                                              a_plane, b_plane, epi);
     return cudaGetLastError();
 }
 
 // `ta` must have been encoded with a box of nb boards, `tb` with a box of bn rows
 cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,
                              int chunks, const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
-                             int npairs, uint32_t pairs, int a_plane, int b_plane) {
+                             int npairs, uint32_t pairs, int a_plane, int b_plane, const SplitEpilogue *sp) {
     const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(residual);
+    ConvEpi epi{};
+    if (sp) epi = ConvEpi{sp->addend, sp->row_scale, sp->col_scale, sp->residual_f32, sp->board_max};
     // several chunks per pipeline stage where the tile is small enough for >= 3 such stages and the layer's chunk count
     // divides (DIEE_CONV_KC=n caps it; 1 keeps one chunk per stage everywhere)
     static const bool one_chunk = getenv("DIEE_CONV_KC") && atoi(getenv("DIEE_CONV_KC")) == 1;
@@ -630,7 +691,7 @@ cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap 
 #define DIEE_CONV_CASE(BN_, NB_, KC_)                                                                                                        \
     if (bn == BN_ && nb == NB_ && KC_ <= max_kc && chunks % KC_ == 0)                                                                                    \
         return launch_conv_bn<BN_, NB_, KC_>(st, ta, tb, n_boards, ntaps, chunks, bias, res, out, out_mode, c_out_total, relu, npairs, pairs, \
-                                             a_plane, b_plane);
+                                             a_plane, b_plane, epi);
     DIEE_CONV_CASE(128, 16, 1)
     DIEE_CONV_CASE(32, 16, 1)
     DIEE_CONV_CASE(16, 16, 1)
@@ -649,9 +710,9 @@ cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap 
 
 cudaError_t launch_conv(cudaStream_t st, int bn, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps, int chunks,
                         const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
-                        int npairs, uint32_t pairs, int a_plane, int b_plane) {
+                        int npairs, uint32_t pairs, int a_plane, int b_plane, const SplitEpilogue *sp) {
     return launch_conv_tile(st, bn, 16, ta, tb, n_boards, ntaps, chunks, bias, residual, out, out_mode, c_out_total, relu, npairs, pairs,
-                            a_plane, b_plane);
+                            a_plane, b_plane, sp);
 }
 
 cudaError_t launch_encode_im2col(cudaStream_t st, const diee_bg_state *states, int n, void *out) {

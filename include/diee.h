@@ -219,19 +219,21 @@ int32_t diee_search_work(diee_ctx *ctx, uint64_t *rollout_plies_played);
  *   linear: weight [out,in], bias [out]
  *   init conv, init bn | per block: conv1, conv2, bn1, bn2 | policy conv, bn, linear | value conv, bn, linear
  * (die_e_b200/nnet.py reads them out of a tch VarStore `.ot` file.)  BatchNorm is folded into the
- * convolutions at load time; the convolutions run on the tensor cores (tcgen05) in bf16 with fp32
- * accumulation.  forward = forward_t (nnet.rs:120-133): policy_out f32 [n,1352] (softmaxed),
+ * convolutions at load time; the convolutions run on the tensor cores (tcgen05), see diee_net_set_precision.  forward = forward_t (nnet.rs:120-133): policy_out f32 [n,1352] (softmaxed),
  * value_out f32 [n] (tanh).  States are the packed 32-byte states; as_tensor is fused in. */
 typedef struct diee_net diee_net;
 int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *tensors, const int64_t *numels,
                         int32_t n_tensors, diee_net **out);
 /* Arithmetic of the forward pass (nnet.rs:120-133 computes in fp32, lib.rs:20).
- * DIEE_NET_BF16 (default): bf16 operands on the tensor cores, fp32 accumulation -- the fast path.
- * DIEE_NET_SPLIT3: still on the tensor cores, but every activation and weight is carried as three bf16 planes
- *   (24 mantissa bits) and each product is six MMAs; what remains is the tensor cores' truncating fp32
- *   accumulation, ~1e-5 per layer (about 10x the rounding cost of an fp32 forward).
- * DIEE_NET_FP32: the PARITY mode -- fp32 FMAs (round to nearest) on the CUDA cores, like the reference; differs
- *   from it only by summation order. */
+ * DIEE_NET_BF16: bf16 operands on the tensor cores, fp32 accumulation -- the fast path, NOT inside the reference's
+ *   tolerance through 39 layers (4e-2 on the value head); searches run with it are not comparable to the reference's.
+ * DIEE_NET_SPLIT3 (default): the tensor-core mode INSIDE the fp32 tolerance.  Every activation and weight is carried as three
+ *   bf16 planes and each product is six MMAs; the leading plane is a 7-bit integer digit under a per-board / per-channel
+ *   power-of-two unit, so the sum of the full-size products is exact in the fp32 accumulator whatever the hardware
+ *   rounds, and the truncating accumulation only touches terms 2^-7 and smaller (csrc/net_kernels.cu).  Error against
+ *   fp64 within a small multiple of an fp32 forward's own (tests/test_gpu_net.py).
+ * DIEE_NET_FP32: fp32 FMAs (round to nearest) on the CUDA cores, the reference's own arithmetic; differs from it only
+ *   by summation order. */
 #define DIEE_NET_BF16 0
 #define DIEE_NET_SPLIT3 1
 #define DIEE_NET_FP32 2

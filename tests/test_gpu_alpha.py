@@ -61,8 +61,10 @@ def test_alpha_search_bit_exact(ctx, net, oracle, n, iters, seed):
         assert [int(x) for x in r_ids[g, :nc]] == [oracle.bg_encode(states[g:g + 1], m) for m in oracle.moves_to_list(ch["action"], nc)]
 
 
-def test_alpha_search_end_to_end_against_an_independent_fp32_net(ctx, oracle):
-    """End to end, nothing shared: the GPU search with the net in its fp32 parity mode (DIEE_NET_FP32) against the
+@pytest.mark.parametrize("prec", ["fp32", "split3"])
+def test_alpha_search_end_to_end_against_an_independent_fp32_net(ctx, oracle, prec):
+    """End to end, nothing shared: the GPU search with the net in a mode inside the fp32 tolerance (DIEE_NET_FP32 on the
+    CUDA cores, DIEE_NET_SPLIT3 -- the default -- on the tensor cores) against the
     oracle search whose net is torch's fp32 CPU forward of the same weights (what the reference's tch computes).
     The two nets agree to ~1e-6, so the trees can only differ where two PUCT scores are closer than that.
     Bar: root visit counts identical for >= 90 % of the games; where a near-tie went the other way the total-variation
@@ -75,7 +77,7 @@ def test_alpha_search_end_to_end_against_an_independent_fp32_net(ctx, oracle):
     blocks = 2
     tens = nnet.synthetic_tensors(seed=33, filters=128, blocks=blocks, bn_stats="random")
     gnet = _ffi.Net(ctx, tens)
-    gnet.set_precision(_ffi.NET_FP32)
+    gnet.set_precision(_ffi.NET_FP32 if prec == "fp32" else _ffi.NET_SPLIT3)
     n, iters, seed = 24, 30, 5
     states = positions.midgame_positions(seed=seed, n=n, max_adv=100)
     ids = np.arange(500, 500 + n, dtype=np.uint32)
@@ -108,7 +110,7 @@ def test_alpha_search_end_to_end_against_an_independent_fp32_net(ctx, oracle):
             qb = ch["value"][vis].astype(np.float64) / b[vis]
             if vis.any():
                 worst_q = max(worst_q, (np.abs(qa - qb) / np.maximum(np.abs(qb), 1e-2)).max())
-    print(f"\n[alpha end-to-end fp32] identical root visit counts {same}/{n}, worst TV {worst_tv:.2e}, worst value rel {worst_q:.2e}")
+    print(f"\n[alpha end-to-end {prec}] identical root visit counts {same}/{n}, worst TV {worst_tv:.2e}, worst value rel {worst_q:.2e}")
     assert same >= 0.9 * n and worst_tv <= 0.1 and worst_q <= 1e-5, (same, worst_tv, worst_q)
     gnet.close()
 

@@ -9,9 +9,10 @@ Floating point: the product computes in bf16 with fp32 accumulation.  Two bars a
   (2) against the fp64 oracle of the reference architecture the bf16 error itself is bounded
       (value |dv| <= 0.1, policy total-variation distance <= 0.05) and printed.
 north_star's 1e-5 (relative, vs the fp32 reference) is NOT met by the bf16 path and is not claimed for it.
-The parity mode is DIEE_NET_FP32 (fp32 FMAs on the CUDA cores, the reference's own arithmetic):
-test_fp32_mode_matches_fp32_reference asserts it against the fp64 oracle next to the reference's own fp32
-rounding cost, and bounds the 24-bit tensor-core mode DIEE_NET_SPLIT3 the same way."""
+The modes inside the tolerance are DIEE_NET_FP32 (fp32 FMAs on the CUDA cores, the reference's own arithmetic) and
+DIEE_NET_SPLIT3 (tensor cores: three bf16 planes per operand, the leading one an integer digit whose products are
+accumulated exactly): test_fp32_mode_matches_fp32_reference asserts both against the fp64 oracle next to the
+reference's own fp32 rounding cost."""
 import numpy as np
 import pytest
 
@@ -38,6 +39,7 @@ def test_forward_matches_oracles(ctx, oracle, filters, blocks, n, bn):
     from die_e_b200 import _ffi, nnet
     tens = nnet.synthetic_tensors(seed=7, filters=filters, blocks=blocks, bn_stats=bn)
     net = _ffi.Net(ctx, tens)
+    net.set_precision(_ffi.NET_BF16)
     states, x = _inputs(oracle, n)
     p, v = net.forward(states)
     assert np.isfinite(p).all() and np.isfinite(v).all()
@@ -69,7 +71,8 @@ def test_fp32_mode_matches_fp32_reference(ctx, oracle, filters, blocks, n, bn):
     max(1e-5, 4 x that cost) on the value (relative to max(|v|, 0.1): the value head is a 72-term sum that cancels, so an absolute floor of 1e-6 on a quantity in [-1, 1]) and on the policy (fraction of the row
     maximum -- a softmax row reaches down to 1e-9, a per-entry relative bar means nothing there).  With these
     synthetic weights the reference's own cost is 3e-7 at 2 blocks and 1.6e-5 at 19 blocks.
-    SPLIT3 is bounded by 20 x the same figure (truncating accumulation in TMEM, ~1e-5 per layer)."""
+    SPLIT3 -- the tensor-core mode -- is held to the SAME bar: its full-size products are accumulated exactly (integer
+    digit planes, csrc/net_kernels.cu) and only terms 2^-7 and smaller meet the tensor core's truncating accumulation."""
     import torch
     from die_e_b200 import _ffi, nnet
     tens = nnet.synthetic_tensors(seed=7, filters=filters, blocks=blocks, bn_stats=bn)
@@ -91,7 +94,8 @@ def test_fp32_mode_matches_fp32_reference(ctx, oracle, filters, blocks, n, bn):
           f"torch fp32 {ref_v:.2e} {ref_p:.2e} | ours fp32 {out['fp32'][0]:.2e} {out['fp32'][1]:.2e} | "
           f"split3 {out['split3'][0]:.2e} {out['split3'][1]:.2e} | bf16 {out['bf16'][0]:.2e} {out['bf16'][1]:.2e}")
     assert out["fp32"][0] <= max(1e-5, 4 * ref_v) and out["fp32"][1] <= max(1e-5, 4 * ref_p)
-    assert out["split3"][0] <= max(1e-5, 20 * ref_v) and out["split3"][1] <= max(1e-5, 20 * ref_p)
+    assert out["split3"][0] <= max(1e-5, 4 * ref_v) and out["split3"][1] <= max(1e-5, 4 * ref_p)
+    assert (out["split3"][2].argmax(1) == p64.argmax(1)).all()
     assert (out["fp32"][2].argmax(1) == p64.argmax(1)).all()
     net.close()
 
@@ -101,10 +105,16 @@ def test_batch_edges_and_determinism(ctx, oracle):
     tens = nnet.synthetic_tensors(seed=9, filters=128, blocks=1, bn_stats="random")
     net = _ffi.Net(ctx, tens)
     states, x = _inputs(oracle, 50, seed=3)
-    p_all, v_all = net.forward(states)
-    for n in (1, 15, 16, 17, 33):
-        p, v = net.forward(states[:n])
-        assert (p == p_all[:n]).all() and (v == v_all[:n]).all()   # results do not depend on the batch tiling
+    for mode in (_ffi.NET_SPLIT3, _ffi.NET_BF16, _ffi.NET_FP32):
+        net.set_precision(mode)
+        p_all, v_all = net.forward(states)
+        for n in (1, 15, 16, 17, 33):
+            p, v = net.forward(states[:n])
+            assert (p == p_all[:n]).all() and (v == v_all[:n]).all(), mode   # results do not depend on the batch tiling
+        order = np.arange(49, -1, -1)
+        p_r, v_r = net.forward(states[order])                        # ... nor on where in the batch a board sits
+        assert (p_r == p_all[order]).all() and (v_r == v_all[order]).all(), mode
+    net.set_precision(_ffi.NET_SPLIT3)
     p0, v0 = net.forward(states[:0])
     assert p0.shape == (0, 1352)
     bad = states[:2].copy()
@@ -123,6 +133,7 @@ def test_every_cta_tile_shape_gives_the_same_bits(ctx, oracle, monkeypatch):
     from die_e_b200 import _ffi, nnet
     tens = nnet.synthetic_tensors(seed=11, filters=256, blocks=2, bn_stats="random")
     net = _ffi.Net(ctx, tens)
+    net.set_precision(_ffi.NET_BF16)
     states, _ = _inputs(oracle, 43, seed=5)
     monkeypatch.setenv("DIEE_CONV_TILE", "16,128")
     p_ref, v_ref = net.forward(states)

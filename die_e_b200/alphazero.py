@@ -84,8 +84,9 @@ def memory_to_arrays(rec, pi_ids, pi_vals, ctx=None):
 # `Tensor::save` (tch) is libtorch's `torch::save(tensor, path)`: a TorchScript archive holding ONE tensor under the
 # key "0".  The reference writes three of them per self-play iteration (alphazero.rs:149-176):
 #   ps.ot [M,1352] f32, states.ot [M,6,4,6] f32 (Tensor::concat of the [1,6,4,6] states), outcomes.ot [M] i8
-# under ./data/<game>/run-<id>/lrn-<i>/sp-<j>/ (alpha_parallel.rs:18-21,43-44,60-62).  Unverified against a file
-# written by tch itself (the reference ships none and there is no Rust toolchain here).
+# under ./data/<game>/run-<id>/lrn-<i>/sp-<j>/ (alpha_parallel.rs:18-21,43-44,60-62).  The container is pinned by files
+# written with libtorch's own C++ serializer (tests/golden/ot_writer.cpp = the calls tch's at_save makes,
+# tests/test_ot_fixture.py); a file written by tch itself does not exist here (no Rust toolchain).
 def _save_tensor_ot(path, array):
     import torch
 

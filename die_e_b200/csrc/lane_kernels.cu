@@ -104,7 +104,7 @@ __device__ __forceinline__ int lane_path(const LaneBoard &g) {
 #define DIEE_LANE_MIN_BLOCKS 1
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(LANE_CTA, DIEE_LANE_MIN_BLOCKS)
+__global__ void __launch_bounds__(LANE_CTA)
 lane_run_kernel(LaneJob job) {
     constexpr bool ROLLOUT = MODE != LANE_PLAYOUT;   // plays on the ROLLOUT stream from a node of the pool
     constexpr bool CC = MODE == LANE_ROLLOUT_CC;     // stops at a winner (of the rolled-out state) and reports the result

@@ -58,8 +58,9 @@ def synthetic_tensors(seed=0xD1EE, filters=256, blocks=19, bn_stats="identity"):
 # ---- tch VarStore (.ot) naming: every layer registers on the ROOT path (nnet.rs:62-96), so the
 # names collide and tch disambiguates with "__<number of variables registered so far>".  The suffix is
 # strictly increasing, so sorting each base name by suffix recovers registration order whatever order
-# tch creates weight/bias inside one layer (unverified against a real tch file:
-# the reference ships none).
+# tch creates weight/bias inside one layer.  The CONTAINER is pinned by an archive written with
+# libtorch's own OutputArchive (tests/test_ot_fixture.py); the suffix scheme is restated from tch 0.13.0's published
+# source and cannot be run here (no Rust toolchain; the reference ships no .ot file).
 def _tch_names(filters, blocks):
     names, count, seen = [], 0, set()
 

@@ -70,7 +70,10 @@ def test_alpha_search_end_to_end_against_an_independent_fp32_net(ctx, oracle, pr
     Bar: root visit counts identical for >= 90 % of the games; where a near-tie went the other way the total-variation
     distance of the root visit distributions stays <= 0.1 (one visit of a 30-iteration search is 1/30, and the torch CPU
     forward itself moves in its last bits with the thread count); value estimates of the root children
-    (value / visits) within 1e-5 relative (floor 1e-2) wherever the visit counts agree."""
+    (value / visits) within 1e-5 relative to max(|q|, 0.1) wherever the visit counts agree -- the metric
+    tests/test_gpu_net.py uses for the value head itself: q is a mean of tanh outputs, each a 72-term sum that cancels,
+    and two correct fp32 forwards already differ by ~2e-7 ABSOLUTE on it, so a purely relative bar on a q near zero
+    would test the rounding of the reference's own arithmetic, not this engine."""
     import torch
     import net_oracle
     from die_e_b200 import _ffi, nnet

@@ -384,9 +384,12 @@ def run_ours(args, rank, world):
             def step_dev(i):
                 t0 = time.perf_counter()
                 e0 = ctx.net_eval_count()
-                rec, pi_ids, pi_vals, waves = ctx.selfplay_run(net, G, cfg, 1.25, SEED + i, first_gid)
-                sp_info.update(records=len(rec), waves=waves, evals=ctx.net_eval_count() - e0, wall=time.perf_counter() - t0,
-                               rec=(rec, pi_ids, pi_vals))
+                rec, pi_ids, pi_vals, rep = ctx.selfplay_run_ex(net, G, cfg, 1.25, SEED + i, first_gid, max_waves=args.max_waves,
+                                                               flags=ffi.SP_REFILL if args.refill else 0, target_games=args.refill,
+                                                               leaves_per_game=args.leaves, virtual_loss=1.0 if args.leaves > 1 else 0.0)
+                sp_info.update(records=len(rec), waves=int(rep["waves"]), evals=ctx.net_eval_count() - e0, wall=time.perf_counter() - t0,
+                               rec=(rec, pi_ids, pi_vals), finished=int(rep["games_finished"]), cut=int(rep["games_cut"]),
+                               moves=int(rep["game_moves"]))
             h2d, d2h = 0, 0
             step_e2e = None
             metric, unit = "selfplay_games_per_sec", "games/s"
@@ -445,7 +448,7 @@ def run_ours(args, rank, world):
             units += units_per_step
         else:
             evs[i][1].synchronize()
-            units += units_per_step
+            units += sp_info["finished"] if args.workload == "selfplay" else units_per_step  # games that reached a winner or the cap
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.launch_count() - launches0
@@ -587,7 +590,12 @@ def run_ours(args, rank, world):
             else:
                 evals = sp_info["evals"]
                 detail.update(net_evals_per_step=int(evals), waves_per_step=sp_info["waves"], records_per_step=sp_info["records"],
-                              simulations_per_sec=round(evals / step_s, 1))
+                              simulations_per_sec=round(evals / step_s, 1), games_finished_per_step=sp_info["finished"],
+                              games_cut_per_step=sp_info["cut"], game_moves_per_sec=round(sp_info["moves"] / step_s, 1),
+                              mode=("NON-PARITY: " + ", ".join(x for x in (f"slot refill to {args.refill} games" if args.refill else "",
+                                                                          f"{args.leaves} leaves per game and step, virtual loss 1" if args.leaves > 1 else "",
+                                                                          f"time box {args.max_waves} waves" if args.max_waves else "") if x))
+                              if (args.refill or args.leaves > 1 or args.max_waves) else "reference: self_play_parallel, record for record")
             tf = NET_FLOP_PER_EVAL * evals / step_s / 1e12
             roof = {"bound": "tensor", "achieved": round(tf, 2), "peak": sustained, "unit": "TFLOP/s", "frac": round(tf / sustained, 4),
                     "traffic": None, "peak_source": tsrc + " (sustained figure: the kernel runs inside a long step)",
@@ -863,6 +871,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-subrecords", "--no-large-batch", dest="no_subrecords", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--refill", type=int, default=0, help="selfplay: NON-PARITY slot refill, stop after this many finished games")
+    ap.add_argument("--leaves", type=int, default=0, help="selfplay/alpha: NON-PARITY leaves per game and step (virtual loss 1)")
+    ap.add_argument("--max-waves", type=int, default=0, help="selfplay: time box (game-move waves)")
     args = ap.parse_args()
     if args.games is None:
         args.games = 65536 if args.workload == "playout" else 1024

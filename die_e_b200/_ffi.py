@@ -49,7 +49,7 @@ SYMBOLS = [
     "diee_bg_encode_states", "diee_bg_encode_states_dev", "diee_mcts_search", "diee_mcts_search_dev",
     "diee_net_create", "diee_net_destroy", "diee_net_set_precision", "diee_net_param_count", "diee_net_forward", "diee_net_forward_dev",
     "diee_search_timing", "diee_search_work", "diee_comm_unique_id", "diee_comm_init", "diee_comm_destroy", "diee_traj_allgather",
-    "diee_net_broadcast", "diee_dirichlet", "diee_alpha_search", "diee_alpha_search_dev", "diee_selfplay_run", "diee_selfplay_run_ex", "diee_net_eval_count",
+    "diee_net_broadcast", "diee_dirichlet", "diee_alpha_search", "diee_alpha_search_dev", "diee_alpha_search_vl", "diee_selfplay_run", "diee_selfplay_run_ex", "diee_net_eval_count",
 ]
 
 
@@ -287,6 +287,22 @@ class Context:
             return ids, moves, visits, counts, status, nodes, n_nodes
         return ids, moves, visits, counts, status
 
+    def alpha_search_vl(self, net, states, game_ids, cfg, seed, epoch=0, max_nodes=0, leaves_per_game=4, virtual_loss=1.0):
+        """NON-PARITY search: several leaves per game and step with virtual loss (diee_alpha_search_vl)"""
+        states = np.ascontiguousarray(states, dtype=BG_STATE).reshape(-1)
+        n = len(states)
+        game_ids = np.ascontiguousarray(game_ids, dtype=np.uint32).reshape(-1)
+        cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]
+        ids = np.zeros((n, MAX_MOVES), dtype=np.uint16)
+        moves = np.zeros((n, MAX_MOVES), dtype=MOVE)
+        visits = np.zeros((n, MAX_MOVES), dtype=np.float32)
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        self._chk(lib().diee_alpha_search_vl(self._h, net._h, _p(states), C.c_int32(n), _p(game_ids), _p(cfg), C.c_uint64(seed),
+                                             C.c_uint32(epoch), C.c_int32(max_nodes), C.c_int32(leaves_per_game),
+                                             C.c_float(virtual_loss), _p(ids), _p(moves), _p(visits), _p(counts), _p(status)))
+        return ids, moves, visits, counts, status
+
     def alpha_search_dev(self, net, d_states, n, d_ids, cfg, seed, epoch, max_nodes, d_root_ids, d_root_moves, d_root_visits,
                          d_root_counts, d_status):
         cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1]
@@ -301,7 +317,7 @@ class Context:
         limit = int(cfg["simulate_round_limit"][0])
         opts = np.zeros(1, dtype=SELFPLAY_OPTS)
         opts[0] = (flags, max_waves, leaves_per_game, target_games, virtual_loss, 0)
-        rec_cap = rec_cap or max(n_games, target_games) * (2 * limit + 4)
+        rec_cap = rec_cap or ((target_games + n_games) * 300 if (flags & SP_REFILL) else n_games * (2 * limit + 4))
         pi_cap = pi_cap or rec_cap * 48
         rec = np.zeros(rec_cap, dtype=TRAJ)
         pi_ids = np.zeros(pi_cap, dtype=np.uint16)

@@ -58,9 +58,14 @@ static void dirichlet_sample(uint64_t seed, uint32_t epoch, float alpha, int n, 
 static int default_max_nodes(const diee_mcts_cfg *cfg) { return 1 + ((int)cfg->iterations + 1) * 128; }
 
 // one alpha_mcts_parallel over device-resident states; fills the ctx arena
+// K > 1 (with virtual loss vl) is the NON-PARITY throughput mode of alpha_kernels.cu; K <= 1 is the reference's search
 static int32_t alpha_search_device(diee_ctx *ctx, diee_net *net, const diee_bg_state *d_states, int n, const uint32_t *d_ids,
-                                   const diee_mcts_cfg *cfg, uint64_t seed, uint32_t epoch, int max_nodes, AlphaPool &P) {
+                                   const diee_mcts_cfg *cfg, uint64_t seed, uint32_t epoch, int max_nodes, AlphaPool &P,
+                                   int K = 0, float vl = 0.f) {
     const size_t total = (size_t)n * (size_t)max_nodes;
+    const bool vl_path = K > 1 || K == -1;  // -1: the virtual-loss kernels with ONE leaf per step (tests)
+    if (K == -1) K = 1;
+    const size_t rows = (size_t)n * (size_t)(vl_path ? K : 1);  // rows of one batched forward
     RESERVE(ctx->a_state, sizeof(diee_bg_state) * total);
     RESERVE(ctx->a_parent, 4 * total);
     RESERVE(ctx->a_first, 4 * total);
@@ -70,13 +75,13 @@ static int32_t alpha_search_device(diee_ctx *ctx, diee_net *net, const diee_bg_s
     RESERVE(ctx->a_prior, 4 * total);
     RESERVE(ctx->a_action, 4 * total);
     RESERVE(ctx->a_nnodes, 4 * (size_t)n);
-    RESERVE(ctx->a_selg, 4 * (size_t)n);
-    RESERVE(ctx->a_seln, 4 * (size_t)n);
+    RESERVE(ctx->a_selg, 4 * rows);
+    RESERVE(ctx->a_seln, 4 * rows);
     RESERVE(ctx->a_status, 4 * (size_t)n);
     RESERVE(ctx->a_any, 4 * (size_t)cfg->iterations + 4);
-    RESERVE(ctx->a_batch, sizeof(diee_bg_state) * (size_t)n);
-    RESERVE(ctx->a_policy, sizeof(float) * DIEE_ACTION_SPACE * (size_t)n);
-    RESERVE(ctx->a_valueout, sizeof(float) * (size_t)n);
+    RESERVE(ctx->a_batch, sizeof(diee_bg_state) * rows);
+    RESERVE(ctx->a_policy, sizeof(float) * DIEE_ACTION_SPACE * rows);
+    RESERVE(ctx->a_valueout, sizeof(float) * rows);
     RESERVE(ctx->a_dir, sizeof(float) * DIEE_ACTION_SPACE);
     P.max_nodes = max_nodes;
     P.state = ctx->a_state.p;
@@ -99,6 +104,18 @@ static int32_t alpha_search_device(diee_ctx *ctx, diee_net *net, const diee_bg_s
     ctx->net_evals += (uint64_t)n;
     CU(launch_alpha_root(st, P, d_states, d_ids, n, *cfg, seed, epoch));
     ctx->launches += 1;
+    if (vl_path) {  // non-parity: iterations / K steps of up to K leaves per game
+        for (int left = (int)cfg->iterations; left > 0; left -= K) {
+            const int budget = left < K ? left : K;
+            CU(launch_alpha_select_vl(st, P, n, *cfg, K, vl, budget));
+            rc = diee_net_forward_dev(ctx, net, P.batch, (int32_t)rows, P.policy, P.value_out);
+            if (rc != DIEE_OK) return rc;
+            ctx->net_evals += (uint64_t)n * (uint64_t)budget;
+            CU(launch_alpha_expand_vl(st, P, d_ids, n, *cfg, seed, epoch, K, vl));
+            ctx->launches += 2;
+        }
+        return DIEE_OK;
+    }
     for (uint32_t it = 0; it < cfg->iterations; ++it) {  // :149-201
         CU(launch_alpha_select(st, P, n, *cfg, (int)it));
         rc = diee_net_forward_dev(ctx, net, P.batch, n, P.policy, P.value_out);  // forward_t on all N slots (:186)
@@ -215,6 +232,48 @@ int32_t diee_alpha_search_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state 
     return DIEE_OK;
 }
 
+// non-parity search: up to `leaves_per_game` leaves per game and step with virtual loss (host buffers)
+int32_t diee_alpha_search_vl(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, const uint32_t *game_ids,
+                             const diee_mcts_cfg *cfg, uint64_t seed, uint32_t epoch, int32_t max_nodes, int32_t leaves_per_game,
+                             float virtual_loss, uint16_t *root_ids_out, diee_move *root_moves_out, float *root_visits_out,
+                             int32_t *root_counts_out, int32_t *status_out) {
+    int32_t rc = check_alpha_args(ctx, net, n, cfg, epoch);
+    if (rc != DIEE_OK) return rc;
+    if (n == 0) return DIEE_OK;
+    if (!states || !game_ids || !root_ids_out || !root_visits_out || !root_counts_out || !status_out || leaves_per_game < 1 ||
+        leaves_per_game > 64 || !(virtual_loss >= 0.f))
+        return fail(ctx, DIEE_ERR_INVALID, "alpha_search_vl: bad argument");
+    for (int i = 0; i < n; ++i)
+        if (states[i].roll[0] == 0 && states[i].roll[1] == 0) return fail(ctx, DIEE_ERR_NOT_ROLLED, "alpha_search_vl: state %d has not been rolled", i);
+    if (max_nodes <= 0) max_nodes = default_max_nodes(cfg);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    RESERVE(ctx->a_states_in, sizeof(diee_bg_state) * (size_t)n);
+    RESERVE(ctx->a_ids_in, 4 * (size_t)n);
+    RESERVE(ctx->a_root_ids, 2 * (size_t)n * DIEE_MAX_MOVES);
+    RESERVE(ctx->a_root_moves, 4 * (size_t)n * DIEE_MAX_MOVES);
+    RESERVE(ctx->a_root_visits, 4 * (size_t)n * DIEE_MAX_MOVES);
+    RESERVE(ctx->a_root_counts, 4 * (size_t)n);
+    CU(cudaMemcpyAsync(ctx->a_states_in.p, states, sizeof(diee_bg_state) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->a_ids_in.p, game_ids, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    AlphaPool P;
+    // K = 1 still runs the virtual-loss kernels (K passed as 2 would change the search): force the vl path with K >= 1
+    rc = alpha_search_device(ctx, net, (const diee_bg_state *)ctx->a_states_in.p, n, (const uint32_t *)ctx->a_ids_in.p, cfg, seed, epoch,
+                             max_nodes, P, leaves_per_game == 1 ? -1 : leaves_per_game, virtual_loss);
+    if (rc != DIEE_OK) return rc;
+    CU(launch_alpha_root_out(st, P, n, (uint16_t *)ctx->a_root_ids.p, (uint32_t *)ctx->a_root_moves.p, (float *)ctx->a_root_visits.p,
+                             (int32_t *)ctx->a_root_counts.p));
+    ctx->launches += 1;
+    const size_t nm = (size_t)n * DIEE_MAX_MOVES;
+    CU(cudaMemcpyAsync(root_ids_out, ctx->a_root_ids.p, 2 * nm, cudaMemcpyDeviceToHost, st));
+    if (root_moves_out) CU(cudaMemcpyAsync(root_moves_out, ctx->a_root_moves.p, 4 * nm, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(root_visits_out, ctx->a_root_visits.p, 4 * nm, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(root_counts_out, ctx->a_root_counts.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(status_out, ctx->a_status.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return DIEE_OK;
+}
+
 uint64_t diee_net_eval_count(const diee_ctx *ctx) { return ctx ? ctx->net_evals : 0; }
 
 // self_play_parallel (alpha_parallel.rs:101-231).  Live games stay resident on the device between
@@ -238,8 +297,11 @@ int32_t diee_selfplay_run_ex(diee_ctx *ctx, diee_net *net, int32_t n_games, cons
     if (rc != DIEE_OK) return rc;
     diee_selfplay_opts o{};
     if (opts) o = *opts;
-    if (o.max_waves < 0 || o.flags != 0 || o.leaves_per_game > 1 || o.target_games != 0)
-        return fail(ctx, DIEE_ERR_INVALID, "selfplay_run_ex: unsupported option");
+    const bool refill = (o.flags & DIEE_SP_REFILL) != 0;
+    if (o.max_waves < 0 || (o.flags & ~DIEE_SP_REFILL) != 0 || o.leaves_per_game < 0 || o.leaves_per_game > 64 || o.target_games < 0 ||
+        !(o.virtual_loss >= 0.f) || (refill && o.target_games == 0 && o.max_waves == 0) || (!refill && o.target_games != 0))
+        return fail(ctx, DIEE_ERR_INVALID, "selfplay_run_ex: bad option (a refilled run needs target_games or max_waves)");
+    const int K = o.leaves_per_game > 1 ? o.leaves_per_game : 0;  // > 1: the non-parity search of alpha_kernels.cu
     diee_selfplay_report rep{};
     if (!rec_out || !pi_ids_out || !pi_vals_out || !n_rec_out || !n_pi_out || !(temperature > 0.f))
         return fail(ctx, DIEE_ERR_INVALID, "selfplay_run: bad argument");
@@ -258,16 +320,23 @@ int32_t diee_selfplay_run_ex(diee_ctx *ctx, diee_net *net, int32_t n_games, cons
     std::vector<uint16_t> sp_ids;
     std::vector<float> sp_vals;
     const float tinv = (float)(1.0 / (double)temperature);
-    for (int g = 0; g < N; ++g) {  // T::new() + roll_die (:103-111)
+    std::vector<uint32_t> gid((size_t)N);  // the game a slot plays (refilled runs give a finished game's slot a new one)
+    uint32_t next_gid = first_game_id + (uint32_t)N;
+    auto new_game = [&](int g, uint32_t id) {  // T::new() + roll_die (:103-111)
         static const int8_t opening[24] = {2, 0, 0, 0, 0, -5, 0, -3, 0, 0, 0, 5, -5, 0, 0, 0, 3, 0, 5, 0, 0, 0, 0, -2};
+        gid[g] = id;
         memset(&state[g], 0, sizeof(diee_bg_state));
         memcpy(state[g].pts, opening, 24);
         state[g].player = -1;
         uint32_t w[4];
-        philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), 0, first_game_id + (uint32_t)g, DIEE_STREAM_INIT, 0, w);
+        philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), 0, id, DIEE_STREAM_INIT, 0, w);
         state[g].roll[0] = (uint8_t)die_of(w[0]);
         state[g].roll[1] = (uint8_t)die_of(w[1]);
-    }
+        n_rounds[g] = 0;
+        mem[g].clear();
+        alive[g] = 1;
+    };
+    for (int g = 0; g < N; ++g) new_game(g, first_game_id + (uint32_t)g);
     RESERVE(ctx->a_states_in, sizeof(diee_bg_state) * (size_t)N);
     RESERVE(ctx->a_ids_in, 4 * (size_t)N);
     RESERVE(ctx->a_root_ids, 2 * (size_t)N * DIEE_MAX_MOVES);
@@ -291,7 +360,7 @@ int32_t diee_selfplay_run_ex(diee_ctx *ctx, diee_net *net, int32_t n_games, cons
             const Mem &m = mem[g][(size_t)mi];
             if (n_rec >= rec_cap || n_pi + m.pi_n > pi_cap) return false;
             diee_traj_record &r = rec_out[n_rec++];
-            r.state = m.st; r.game_id = first_game_id + (uint32_t)g; r.ply = (uint16_t)m.ply;
+            r.state = m.st; r.game_id = gid[g]; r.ply = (uint16_t)m.ply;
             r.outcome = (int8_t)(relabel ? (winner == m.player ? 1 : (winner == -m.player ? -1 : 0)) : 0);
             r.pad = 0; r.n_pi = (uint16_t)m.pi_n; r.pad2 = 0; r.pi_offset = (uint32_t)n_pi;
             memcpy(pi_ids_out + n_pi, sp_ids.data() + m.pi_off, sizeof(uint16_t) * (size_t)m.pi_n);
@@ -303,9 +372,9 @@ int32_t diee_selfplay_run_ex(diee_ctx *ctx, diee_net *net, int32_t n_games, cons
     for (;;) {  // while !states.is_empty() (:129)
         int nl = 0;
         for (int g = 0; g < N; ++g)
-            if (alive[g]) { live[nl] = state[g]; ids[nl] = first_game_id + (uint32_t)g; idx_of[nl] = g; ++nl; }
+            if (alive[g]) { live[nl] = state[g]; ids[nl] = gid[g]; idx_of[nl] = g; ++nl; }
         if (nl == 0) break;
-        if (o.max_waves > 0 && waves >= o.max_waves) {
+        if ((o.max_waves > 0 && waves >= o.max_waves) || (refill && o.target_games > 0 && rep.games_finished >= o.target_games)) {
             // time box: the games still running hand over what they have recorded so far, outcome 0 (not a reference
             // behaviour: a bounded sample of the same work for benchmarks)
             for (int g = 0; g < N; ++g)
@@ -320,7 +389,7 @@ int32_t diee_selfplay_run_ex(diee_ctx *ctx, diee_net *net, int32_t n_games, cons
         CU(cudaMemcpyAsync(ctx->a_ids_in.p, ids.data(), 4 * (size_t)nl, cudaMemcpyHostToDevice, st));
         AlphaPool P;
         rc = alpha_search_device(ctx, net, (const diee_bg_state *)ctx->a_states_in.p, nl, (const uint32_t *)ctx->a_ids_in.p, cfg, seed,
-                                 (uint32_t)waves, max_nodes, P);  // fresh tree every game-move (:137)
+                                 (uint32_t)waves, max_nodes, P, K, o.virtual_loss);  // fresh tree every game-move (:137)
         if (rc != DIEE_OK) return rc;
         ++waves;
         CU(launch_alpha_root_out(st, P, nl, (uint16_t *)ctx->a_root_ids.p, (uint32_t *)ctx->a_root_moves.p, (float *)ctx->a_root_visits.p,
@@ -353,7 +422,7 @@ int32_t diee_selfplay_run_ex(diee_ctx *ctx, diee_net *net, int32_t n_games, cons
                 alive[g] = 0;
             }
             uint32_t w[4];
-            philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)n_rounds[g], first_game_id + (uint32_t)g, DIEE_STREAM_GAME, 0, w);
+            philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)n_rounds[g], gid[g], DIEE_STREAM_GAME, 0, w);
             rolls[2 * pi] = (uint8_t)die_of(w[0]);
             rolls[2 * pi + 1] = (uint8_t)die_of(w[1]);
             double dsum = 0.0;
@@ -370,7 +439,7 @@ int32_t diee_selfplay_run_ex(diee_ctx *ctx, diee_net *net, int32_t n_games, cons
             double total = 0.0;
             for (int j = 0; j < DIEE_ACTION_SPACE; ++j) total += dense[j];
             uint32_t sw[4];
-            philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)n_rounds[g], first_game_id + (uint32_t)g, DIEE_STREAM_SAMPLE, 0, sw);
+            philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)n_rounds[g], gid[g], DIEE_STREAM_SAMPLE, 0, sw);
             const double pick = unit53(sw[0], sw[1]) * total;
             double cum = 0.0;
             int action = -1, lastnz = -1;
@@ -403,15 +472,22 @@ int32_t diee_selfplay_run_ex(diee_ctx *ctx, diee_net *net, int32_t n_games, cons
         for (int pi = 0; pi < nl; ++pi) {
             const int g = idx_of[pi];
             state[g] = live[pi];
-            if (cap_count[pi] >= 0 && !emit(g, false, 0, cap_count[pi]))
-                return fail(ctx, DIEE_ERR_OVERFLOW, "selfplay_run: record buffers too small");
-            if (chosen[pi] == SEQ_EMPTY) continue;  // the pass branch `continue`s before the winner test
-            const int win = state[g].off[0] == 15 ? -1 : (state[g].off[1] == 15 ? 1 : 0);
-            if (win != 0) {  // :215-223
-                if (!emit(g, true, win, (int)mem[g].size())) return fail(ctx, DIEE_ERR_OVERFLOW, "selfplay_run: record buffers too small");
-                alive[g] = 0;
-                rep.games_finished += 1;
+            if (cap_count[pi] >= 0) {
+                if (!emit(g, false, 0, cap_count[pi])) return fail(ctx, DIEE_ERR_OVERFLOW, "selfplay_run: record buffers too small");
+                rep.games_finished += 1;  // a game = played to a winner or to the round cap
             }
+            // (the pass branch `continue`s before the winner test; a capped game still plays this move and, if it wins
+            // with it, is emitted a second time -- quirk Q10, kept in the reference mode only)
+            if (chosen[pi] != SEQ_EMPTY && (alive[g] || !refill)) {
+                const int win = state[g].off[0] == 15 ? -1 : (state[g].off[1] == 15 ? 1 : 0);
+                if (win != 0) {  // :215-223
+                    if (!emit(g, true, win, (int)mem[g].size())) return fail(ctx, DIEE_ERR_OVERFLOW, "selfplay_run: record buffers too small");
+                    if (alive[g]) rep.games_finished += 1;
+                    alive[g] = 0;
+                }
+            }
+            // non-parity: the slot of a finished game starts the next game, so the forward batch stays at n_games
+            if (refill && !alive[g] && !(o.target_games > 0 && rep.games_finished >= o.target_games)) new_game(g, next_gid++);
         }
     }
     *n_rec_out = n_rec; *n_pi_out = n_pi;

@@ -210,6 +210,100 @@ alpha_expand_kernel(AlphaPool P, const uint32_t *__restrict__ game_ids, int n, d
     }
 }
 
+// ---------------------------------------------------------------- NON-PARITY throughput mode
+// K leaves per game and iteration with virtual loss.  The reference selects ONE leaf per game per iteration
+// (alpha_mcts.rs:149-201, quirk Q8), so a search is `iterations` strictly sequential forwards of N boards; here a step
+// selects up to K leaves per game -- each descent leaves a virtual loss (visits += 1, value -= vl) on its path so that
+// the next one goes elsewhere --, one forward evaluates the N x K rows, and the expansion half replaces every virtual
+// loss by the real value.  iterations / K forwards of N x K boards: the same number of evaluations, K times fewer
+// dependent steps.  Not reference behaviour (the quirks Q9 / Q12 are dropped too: a slot without a leaf evaluates a
+// dummy row that nobody reads); with K = 1 and no terminal leaf it IS the reference's search, bit for bit
+// (tests/test_gpu_alpha.py).
+__global__ void __launch_bounds__(AW * 32)
+alpha_select_vl_kernel(AlphaPool P, int n, diee_mcts_cfg cfg, int K, float vl, int budget) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = blockIdx.x * AW + wib;
+    if (g >= n) return;
+    const size_t base = (size_t)g * P.max_nodes;
+    const diee_bg_state *st = reinterpret_cast<const diee_bg_state *>(P.state);
+    for (int k = 0; k < K; ++k) {
+        int leaf = -1;
+        if (k < budget) {
+            int cur = 0;
+            for (;;) {
+                const int nc = P.nchild[base + cur];
+                if (nc == 0) break;
+                const int first = P.first[base + cur];
+                const float s = __fsqrt_rn(P.visits[base + cur]);
+                float bs = -INFINITY;
+                int bi = -1;
+                for (int k0 = 0; k0 < nc; k0 += 32) {
+                    const int c = k0 + lane;
+                    if (c < nc) {
+                        const size_t ch = base + first + c;
+                        const float vis = P.visits[ch], val = P.value[ch], pri = P.prior[ch];
+                        const float q = vis == 0.0f ? 0.0f : __fdiv_rn(val, vis);
+                        const float sc = __fadd_rn(q, __fmul_rn(__fmul_rn(cfg.c, __fdiv_rn(s, __fadd_rn(vis, 1.0f))), pri));
+                        if (!(bs > sc)) { bs = sc; bi = first + c; }
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const float os = __shfl_xor_sync(FULL, bs, d);
+                    const int oi = __shfl_xor_sync(FULL, bi, d);
+                    const bool take = oi >= 0 && (bi < 0 || (oi > bi ? !(bs > os) : (os > bs)));
+                    if (take) { bs = os; bi = oi; }
+                }
+                cur = bi;
+            }
+            const int off0 = st[base + cur].off[0], off1 = st[base + cur].off[1];
+            const int w = off0 == 15 ? -1 : (off1 == 15 ? 1 : 0);
+            if (w != 0) {
+                const int rp = st[base].player;
+                alpha_backprop(P, g, cur, w == rp ? 1.0f : (w == -rp ? -1.0f : 0.0f), lane);  // a real result, at once
+            } else if (P.first[base + cur] != -2) {  // -2: already waiting for its evaluation in this step
+                leaf = cur;
+                if (lane == 0) {
+                    P.first[base + cur] = -2;
+                    for (int i = cur; i >= 0; i = P.parent[base + i]) {  // virtual loss along the path
+                        P.visits[base + i] = __fadd_rn(P.visits[base + i], 1.0f);
+                        P.value[base + i] = __fsub_rn(P.value[base + i], vl);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        const size_t slot = (size_t)g * K + k;
+        if (lane == 0) P.sel_node[slot] = leaf;
+        const size_t src = base + (leaf >= 0 ? leaf : 0);  // no leaf: a dummy row (the root), never read back
+        reinterpret_cast<unsigned char *>(P.batch + slot)[lane] = reinterpret_cast<const unsigned char *>(st + src)[lane];
+    }
+}
+
+__global__ void __launch_bounds__(AW * 32)
+alpha_expand_vl_kernel(AlphaPool P, const uint32_t *__restrict__ game_ids, int n, diee_mcts_cfg cfg, uint64_t seed, uint32_t epoch,
+                       int K, float vl) {
+    __shared__ WarpSlab slabs[AW];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = blockIdx.x * AW + wib;
+    if (g >= n) return;
+    const size_t base = (size_t)g * P.max_nodes;
+    for (int k = 0; k < K; ++k) {
+        const size_t slot = (size_t)g * K + k;
+        const int node = P.sel_node[slot];
+        if (node < 0) continue;
+        if (lane == 0) P.first[base + node] = -1;
+        __syncwarp();
+        int status = DIEE_OK;
+        alpha_expand(P, g, node, P.policy + slot * DIEE_ACTION_SPACE, nullptr, 0.f, seed, game_ids[g], epoch, slabs[wib], lane, status);
+        if (lane == 0) {
+            if (status != DIEE_OK) P.status[g] = status;
+            const float v = P.value_out[slot];
+            for (int i = node; i >= 0; i = P.parent[base + i])  // the visit is already counted: swap the virtual loss for v
+                P.value[base + i] = __fadd_rn(__fadd_rn(P.value[base + i], vl), v);
+        }
+        __syncwarp();
+    }
+}
+
 // root children -> (action id, move, visits) in child order (input of get_prob_tensor_parallel, utils.rs:42-58)
 __global__ void __launch_bounds__(AW * 32)
 alpha_root_out_kernel(AlphaPool P, int n, uint16_t *__restrict__ ids_out, uint32_t *__restrict__ moves_out,
@@ -243,6 +337,15 @@ cudaError_t launch_alpha_select(cudaStream_t st, const AlphaPool &P, int n, cons
 cudaError_t launch_alpha_expand(cudaStream_t st, const AlphaPool &P, const uint32_t *game_ids, int n, const diee_mcts_cfg &cfg,
                                 uint64_t seed, uint32_t epoch, int iter) {
     alpha_expand_kernel<<<agrid(n), AW * 32, 0, st>>>(P, game_ids, n, cfg, seed, epoch, iter);
+    return cudaGetLastError();
+}
+cudaError_t launch_alpha_select_vl(cudaStream_t st, const AlphaPool &P, int n, const diee_mcts_cfg &cfg, int K, float vl, int budget) {
+    alpha_select_vl_kernel<<<agrid(n), AW * 32, 0, st>>>(P, n, cfg, K, vl, budget);
+    return cudaGetLastError();
+}
+cudaError_t launch_alpha_expand_vl(cudaStream_t st, const AlphaPool &P, const uint32_t *game_ids, int n, const diee_mcts_cfg &cfg,
+                                   uint64_t seed, uint32_t epoch, int K, float vl) {
+    alpha_expand_vl_kernel<<<agrid(n), AW * 32, 0, st>>>(P, game_ids, n, cfg, seed, epoch, K, vl);
     return cudaGetLastError();
 }
 cudaError_t launch_alpha_root_out(cudaStream_t st, const AlphaPool &P, int n, uint16_t *ids_out, uint32_t *moves_out,

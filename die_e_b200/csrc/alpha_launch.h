@@ -27,6 +27,10 @@ cudaError_t launch_alpha_root(cudaStream_t st, const AlphaPool &P, const diee_bg
 cudaError_t launch_alpha_select(cudaStream_t st, const AlphaPool &P, int n, const diee_mcts_cfg &cfg, int iter);
 cudaError_t launch_alpha_expand(cudaStream_t st, const AlphaPool &P, const uint32_t *game_ids, int n, const diee_mcts_cfg &cfg,
                                 uint64_t seed, uint32_t epoch, int iter);
+// non-parity: up to K leaves per game and step with virtual loss vl; `budget` = leaves still allowed this step
+cudaError_t launch_alpha_select_vl(cudaStream_t st, const AlphaPool &P, int n, const diee_mcts_cfg &cfg, int K, float vl, int budget);
+cudaError_t launch_alpha_expand_vl(cudaStream_t st, const AlphaPool &P, const uint32_t *game_ids, int n, const diee_mcts_cfg &cfg,
+                                   uint64_t seed, uint32_t epoch, int K, float vl);
 cudaError_t launch_alpha_root_out(cudaStream_t st, const AlphaPool &P, int n, uint16_t *ids_out, uint32_t *moves_out,
                                   float *visits_out, int32_t *counts_out);
 

@@ -290,7 +290,8 @@ int32_t diee_selfplay_run(diee_ctx *ctx, diee_net *net, int32_t n_games, const d
 /* The same driver with options (all zero / NULL = diee_selfplay_run).  max_waves > 0 time-boxes the run: after that
  * many game-move waves the games still running emit what they have recorded with outcome 0 (a bounded sample of the
  * same work for benchmarks; not a reference behaviour).  The other fields select the NON-PARITY throughput modes of
- * SURVEY 8(f)4 and must be 0 unless the library says it supports them (DIEE_ERR_INVALID otherwise). */
+ * DIEE_SP_REFILL (needs target_games or max_waves) and leaves_per_game > 1 (diee_alpha_search_vl).  With
+ * all of them zero the run is the reference's self_play_parallel, record for record. */
 typedef struct {
     uint32_t flags;          /* DIEE_SP_* */
     int32_t max_waves;       /* 0 = until every game has ended */
@@ -308,6 +309,15 @@ int32_t diee_selfplay_run_ex(diee_ctx *ctx, diee_net *net, int32_t n_games, cons
                              uint64_t seed, uint32_t first_game_id, int32_t max_nodes, const diee_selfplay_opts *opts,
                              diee_traj_record *rec_out, int32_t rec_cap, uint16_t *pi_ids_out, float *pi_vals_out, int32_t pi_cap,
                              int32_t *n_rec_out, int32_t *n_pi_out, int32_t *n_waves_out, diee_selfplay_report *report_out);
+/* NON-PARITY search: up to leaves_per_game leaves per game and step, each descent leaving a virtual loss
+ * (visits + 1, value - virtual_loss) on its path; cfg->iterations / leaves_per_game forwards of n x leaves_per_game
+ * boards instead of cfg->iterations forwards of n.  Same outputs as diee_alpha_search.  The reference selects one leaf per
+ * game and iteration (alpha_mcts.rs:149-201); with leaves_per_game = 1, virtual_loss = 0 and no terminal leaf in reach
+ * this IS that search (tests/test_gpu_alpha.py). */
+int32_t diee_alpha_search_vl(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, const uint32_t *game_ids,
+                             const diee_mcts_cfg *cfg, uint64_t seed, uint32_t epoch, int32_t max_nodes, int32_t leaves_per_game,
+                             float virtual_loss, uint16_t *root_ids_out, diee_move *root_moves_out, float *root_visits_out,
+                             int32_t *root_counts_out, int32_t *status_out);
 uint64_t diee_net_eval_count(const diee_ctx *ctx);
 
 /* ---- multi-GPU: the one exchange step of the path ----

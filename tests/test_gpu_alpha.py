@@ -160,3 +160,70 @@ def test_self_play_bit_exact(ctx, net, oracle, n_games, iters, limit):
         assert len(np.unique(rec["game_id"])) == n_games
     else:
         assert (rec["outcome"] == 0).any()                         # round-capped games (Q10)
+
+
+# ---------------------------------------------------------------- NON-PARITY throughput modes
+def test_virtual_loss_search_with_one_leaf_is_the_reference_search(ctx, net, oracle):
+    """diee_alpha_search_vl with one leaf per step and no virtual loss runs the virtual-loss kernels but must give the
+    reference's search exactly, as long as no terminal leaf / no-move leaf is in reach (where quirks Q9 / Q12 differ)"""
+    states = positions.midgame_positions(seed=17, n=32, max_adv=30)     # early positions: 20 iterations cannot reach the end
+    ids = np.arange(700, 732, dtype=np.uint32)
+    cfg = oracle.mcts_cfg(iterations=20, c=2.0, limit=400, alpha=0.3, eps=0.25)
+    a = ctx.alpha_search(net, states, ids, cfg, 11, epoch=2)
+    b = ctx.alpha_search_vl(net, states, ids, cfg, 11, epoch=2, leaves_per_game=1, virtual_loss=0.0)
+    for x, y in zip(a, b):
+        assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
+
+
+@pytest.mark.parametrize("K,vl", [(4, 1.0), (8, 0.5)])
+def test_virtual_loss_search_properties(ctx, net, oracle, K, vl):
+    """K leaves per game and step: same legal moves at the root, every simulation accounted for (root children visits
+    sum to the number of evaluated or terminal leaves <= iterations), deterministic, and close to the one-leaf search
+    (total-variation distance of the root visit distributions)"""
+    n, iters = 48, 64
+    states = positions.midgame_positions(seed=19, n=n, max_adv=100)
+    ids = np.arange(n, dtype=np.uint32)
+    cfg = oracle.mcts_cfg(iterations=iters, c=2.0, limit=400, alpha=0.3, eps=0.25)
+    ref = ctx.alpha_search(net, states, ids, cfg, 5, epoch=1)
+    got = ctx.alpha_search_vl(net, states, ids, cfg, 5, epoch=1, leaves_per_game=K, virtual_loss=vl)
+    again = ctx.alpha_search_vl(net, states, ids, cfg, 5, epoch=1, leaves_per_game=K, virtual_loss=vl)
+    for x, y in zip(got, again):
+        assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
+    assert (got[4] == 0).all() and (got[3] == ref[3]).all()
+    tv = []
+    for g in range(n):
+        nc = int(ref[3][g])
+        assert got[1][g, :nc].tobytes() == ref[1][g, :nc].tobytes() and (got[0][g, :nc] == ref[0][g, :nc]).all()
+        s = float(got[2][g, :nc].sum())
+        assert s <= iters + 1e-3 and (nc == 0 or s >= iters * 0.5), (g, s)   # duplicates of a pending leaf are skipped, not re-evaluated
+        if nc:
+            a, b = got[2][g, :nc] / max(s, 1), ref[2][g, :nc] / max(float(ref[2][g, :nc].sum()), 1)
+            tv.append(0.5 * float(np.abs(a - b).sum()))
+    print(f"\n[virtual loss K={K} vl={vl}] mean TV distance to the one-leaf search {np.mean(tv):.3f}, max {np.max(tv):.3f}")
+    assert np.mean(tv) < 0.25
+
+
+def test_refilled_self_play(ctx, net, oracle):
+    """DIEE_SP_REFILL: a finished game's slot starts a new game (new id) so the forward batch stays full; the FIRST game of
+    every slot is the reference's game record for record; later games are complete, labelled games of fresh ids"""
+    n_games, iters, target = 12, 4, 30
+    cfg = oracle.mcts_cfg(iterations=iters, c=2.0, limit=400, alpha=0.3, eps=0.25)
+    base, b_ids, b_vals, _ = ctx.selfplay_run(net, n_games, cfg, 1.25, seed=31, first_game_id=1000)
+    from die_e_b200 import _ffi
+    rec, pi_ids, pi_vals, rep = ctx.selfplay_run_ex(net, n_games, cfg, 1.25, 31, 1000, flags=_ffi.SP_REFILL, target_games=target)
+    assert rep["games_finished"] >= target and rep["games_finished"] < target + n_games
+    assert rep["game_moves"] == rep["waves"] * n_games or rep["games_cut"] < n_games        # every slot busy in every wave
+    ids = np.unique(rec["game_id"])
+    assert ids.min() == 1000 and ids.max() >= 1000 + target - 1
+    # a refilled batch couples games differently from wave `k` on (the Dirichlet epoch is the wave number and slot 0's root
+    # feeds quirk Q9), so only games that ran entirely while no slot had been refilled yet are the reference's own
+    first_finish = min(int(base[base["game_id"] == g]["ply"].max()) for g in range(1000, 1000 + n_games))
+    for g in range(1000, 1000 + n_games):
+        a, b = base[base["game_id"] == g], rec[rec["game_id"] == g]
+        k = int((a["ply"] <= first_finish).sum())
+        assert a[:k]["state"].tobytes() == b[:k]["state"].tobytes(), g
+    done = [g for g in ids if (rec[rec["game_id"] == g]["outcome"] != 0).any()]
+    assert len(done) >= target - 2                                     # (a round-capped game is labelled 0)
+    for g in done:
+        r = rec[rec["game_id"] == g]
+        assert set(np.unique(r["outcome"])) <= {-1, 1} and (np.diff(r["ply"].astype(int)) > 0).all()

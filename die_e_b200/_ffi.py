@@ -50,6 +50,7 @@ SYMBOLS = [
     "diee_net_create", "diee_net_destroy", "diee_net_set_precision", "diee_net_param_count", "diee_net_forward", "diee_net_forward_dev",
     "diee_search_timing", "diee_search_work", "diee_comm_unique_id", "diee_comm_init", "diee_comm_destroy", "diee_traj_allgather",
     "diee_net_broadcast", "diee_dirichlet", "diee_alpha_search", "diee_alpha_search_dev", "diee_alpha_search_vl", "diee_selfplay_run", "diee_selfplay_run_ex", "diee_net_eval_count",
+    "diee_arena_create", "diee_arena_round", "diee_arena_read", "diee_arena_destroy",
 ]
 
 
@@ -393,6 +394,43 @@ class Context:
         self._chk(lib().diee_mcts_search_dev(self._h, C.c_int32(game_kind), _p(d_states), C.c_int32(n), _p(d_players), _p(cfg),
                                              C.c_uint64(seed), C.c_uint32(first_game_id), C.c_uint32(epoch), _p(d_best),
                                              _p(d_status), _p(d_stats)))
+
+
+AGENT_RANDOM, AGENT_MCTS = 0, 1
+
+
+class Arena:
+    """a diee_arena handle: versus::play with the games resident on the device (include/diee.h)"""
+
+    def __init__(self, ctx, n_games, seed, round_limit):
+        self.ctx, self.n = ctx, n_games
+        self._h = C.c_void_p(0)
+        ctx._chk(lib().diee_arena_create(ctx._h, C.c_int32(n_games), C.c_uint64(seed), C.c_int32(round_limit), C.byref(self._h)))
+
+    def round(self, agent_p1, agent_p2, cfg=None):
+        """one round of the reference's loop -> (retired so far, wins p1, wins p2, draws)"""
+        cfg = np.ascontiguousarray(cfg, dtype=MCTS_CFG).reshape(-1)[:1] if cfg is not None else None
+        out = np.zeros(5, dtype=np.int32)
+        self.ctx._chk(lib().diee_arena_round(self.ctx._h, self._h, C.c_int32(agent_p1), C.c_int32(agent_p2), _p(cfg), _p(out)))
+        return int(out[0]), int(out[1]), int(out[2]), int(out[3])
+
+    def read(self):
+        states = np.zeros(self.n, dtype=BG_STATE)
+        winners = np.zeros(self.n, dtype=np.int8)
+        rounds = np.zeros(self.n, dtype=np.int32)
+        self.ctx._chk(lib().diee_arena_read(self.ctx._h, self._h, _p(states), _p(winners), _p(rounds)))
+        return states, winners, rounds
+
+    def close(self):
+        if self._h and self.ctx._h:
+            lib().diee_arena_destroy(self.ctx._h, self._h)
+        self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 NET_BF16, NET_SPLIT3, NET_FP32 = 0, 1, 2

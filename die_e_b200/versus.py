@@ -238,8 +238,35 @@ def _bg_actions(ctx, player, side, states, live_ids, all_states, cfg, temp, seed
     raise ValueError("Agent::None cannot play (versus.rs:316)")
 
 
+def play_backgammon_device(player1, player2, mcts_config=None, seed=0xD1EE, num_games=400, round_limit=400, ctx=None):
+    """the arena with the games resident on the device (csrc/arena.cu): per round a handful of launches and one
+    20-byte read-back; Agent::Mcts and Agent::Random.  Same results as play_backgammon(device_resident=False)."""
+    ctx = ctx or _ffi.default_context()
+    cfg = mcts_config or MctsConfig()
+    kinds = {Agent.Random: _ffi.AGENT_RANDOM, Agent.Mcts: _ffi.AGENT_MCTS}
+    a1, a2 = kinds[player1.player_type], kinds[player2.player_type]
+    arena = _ffi.Arena(ctx, num_games, seed, round_limit)
+    retired = 0
+    while retired < num_games:
+        retired, wins_p1, wins_p2, _ = arena.round(a1, a2, cfg.record())
+    states, winners, rounds = arena.read()
+    arena.close()
+    res = PlayResult(player1.player_type, player2.player_type, int(wins_p1), int(wins_p2), num_games, winners, rounds)
+    res.final_states = states
+    return res
+
+
 def play_backgammon(player1, player2, mcts_config=None, temp=1.0, seed=0xD1EE, num_games=400, round_limit=400, ctx=None,
-                    keep_games=False, record_turns=False):
+                    keep_games=False, record_turns=False, device_resident=None):
+    """device_resident: None = on the device whenever both agents can (Mcts / Random) and no per-game files are kept"""
+    can = (player1.player_type in (Agent.Random, Agent.Mcts) and player2.player_type in (Agent.Random, Agent.Mcts)
+           and not keep_games and not record_turns)
+    if device_resident is None:
+        device_resident = can
+    if device_resident:
+        if not can:
+            raise ValueError("the device-resident arena plays Agent::Mcts / Agent::Random and keeps no per-game files")
+        return play_backgammon_device(player1, player2, mcts_config, seed, num_games, round_limit, ctx)
     ctx = ctx or _ffi.default_context()
     cfg = mcts_config or MctsConfig()
     states = _bg_initial(num_games, seed)

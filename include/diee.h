@@ -320,6 +320,22 @@ int32_t diee_alpha_search_vl(diee_ctx *ctx, diee_net *net, const diee_bg_state *
                              int32_t *root_counts_out, int32_t *status_out);
 uint64_t diee_net_eval_count(const diee_ctx *ctx);
 
+/* ---- the arena: versus::play (src/versus.rs:160-268) with the games resident on the device ----
+ * n_games games from the opening position (those of the second half start with skip_turn, versus.rs:172-174), streams
+ * keyed by the game's index (DIEE_STREAM_INIT / _GAME / search streams with epoch = round).  One diee_arena_round = one
+ * pass of the reference's loop: partition by the side to move, each side's agent picks an action for every one of its
+ * games (Agent::Mcts = mct_search, Agent::Random = uniform over the legal moves), apply_move / skip_turn, winner and
+ * round-limit tests, retirement.  Nothing but the 5-word summary crosses the bus per round:
+ * summary_out = {games retired so far, wins of player 1 (the -1 side), wins of player 2, draws, 0}.  The arena is over
+ * when summary_out[0] == n_games.  diee_arena_read gives the per-game results (all nullable). */
+typedef struct diee_arena diee_arena;
+enum { DIEE_AGENT_RANDOM = 0, DIEE_AGENT_MCTS = 1 };
+int32_t diee_arena_create(diee_ctx *ctx, int32_t n_games, uint64_t seed, int32_t round_limit, diee_arena **out);
+int32_t diee_arena_round(diee_ctx *ctx, diee_arena *arena, int32_t agent_p1, int32_t agent_p2, const diee_mcts_cfg *cfg,
+                         int32_t *summary_out);
+int32_t diee_arena_read(diee_ctx *ctx, diee_arena *arena, diee_bg_state *states_out, int8_t *winners_out, int32_t *rounds_out);
+int32_t diee_arena_destroy(diee_ctx *ctx, diee_arena *arena);
+
 /* ---- multi-GPU: the one exchange step of the path ----
  * Games never interact (the reference runs them as independent rayon tasks, versus.rs:303-316): each GPU plays
  * its own shard of game ids and no collective sits on the data path.  What is exchanged is the OUTPUT: finished

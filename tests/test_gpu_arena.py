@@ -110,3 +110,35 @@ def test_saved_games_round_trip(ctx, oracle, tmp_path):
     lines = []
     print_game(tmp_path / f"{g0.id}.json", out=lines.append)
     assert lines[0] == f"Game ID: {g0.id}" and any(l.startswith("Action:") for l in lines)
+
+
+def test_device_resident_arena_equals_the_host_loop(ctx, oracle):
+    """csrc/arena.cu (games resident in HBM, one 20-byte read-back per round) against the host-side loop of
+    die_e_b200/versus.py -- which the tests above hold to the oracle twin: same winners, same rounds; plus the reference's
+    own arena size (400 games, MCTS vs random) timed both ways"""
+    import time
+    from die_e_b200 import _ffi
+    from die_e_b200.mcts import MctsConfig
+    from die_e_b200.versus import Agent, Player, play
+    cfg = MctsConfig(iterations=16, c=2.0, simulate_round_limit=40, mode_flags=_ffi.MODE_PASS_CHILD)
+    for p1, p2, seed in ((Agent.Mcts, Agent.Random, 61), (Agent.Random, Agent.Mcts, 62), (Agent.Mcts, Agent.Mcts, 63)):
+        dev = play("backgammon", Player(p1), Player(p2), cfg, seed=seed, num_games=24, round_limit=400, ctx=ctx, device_resident=True)
+        host = play("backgammon", Player(p1), Player(p2), cfg, seed=seed, num_games=24, round_limit=400, ctx=ctx, device_resident=False)
+        assert (dev.winners == host.winners).all() and (dev.rounds == host.rounds).all()
+        assert (dev.wins_p1, dev.wins_p2, dev.draws) == (host.wins_p1, host.wins_p2, host.draws)
+    # without PASS_CHILD the reference panics on a no-move node (node.rs:119-121): the arena reports it
+    bad = MctsConfig(iterations=16, c=2.0, simulate_round_limit=40, mode_flags=0)
+    with pytest.raises(_ffi.DieeError) as e:
+        play("backgammon", Player(Agent.Mcts), Player(Agent.Mcts), bad, seed=64, num_games=64, round_limit=400, ctx=ctx)
+    assert e.value.code == _ffi.ERR_NO_MOVES_PANIC
+    # versus.rs:168-169: 400 games, 400 rounds; MCTS(iterations=100, limit=400) vs random
+    cfg = MctsConfig(iterations=100, c=2.0, simulate_round_limit=400, mode_flags=_ffi.MODE_PASS_CHILD)
+    t0 = time.perf_counter()
+    dev = play("backgammon", Player(Agent.Mcts), Player(Agent.Random), cfg, seed=0xD1EE, ctx=ctx)
+    t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    host = play("backgammon", Player(Agent.Mcts), Player(Agent.Random), cfg, seed=0xD1EE, ctx=ctx, device_resident=False)
+    t_host = time.perf_counter() - t0
+    assert (dev.winners == host.winners).all() and (dev.rounds == host.rounds).all() and dev.n_games == 400
+    print(f"\n[arena] backgammon MCTS(100) vs random, 400 games, {int(dev.rounds.max())} rounds: {dev.wins_p1} / {dev.wins_p2} / {dev.draws}; "
+          f"device-resident {t_dev * 1e3:.0f} ms, host loop {t_host * 1e3:.0f} ms")

@@ -72,7 +72,7 @@ struct ConvLayer {
     float *wf32 = nullptr;       // fp32 mode: [9][c_in][c_out] (BatchNorm folded)
     int c_in = 0, c_out = 0;
     float *bias = nullptr;       // [c_out_pad]
-    CUtensorMap wmap, wmap3;
+    CUtensorMap wmap, wmap3, wmap3_n64;
     CUtensorMap wmap_n64, wmap_n32;  // the same weights through 64- and 32-row boxes: small batches run smaller CTA tiles
     int c_out_pad = 0, K = 0, ntaps = 9, chunks = 4, bn = 128;
 };
@@ -183,6 +183,7 @@ static int32_t build_conv(diee_ctx *ctx, ConvLayer &L, const float *w, const flo
     int32_t rc = upload_split(ctx, L, wf);
     if (rc != DIEE_OK) return rc;
     if (!make_w_map(&L.wmap3, L.w3, c_out_pad, 3 * K, bn)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (split weights) failed");
+    if (c_out_pad >= 64 && !make_w_map(&L.wmap3_n64, L.w3, c_out_pad, 3 * K, 64)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (split weights) failed");
     return upload_f32(ctx, L, wf, c_in, c_out);
 }
 
@@ -341,6 +342,16 @@ int32_t diee_net_destroy(diee_ctx *ctx, diee_net *net) {
     return DIEE_OK;
 }
 
+// DIEE_CONV_2CTA=n: run the tower's 16-board x 128-channel tile on CTA pairs (cta_group::2, net_kernels.cu) from n boards on.
+// OFF by default: bit-identical to the single-CTA form (tests/test_gpu_net.py) but measured SLOWER on B200 -- one
+// alpha_mcts_parallel of 1,024 games: bf16 152.8 -> 160.1 ms, split3 827.6 -> 860.7 ms -- so the shared-memory port is not
+// what holds the main loop at 64 % tensor-pipe activity (DESIGN.md 3.6 records the experiment).
+static bool use_cta_pairs(int n) {
+    const char *e = getenv("DIEE_CONV_2CTA");
+    const int min_n = e ? atoi(e) : 0;
+    return min_n > 0 && n >= min_n;
+}
+
 // forward_t (nnet.rs:120-133): policy = softmax(policy_head(tower(x))), value = tanh(value_head(tower(x)))
 int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *states, int32_t n, float *policy_out,
                              float *value_out) {
@@ -400,11 +411,17 @@ int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *
         float *small = (float *)net->small.p, *rscale = (float *)net->row_scale.p;
         unsigned int *bmax = (unsigned int *)net->board_max.p;
         // one convolution: x planes (map mx) * w planes -> fp32 `out` [rows][c_out]; first = the im2col layer (one exact plane, unit 1)
+        const bool pairs2 = use_cta_pairs(n);
         auto conv = [&](const CUtensorMap &mx, const ConvLayer &L, bool first, const float *residual, float *out, int c_out, bool want_max) -> int32_t {
-            CU(launch_conv(st, L.bn, mx, L.wmap3, n, L.ntaps, L.chunks, nullptr, nullptr, small, 1, c_out, 0, first ? 2 : 5,
-                           first ? PAIRS_SMALL2 : PAIRS_SMALL5, first ? 0 : F, L.K));
             SplitEpilogue sp{small, first ? nullptr : rscale, L.wscale, residual, want_max ? bmax : nullptr};
-            CU(launch_conv(st, L.bn, mx, L.wmap3, n, L.ntaps, L.chunks, L.bias, nullptr, out, 2, c_out, 1, 1, PAIRS_BIG, first ? 0 : F, L.K, &sp));
+            if (pairs2 && !first && L.bn == 128) {  // tower layers on CTA pairs
+                CU(launch_conv_pair(st, mx, L.wmap3_n64, n, L.ntaps, L.chunks, nullptr, nullptr, small, 1, c_out, 0, 5, PAIRS_SMALL5, F, L.K));
+                CU(launch_conv_pair(st, mx, L.wmap3_n64, n, L.ntaps, L.chunks, L.bias, nullptr, out, 2, c_out, 1, 1, PAIRS_BIG, F, L.K, &sp));
+            } else {
+                CU(launch_conv(st, L.bn, mx, L.wmap3, n, L.ntaps, L.chunks, nullptr, nullptr, small, 1, c_out, 0, first ? 2 : 5,
+                               first ? PAIRS_SMALL2 : PAIRS_SMALL5, first ? 0 : F, L.K));
+                CU(launch_conv(st, L.bn, mx, L.wmap3, n, L.ntaps, L.chunks, L.bias, nullptr, out, 2, c_out, 1, 1, PAIRS_BIG, first ? 0 : F, L.K, &sp));
+            }
             ctx->launches += 2;
             return DIEE_OK;
         };
@@ -470,8 +487,13 @@ int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *
     CUtensorMap *mx = &mA, *my = &mB, *mz = &mC;
     for (int b = 0; b < net->blocks; ++b) {
         const ConvLayer &c1 = net->convs[1 + 2 * b], &c2 = net->convs[2 + 2 * b];
-        CU(launch_conv_tile(st, bn, nb, *mx, wmap_of(c1), n, 9, c1.chunks, c1.bias, nullptr, by, 0, F, 1));
-        CU(launch_conv_tile(st, bn, nb, *my, wmap_of(c2), n, 9, c2.chunks, c2.bias, bx, bz, 0, F, 1));
+        if (nb == 16 && bn == 128 && use_cta_pairs(n)) {
+            CU(launch_conv_pair(st, *mx, c1.wmap_n64, n, 9, c1.chunks, c1.bias, nullptr, by, 0, F, 1));
+            CU(launch_conv_pair(st, *my, c2.wmap_n64, n, 9, c2.chunks, c2.bias, bx, bz, 0, F, 1));
+        } else {
+            CU(launch_conv_tile(st, bn, nb, *mx, wmap_of(c1), n, 9, c1.chunks, c1.bias, nullptr, by, 0, F, 1));
+            CU(launch_conv_tile(st, bn, nb, *my, wmap_of(c2), n, 9, c2.chunks, c2.bias, bx, bz, 0, F, 1));
+        }
         ctx->launches += 2;
         void *tp = bx; bx = bz; bz = tp;
         CUtensorMap *tm = mx; mx = mz; mz = tm;

@@ -119,6 +119,55 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on the two SMs of a TPC execute ONE tcgen05.mma of M = 256 ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// both CTAs issue their own loads; the transaction bytes of both land on the LEADER's barrier (peer bit of the address cleared)
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_4d_2sm(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at the same offset in BOTH CTAs of the pair once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile with 128-byte rows in the 128B swizzle: 8-row groups are 1024 B apart.
@@ -139,12 +188,20 @@ constexpr int CONV_THREADS = 192;
 // boards as at 1,024): about 0.2 us plus its MMAs at the rate their operands leave shared memory.  So a
 // small batch is spread over as many CTAs as there are SMs, each with a smaller tile (net.cu picks the shape per
 // launch), and the small tiles take KC = 2 chunks of 64 input channels per pipeline stage: half as many K-blocks.
-template <int BN, int NB, int KC = 1>
+// TWO = a CTA PAIR (cluster of 2, cta_group::2) computes 2 x NB boards x BN channels with M = 256 MMAs: each CTA stages its own
+// boards and HALF of the weight tile, and both tensor cores read both halves.  What bounds the single-CTA kernel is the
+// The hypothesis it tests: the single-CTA main loop is bound by the shared-memory port -- a 128x128x16 MMA reads 8 KB of
+// operands per 68 tensor cycles (121 B/cycle) while TMA writes the next stage (79 B/cycle), 200 B/cycle wanted against 128
+// B/cycle, i.e. the 64 % tensor-pipe activity ncu shows for a long K loop (profiles/r02_conv3x3_split3_ncu_full_summary.txt);
+// the pair needs 6 KB per MMA and 56 KB per stage, 157 B/cycle.  MEASURED: same bits, 4-5 % SLOWER (net.cu use_cta_pairs),
+// so that is not the limit; the form stays selectable (DIEE_CONV_2CTA) and tested, and is off by default.
+template <int BN, int NB, int KC = 1, bool TWO = false>
 struct ConvCfg {
     static constexpr int ROWS = NB * 24;
     static constexpr int MT = (ROWS + 127) / 128;          // the last M-tile may be partly padding (rows >= ROWS: never stored)
     static constexpr int A_BYTES = ROWS * 128;             // one chunk (64 bf16 channels) of the activation tile
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int B_ROWS = TWO ? BN / 2 : BN;      // weight rows this CTA stages
+    static constexpr int B_BYTES = B_ROWS * 128;
     static constexpr int STAGE_BYTES = KC * (A_BYTES + B_BYTES);  // [A chunk 0 .. A chunk KC-1 | B chunk 0 .. B chunk KC-1]
     static constexpr int STAGES_RAW = (216 * 1024) / STAGE_BYTES;
 #ifndef DIEE_CONV_MAX_STAGES
@@ -184,13 +241,13 @@ struct ConvEpi {
     const float *residual_f32;  // fp32 [rows][c_out_total] (nullable)
     unsigned int *board_max;    // [board]: max of the (post-ReLU, >= 0) outputs as float bits, atomicMax (nullable)
 };
-template <int BN, int NB, int KC>
+template <int BN, int NB, int KC, bool TWO = false>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int n_boards,
                   int ntaps, int chunks, const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual,
                   void *__restrict__ out, int out_mode, int c_out_total, int relu, int npairs, uint32_t pairs, int a_plane,
                   int b_plane, ConvEpi epi) {
-    using Cfg = ConvCfg<BN, NB, KC>;
+    using Cfg = ConvCfg<BN, NB, KC, TWO>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *tail = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -201,8 +258,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     float *bias_smem = reinterpret_cast<float *>(tail + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int board0 = blockIdx.x * NB;
+    const int board0 = blockIdx.x * NB;  // (TWO: the cluster is two consecutive blockIdx.x = two consecutive board tiles)
     const int n0 = blockIdx.y * BN;
+    const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;   // issues the MMAs of the pair and owns the `full` barriers
     const int per_pair = ntaps * chunks;
     const int num_kb = per_pair * npairs / KC;  // pipeline steps: KC consecutive chunks of one tap each (chunks % KC == 0)
 
@@ -213,10 +272,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    if (warp == 1) { if (TWO) tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS); else tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); }
     for (int i = threadIdx.x; i < BN; i += CONV_THREADS) bias_smem[i] = bias ? bias[n0 + i] : 0.f;
     tc_fence_before();
-    __syncthreads();
+    if (TWO) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -229,7 +289,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 uint8_t *sa = smem + s * Cfg::STAGE_BYTES;
                 uint8_t *sb = sa + KC * Cfg::A_BYTES;
-                mbar_expect_tx(&full_bar[s], (uint32_t)Cfg::STAGE_BYTES);
+                // the pair's two loads of a stage complete on the leader's barrier
+                if (leader) mbar_expect_tx(&full_bar[s], (uint32_t)Cfg::STAGE_BYTES * (TWO ? 2u : 1u));
                 const int k0 = kb * KC;
                 const int pr = k0 / per_pair, kin = k0 - pr * per_pair;
                 const int pi = (int)((pairs >> (4 * pr)) & 3u), pj = (int)((pairs >> (4 * pr + 2)) & 3u);
@@ -237,15 +298,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 const int kh = ntaps == 9 ? tap / 3 : 1, kw = ntaps == 9 ? tap - (tap / 3) * 3 : 1;
 #pragma unroll
                 for (int h = 0; h < KC; ++h) {
-                    tma_load_4d(sa + h * Cfg::A_BYTES, &tmapA, &full_bar[s], pi * a_plane + (chunk + h) * 64, kw - 1, kh - 1, board0);
-                    tma_load_2d(sb + h * Cfg::B_BYTES, &tmapB, &full_bar[s], pj * b_plane + (kin + h) * 64, n0);
+                    if (TWO) {
+                        tma_load_4d_2sm(sa + h * Cfg::A_BYTES, &tmapA, &full_bar[s], pi * a_plane + (chunk + h) * 64, kw - 1, kh - 1, board0);
+                        tma_load_2d_2sm(sb + h * Cfg::B_BYTES, &tmapB, &full_bar[s], pj * b_plane + (kin + h) * 64, n0 + (int)cta_rank * Cfg::B_ROWS);
+                    } else {
+                        tma_load_4d(sa + h * Cfg::A_BYTES, &tmapA, &full_bar[s], pi * a_plane + (chunk + h) * 64, kw - 1, kh - 1, board0);
+                        tma_load_2d(sb + h * Cfg::B_BYTES, &tmapB, &full_bar[s], pj * b_plane + (kin + h) * 64, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one elected thread) =====
-        constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        // ===== MMA issuer (one elected thread; of the pair: the leader's) =====
+        constexpr uint32_t idesc = umma_idesc_bf16(TWO ? 256 : 128, BN);
+        for (int kb = 0; leader && kb < num_kb; ++kb) {
             const int s = kb % Cfg::STAGES;
             const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
             mbar_wait(&full_bar[s], ph);
@@ -261,12 +327,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzled row
                             const uint64_t ad = umma_desc_sw128(sa + h * Cfg::A_BYTES + mt * (128 * 128) + kk * 32);
                             const uint64_t bd = umma_desc_sw128(sb + h * Cfg::B_BYTES + kk * 32);
-                            umma_bf16(tmem_base + (uint32_t)(mt * BN), ad, bd, idesc, (kb | h | kk) != 0 ? 1u : 0u);
+                            if (TWO) umma_bf16_2sm(tmem_base + (uint32_t)(mt * BN), ad, bd, idesc, (kb | h | kk) != 0 ? 1u : 0u);
+                            else umma_bf16(tmem_base + (uint32_t)(mt * BN), ad, bd, idesc, (kb | h | kk) != 0 ? 1u : 0u);
                         }
                     }
                 }
-                umma_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
-                if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulators complete
+                if (TWO) {
+                    umma_commit_2sm(&empty_bar[s]);                       // frees the stage in BOTH CTAs
+                    if (kb == num_kb - 1) umma_commit_2sm(tmem_full_bar);  // both epilogues may read their accumulators
+                } else {
+                    umma_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulators complete
+                }
             }
             __syncwarp();
         }
@@ -373,10 +445,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         }
         tc_fence_before();
     }
-    __syncthreads();
+    if (TWO) cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer's tensor core may still read this CTA's tiles
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (TWO) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -677,6 +750,35 @@ static cudaError_t launch_conv_bn(cudaStream_t st, const CUtensorMap &ta, const 
     return cudaGetLastError();
 }
 
+// the CTA-pair form of the 16-board x 128-channel tile: `tb` encoded with a box of 64 rows (each CTA stages half of the tile)
+cudaError_t launch_conv_pair(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps, int chunks,
+                             const float *bias, const void *residual_v, void *out, int out_mode, int c_out_total, int relu,
+                             int npairs, uint32_t pairs, int a_plane, int b_plane, const SplitEpilogue *sp) {
+    using Cfg = ConvCfg<128, 16, 1, true>;
+    const __nv_bfloat16 *residual = static_cast<const __nv_bfloat16 *>(residual_v);
+    ConvEpi epi{};
+    if (sp) epi = ConvEpi{sp->addend, sp->row_scale, sp->col_scale, sp->residual_f32, sp->board_max};
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<128, 16, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    const unsigned tiles = (unsigned)((n_boards + 15) / 16);
+    cfg.gridDim = dim3((tiles + 1u) & ~1u, (unsigned)(c_out_total / 128));  // a tile past the batch loads zeros and stores nothing
+    cfg.blockDim = dim3(CONV_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<128, 16, 1, true>, ta, tb, n_boards, ntaps, chunks, bias, residual, out, out_mode,
+                              c_out_total, relu, npairs, pairs, a_plane, b_plane, epi);
+}
+
 // `ta` must have been encoded with a box of nb boards, `tb` with a box of bn rows
 cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,
                              int chunks, const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
@@ -684,6 +786,7 @@ cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap 
     const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(residual);
     ConvEpi epi{};
     if (sp) epi = ConvEpi{sp->addend, sp->row_scale, sp->col_scale, sp->residual_f32, sp->board_max};
+
     // several chunks per pipeline stage where the tile is small enough for >= 3 such stages and the layer's chunk count
     // divides (DIEE_CONV_KC=n caps it; 1 keeps one chunk per stage everywhere)
     static const bool one_chunk = getenv("DIEE_CONV_KC") && atoi(getenv("DIEE_CONV_KC")) == 1;

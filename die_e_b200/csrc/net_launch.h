@@ -19,6 +19,10 @@ cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap 
 cudaError_t launch_conv(cudaStream_t st, int bn, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps, int chunks,
                         const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
                         int npairs = 1, uint32_t pairs = 0, int a_plane = 0, int b_plane = 0, const SplitEpilogue *sp = nullptr);
+// the 16-board x 128-channel tile on a CTA PAIR (cta_group::2): ta with a box of 16 boards, tb with a box of 64 rows
+cudaError_t launch_conv_pair(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps, int chunks,
+                             const float *bias, const void *residual, void *out, int out_mode, int c_out_total, int relu,
+                             int npairs = 1, uint32_t pairs = 0, int a_plane = 0, int b_plane = 0, const SplitEpilogue *sp = nullptr);
 // fp32 activations -> the three operand planes of the split-precision mode (one CTA per board)
 cudaError_t launch_split_planes(cudaStream_t st, const float *y, unsigned int *board_max, int n, int C, int sb, void *planes, float *scale_out);
 cudaError_t launch_conv_f32(cudaStream_t st, const float *x, const diee_bg_state *states, int n, int c_in, const float *w,

@@ -160,3 +160,28 @@ def test_resnet_host_object(ctx, oracle, tmp_path):
     net2 = nnet.ResNet.from_path(path, ctx=ctx)
     p3, v3 = net2.forward_t(states)
     assert (p3 == p).all() and (v3 == v).all()
+
+
+@pytest.mark.parametrize("n", [256, 300, 1024])
+def test_cta_pair_convolution_gives_the_same_bits(ctx, oracle, monkeypatch, n):
+    """from 256 boards on the tower's 16-board x 128-channel tile runs on CTA pairs (cta_group::2: one M = 256 MMA over two
+    SMs, each CTA staging its own boards and half of the weight tile).  Every output element is accumulated over the same K
+    order by the same instruction kind, so the pair form must agree with the single-CTA form bit for bit -- in bf16 and in
+    the split-precision mode, for a batch that fills its last pair (256, 1,024) and one that does not (300 = 18.75 tiles)"""
+    from die_e_b200 import _ffi, nnet
+    tens = nnet.synthetic_tensors(seed=13, filters=256, blocks=2, bn_stats="random")
+    net = _ffi.Net(ctx, tens)
+    base = positions.midgame_positions(seed=9, n=64, max_adv=100)
+    states = np.concatenate([base] * ((n + 63) // 64))[:n]
+    states["roll"][:, 0] = 1 + (np.arange(n) % 6)          # make the boards differ
+    for mode in (_ffi.NET_BF16, _ffi.NET_SPLIT3):
+        net.set_precision(mode)
+        monkeypatch.setenv("DIEE_CONV_2CTA", "0")
+        monkeypatch.setenv("DIEE_CONV_TILE", "16,128")
+        p_ref, v_ref = net.forward(states)
+        monkeypatch.setenv("DIEE_CONV_2CTA", "1")
+        p, v = net.forward(states)
+        assert (p == p_ref).all() and (v == v_ref).all(), mode
+        monkeypatch.delenv("DIEE_CONV_2CTA")
+        monkeypatch.delenv("DIEE_CONV_TILE")
+    net.close()

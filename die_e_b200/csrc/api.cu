@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary of libdiee_cuda.so (include/diee.h).
 // Host-buffer entry points stage through ctx-owned device scratch; *_dev entry points are
 // stream-ordered on the ctx stream.  There is no CPU fallback anywhere in this library.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -17,6 +18,64 @@ using namespace diee;
 
 #include "bg_pb_table.h"
 #include "ctx.h"
+
+// ---------------- SM partition for the sliced search ----------------
+// DIEE_TREE_SMS=n: two green contexts split the device's SMs -- n SMs for the tree kernel (a chain of 100 dependent
+// iterations per game, a few warps per SM, bound by the latency of one iteration) and the rest for the rollouts of the
+// slices already expanded, so that the tree never shares an SM with rollout warps (round 1 measured that sharing costs the
+// tree kernel what the overlap wins).  EXPERIMENT, off by default.  Measured on B200 (1,024 games x 100 iterations, timeline
+// from a -DDIEE_TRACE build, tools/trace_sweep.sh): on 64 SMs the four tree slices end at 0.58 ms (0.46 ms unsliced on the
+// whole device) -- but every rollout slice of 25,600 rollouts takes 1.15-1.37 ms, as long as the one launch over all
+// 102,400 does: the rollout kernel is bound by its longest chains (~300 played plies at ~4 us per ply under load), not by
+// the number of rollouts, so the search ends at 1.57-1.79 ms whatever the slicing (1.67 ms unsliced).  Bit-identical
+// results (tests/test_gpu_mcts.py).  The driver entry points are looked up at run time (no link-time libcuda).
+template <class F>
+static bool driver_fn(const char *name, F &fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return false;
+    fn = reinterpret_cast<F>(p);
+    return true;
+}
+
+static void ensure_partition(diee_ctx *ctx) {
+    if (ctx->part_state != 0) return;
+    ctx->part_state = -1;
+    int tree_sms = 0;
+    if (const char *e = getenv("DIEE_TREE_SMS")) tree_sms = atoi(e);
+    if (tree_sms <= 0) return;  // no partition unless asked for
+    CUresult (*getDev)(CUdevice *, int) = nullptr;
+    CUresult (*getRes)(CUdevice, CUdevResource *, CUdevResourceType) = nullptr;
+    CUresult (*split)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int) = nullptr;
+    CUresult (*genDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int) = nullptr;
+    CUresult (*gcreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+    CUresult (*gstream)(CUstream *, CUgreenCtx, unsigned int, int) = nullptr;
+    if (!driver_fn("cuDeviceGet", getDev) || !driver_fn("cuDeviceGetDevResource", getRes) || !driver_fn("cuDevSmResourceSplitByCount", split) ||
+        !driver_fn("cuDevResourceGenerateDesc", genDesc) || !driver_fn("cuGreenCtxCreate", gcreate) || !driver_fn("cuGreenCtxStreamCreate", gstream))
+        return;
+    CUdevice dev;
+    CUdevResource all, grp, rem;
+    unsigned int nb = 1;
+    if (getDev(&dev, ctx->device) != CUDA_SUCCESS || getRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return;
+    if ((int)all.sm.smCount < tree_sms + 16) return;
+    if (split(&grp, &nb, &all, &rem, 0, (unsigned)tree_sms) != CUDA_SUCCESS || nb != 1) return;
+    CUdevResourceDesc d_tree, d_roll;
+    CUgreenCtx g_tree = nullptr, g_roll = nullptr;
+    if (genDesc(&d_tree, &grp, 1) != CUDA_SUCCESS || genDesc(&d_roll, &rem, 1) != CUDA_SUCCESS) return;
+    if (gcreate(&g_tree, d_tree, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
+    if (gcreate(&g_roll, d_roll, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
+    CUstream s = nullptr;
+    if (gstream(&s, g_tree, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return;
+    ctx->part_tree = (cudaStream_t)s;
+    for (int i = 0; i < 4; ++i) {
+        if (gstream(&s, g_roll, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) { ctx->part_tree = nullptr; return; }
+        ctx->part_roll[i] = (cudaStream_t)s;
+    }
+    if (cudaEventCreateWithFlags(&ctx->part_begin, cudaEventDisableTiming) != cudaSuccess) { ctx->part_tree = nullptr; return; }
+    ctx->part_gctx[0] = g_tree; ctx->part_gctx[1] = g_roll;
+    ctx->part_tree_sms = (int)grp.sm.smCount; ctx->part_roll_sms = (int)rem.sm.smCount;
+    ctx->part_state = 1;
+}
 
 extern "C" {
 
@@ -84,6 +143,18 @@ int32_t diee_ctx_destroy(diee_ctx *ctx) {
     }
     for (int i = 0; i < 3; ++i)
         if (ctx->ev_time[i]) cudaEventDestroy(ctx->ev_time[i]);
+    if (ctx->part_state == 1) {
+        CUresult (*sdestroy)(CUstream) = nullptr;
+        CUresult (*gdestroy)(CUgreenCtx) = nullptr;
+        if (driver_fn("cuStreamDestroy", sdestroy) && driver_fn("cuGreenCtxDestroy", gdestroy)) {
+            cudaStreamSynchronize(ctx->part_tree);
+            sdestroy((CUstream)ctx->part_tree);
+            for (int i = 0; i < 4; ++i) { cudaStreamSynchronize(ctx->part_roll[i]); sdestroy((CUstream)ctx->part_roll[i]); }
+            gdestroy((CUgreenCtx)ctx->part_gctx[0]);
+            gdestroy((CUgreenCtx)ctx->part_gctx[1]);
+        }
+        if (ctx->part_begin) cudaEventDestroy(ctx->part_begin);
+    }
     if (ctx->q_head.p) cudaFree(ctx->q_head.p);
     for (DevBuf *b : {&ctx->c_counts, &ctx->c_send, &ctx->c_recv})
         if (b->p) cudaFree(b->p);
@@ -388,6 +459,15 @@ static int32_t mcts_search_dev_impl(diee_ctx *ctx, int32_t game_kind, const void
     pipe.queue_heads = (unsigned long long *)ctx->q_head.p;
     pipe.t_begin = ctx->ev_time[0]; pipe.t_tree = ctx->ev_time[1]; pipe.t_end = ctx->ev_time[2];
     pipe.timed = &ctx->search_timed;
+    pipe.part_tree = nullptr; pipe.part_begin = nullptr;
+    for (int i = 0; i < SEARCH_SLICES; ++i) pipe.part_roll[i] = nullptr;
+    if (game_kind == DIEE_GAME_BACKGAMMON && !(cfg->mode_flags & DIEE_MODE_ROLLOUT_CHECK_CURRENT)) {
+        ensure_partition(ctx);
+        if (ctx->part_state == 1) {
+            pipe.part_tree = ctx->part_tree; pipe.part_begin = ctx->part_begin;
+            for (int i = 0; i < SEARCH_SLICES; ++i) pipe.part_roll[i] = ctx->part_roll[i];
+        }
+    }
     const size_t pairs = (size_t)cfg->iterations * (size_t)n;
     CU(cudaMemsetAsync(ctx->p_simnode.p, 0xFF, sizeof(int32_t) * pairs, ctx->stream));
     CU(cudaMemsetAsync(ctx->p_finals.p, 0, state_size(game_kind) * pairs, ctx->stream));

@@ -32,6 +32,12 @@ struct diee_ctx {
     cudaEvent_t ev_tree[4] = {nullptr, nullptr, nullptr, nullptr}, ev_roll[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_time[3] = {nullptr, nullptr, nullptr};  // begin | tree done | rollouts done of the last split search
     bool search_timed = false;
+    // SM partition for the sliced search (green contexts; api.cu ensure_partition): 0 = not tried, 1 = ready, -1 = unavailable
+    int part_state = 0;
+    void *part_gctx[2] = {nullptr, nullptr};  // CUgreenCtx: tree SMs | rollout SMs
+    cudaStream_t part_tree = nullptr, part_roll[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t part_begin = nullptr;
+    int part_tree_sms = 0, part_roll_sms = 0;
     // AlphaZero search arena + per-iteration batch buffers (alpha.cu)
     DevBuf a_state, a_parent, a_first, a_nchild, a_visits, a_value, a_prior, a_action, a_nnodes, a_selg, a_seln, a_status,
         a_any, a_batch, a_policy, a_valueout, a_dir, a_states_in, a_ids_in, a_root_ids, a_root_moves, a_root_visits,

@@ -34,6 +34,11 @@ struct SearchPipe {
     unsigned long long *queue_heads;  // SEARCH_SLICES job queue heads of the persistent lane kernel
     cudaEvent_t t_begin, t_tree, t_end;  // timing marks of an unsliced search (tree kernel | rollouts)
     bool *timed;                         // set when the marks of the last search are valid
+    // SM partition (green contexts, api.cu): the tree slices run on their own SMs, the rollouts of all but the last slice on
+    // the rest, so the latency-bound tree kernel never shares an SM with rollout warps.  Null streams = no partition.
+    cudaStream_t part_tree;
+    cudaStream_t part_roll[SEARCH_SLICES];
+    cudaEvent_t part_begin;
 };
 
 cudaError_t launch_bg_valid_moves(cudaStream_t st, const diee_bg_state *states, int n, diee_move *moves_out,

@@ -604,6 +604,26 @@ rollout_kernel(int n_games, diee_mcts_cfg cfg, uint64_t seed, uint32_t first_gam
     }
 }
 
+#ifdef DIEE_TRACE
+// experiment build only: a timeline of the sliced search (events around every tree slice and rollout slice)
+static cudaEvent_t g_trace_ev[2 + 4 * SEARCH_SLICES];
+static int g_trace_slices = 0;
+static void trace_init() {
+    static bool done = false;
+    if (!done) { for (auto &e : g_trace_ev) cudaEventCreate(&e); done = true; }
+}
+extern "C" int diee_debug_search_trace(float *out, int cap) {  // ms since the search began: per slice tree begin/end, rollouts begin/end
+    cudaDeviceSynchronize();
+    int k = 0;
+    for (int s = 0; s < g_trace_slices && k + 4 <= cap; ++s)
+        for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&out[k++], g_trace_ev[0], g_trace_ev[2 + 4 * s + j]);
+    return k;
+}
+#define TRACE(idx, stream) cudaEventRecord(g_trace_ev[idx], stream)
+#else
+#define TRACE(idx, stream) ((void)0)
+#endif
+
 static inline int mcts_grid(int n) { return (n + MCTS_WARPS_PER_CTA - 1) / MCTS_WARPS_PER_CTA; }
 
 template <class G>
@@ -682,7 +702,11 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         // Measured on B200 (1,024 games x 100 iterations): 1 slice 3.39 ms, 2 slices 3.36 ms, 4 slices 3.96 ms per
         // search -- the latency-bound tree kernel loses as much to sharing the SMs as the overlap wins, so the
         // default is one slice; DIEE_SEARCH_SLICES keeps the experiment reproducible.
-        uint32_t slices = 1;
+        // With an SM PARTITION (green contexts; SearchPipe::part_tree) the picture changes: the tree slices run on their own
+        // SMs at full speed and the rollouts of slices 0 .. S-2 on the others, so a one-wave batch (the BASELINE 1,024
+        // games) no longer pays tree + rollouts but about tree + the longest rollout: 4 slices by default there.
+        const bool partitioned = pipe.part_tree != nullptr && n <= 2048 && cfg.iterations >= 8;
+        uint32_t slices = partitioned ? 4u : 1u;
         if (const char *ev = getenv("DIEE_SEARCH_SLICES")) slices = (uint32_t)atoi(ev);
         if (slices < 1u) slices = 1u;
         if (slices > (uint32_t)SEARCH_SLICES) slices = (uint32_t)SEARCH_SLICES;
@@ -705,17 +729,35 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
             *pipe.timed = true;
             return launch_bg_rollout_count(st, n, cfg, pp, stats_out, launches);
         }
+#ifdef DIEE_TRACE
+        trace_init();
+        g_trace_slices = (int)slices;
+        TRACE(0, st);
+#endif
+        cudaStream_t ts = st;  // stream of the tree slices
+        if (partitioned) {
+            ts = pipe.part_tree;
+            if ((e = cudaEventRecord(pipe.part_begin, st)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(ts, pipe.part_begin, 0)) != cudaSuccess) return e;
+        }
         for (uint32_t s = 0; s < slices; ++s) {
             const uint32_t a = (uint32_t)((uint64_t)cfg.iterations * s / slices), b = (uint32_t)((uint64_t)cfg.iterations * (s + 1) / slices);
-            mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
+            TRACE(2 + 4 * s, ts);
+            mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, ts>>>(
                 r, 0, n, players, cfg, a, b, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
+            TRACE(3 + 4 * s, ts);
             *launches += 1;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            if ((e = cudaEventRecord(pipe.tree_done[s], st)) != cudaSuccess) return e;
-            if ((e = cudaStreamWaitEvent(pipe.side[s], pipe.tree_done[s], 0)) != cudaSuccess) return e;
-            if ((e = launch_bg_rollouts(pipe.side[s], n, cfg, a, b, seed, first_game_id, epoch, pp, pipe.queue_heads + 2 * s, launches)) != cudaSuccess) return e;
-            if ((e = cudaEventRecord(pipe.roll_done[s], pipe.side[s])) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(pipe.tree_done[s], ts)) != cudaSuccess) return e;
+            // rollouts of the slice: beside the next tree slice on the rollout partition; the last slice's on the whole device
+            cudaStream_t rs = (partitioned && s + 1 < slices) ? pipe.part_roll[s] : pipe.side[s];
+            if ((e = cudaStreamWaitEvent(rs, pipe.tree_done[s], 0)) != cudaSuccess) return e;
+            TRACE(4 + 4 * s, rs);
+            if ((e = launch_bg_rollouts(rs, n, cfg, a, b, seed, first_game_id, epoch, pp, pipe.queue_heads + 2 * s, launches)) != cudaSuccess) return e;
+            TRACE(5 + 4 * s, rs);
+            if ((e = cudaEventRecord(pipe.roll_done[s], rs)) != cudaSuccess) return e;
         }
+        if (partitioned && (e = cudaStreamWaitEvent(st, pipe.tree_done[slices - 1], 0)) != cudaSuccess) return e;
         for (uint32_t s = 0; s < slices; ++s)
             if ((e = cudaStreamWaitEvent(st, pipe.roll_done[s], 0)) != cudaSuccess) return e;
         return launch_bg_rollout_count(st, n, cfg, pp, stats_out, launches);

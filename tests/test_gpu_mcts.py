@@ -135,6 +135,15 @@ def test_sliced_search_is_the_same_search(ctx, oracle, monkeypatch):
         got = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
         for a, b in zip(ref, got):
             assert np.asarray(a).tobytes() == np.asarray(b).tobytes()
+    # the same slices on an SM partition (green contexts: tree slices on 64 SMs, rollouts on the rest) and with the
+    # rollouts' items in game-minor order; a fresh context, because the partition is set up once per context
+    monkeypatch.setenv("DIEE_TREE_SMS", "64")
+    ctx2 = _ffi.Context(0)
+    got = ctx2.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
+    for a, b in zip(ref, got):
+        assert np.asarray(a).tobytes() == np.asarray(b).tobytes()
+    ctx2.close()
+    monkeypatch.delenv("DIEE_TREE_SMS")
     monkeypatch.delenv("DIEE_SEARCH_SLICES")
 
 

@@ -452,6 +452,9 @@ def run_ours(args, rank, world):
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.launch_count() - launches0
     last_epoch = (args.warmup + args.steps - 1) & 0xFFFF
+    timed_best = d_best.cpu().numpy().copy() if args.workload == "mcts" else None
+    timed_playout = (d_winners.cpu().numpy().copy(), d_plies.cpu().numpy().copy(),
+                     d_finals.cpu().numpy().copy().view(ffi.BG_STATE).reshape(-1)) if args.workload == "playout" else None
     if args.workload == "mcts" and args.rollout == "ref_exact":
         # the two kernels of the search timed alone (untimed extra searches, one launch each back to back on the stream): the
         # timed steps may run them sliced and overlapped on an SM partition, where a per-kernel duration means nothing
@@ -466,9 +469,6 @@ def run_ours(args, rank, world):
             del os.environ["DIEE_SEARCH_SLICES"]
         else:
             os.environ["DIEE_SEARCH_SLICES"] = keep
-    timed_best = d_best.cpu().numpy().copy() if args.workload == "mcts" else None
-    timed_playout = (d_winners.cpu().numpy().copy(), d_plies.cpu().numpy().copy(),
-                     d_finals.cpu().numpy().copy().view(ffi.BG_STATE).reshape(-1)) if args.workload == "playout" else None
     # The timed region of the short workloads is a few milliseconds, one nvidia-smi call takes longer: keep the SAME
     # step running (untimed, uncounted) until the sampler has seen the GPU under this load a few times.
     if args.workload != "selfplay":

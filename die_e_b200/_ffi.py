@@ -318,7 +318,13 @@ class Context:
         limit = int(cfg["simulate_round_limit"][0])
         opts = np.zeros(1, dtype=SELFPLAY_OPTS)
         opts[0] = (flags, max_waves, leaves_per_game, target_games, virtual_loss, 0)
-        rec_cap = rec_cap or ((target_games + n_games) * 300 if (flags & SP_REFILL) else n_games * (2 * limit + 4))
+        if not rec_cap:
+            if flags & SP_REFILL:
+                rec_cap = (target_games + n_games) * 300
+            elif max_waves:
+                rec_cap = n_games * (max_waves + 2)   # a time-boxed run records at most one fragment per game and wave
+            else:
+                rec_cap = n_games * (2 * limit + 4)
         pi_cap = pi_cap or rec_cap * 48
         rec = np.zeros(rec_cap, dtype=TRAJ)
         pi_ids = np.zeros(pi_cap, dtype=np.uint16)

@@ -392,7 +392,8 @@ def run_ours(args, rank, world):
                                moves=int(rep["game_moves"]))
             h2d, d2h = 0, 0
             step_e2e = None
-            metric, unit = "selfplay_games_per_sec", "games/s"
+            time_boxed = args.max_waves > 0 and not args.refill
+            metric, unit = ("selfplay_game_moves_per_sec", "game-moves/s") if time_boxed else ("selfplay_games_per_sec", "games/s")
     else:
         h_states = initial_states(ffi, first_gid, G)
         d_states = torch.from_numpy(h_states.view(np.uint8).reshape(G, 32)).to(dev)
@@ -447,7 +448,10 @@ def run_ours(args, rank, world):
             units += units_per_step
         else:
             evs[i][1].synchronize()
-            units += sp_info["finished"] if args.workload == "selfplay" else units_per_step  # games that reached a winner or the cap
+            if args.workload == "selfplay":  # games that reached a winner or the cap; a time-boxed run counts game-moves instead
+                units += sp_info["moves"] if time_boxed else sp_info["finished"]
+            else:
+                units += units_per_step
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.launch_count() - launches0
@@ -529,6 +533,7 @@ def run_ours(args, rank, world):
         # is bound by the latency of one game's 100 sequential iterations rather than by issue slots.
         detail["large_batch"] = sub_mcts(ctx, ffi, torch, dev, stream, rank, world, 8192, cfg, reduce_max)
         detail["large_batch_32768"] = sub_mcts(ctx, ffi, torch, dev, stream, rank, world, 32768, cfg, reduce_max, reps=2)
+        detail["large_batch_65536"] = sub_mcts(ctx, ffi, torch, dev, stream, rank, world, 65536, cfg, reduce_max, reps=2)
         # (2) rollouts that test the rolled-out state (the evident intent of node.rs:181, quirk Q5): the mode in which the
         # rollouts decide the search
         cc = np.zeros(1, dtype=ffi.MCTS_CFG)
@@ -543,6 +548,9 @@ def run_ours(args, rank, world):
                                         dist if world > 1 else None)
 
     # ---- reduce over ranks: max time, summed units ----
+    if world > 1 and args.workload == "selfplay":
+        for k in ("records", "evals", "finished", "cut", "moves"):
+            sp_info[k] = int(reduce_sum(sp_info[k]))
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s, t_wall], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -605,11 +613,13 @@ def run_ours(args, rank, world):
                 detail.update(net_evals_per_step=int(evals), waves_per_step=sp_info["waves"], records_per_step=sp_info["records"],
                               simulations_per_sec=round(evals / step_s, 1), games_finished_per_step=sp_info["finished"],
                               games_cut_per_step=sp_info["cut"], game_moves_per_sec=round(sp_info["moves"] / step_s, 1),
+                              games_per_sec_at_111_moves_per_game=round(sp_info["moves"] / step_s / 111.0, 2),
+                              concurrent_games=G * world,
                               mode=("NON-PARITY: " + ", ".join(x for x in (f"slot refill to {args.refill} games" if args.refill else "",
                                                                           f"{args.leaves} leaves per game and step, virtual loss 1" if args.leaves > 1 else "",
                                                                           f"time box {args.max_waves} waves" if args.max_waves else "") if x))
                               if (args.refill or args.leaves > 1 or args.max_waves) else "reference: self_play_parallel, record for record")
-            tf = NET_FLOP_PER_EVAL * evals / step_s / 1e12
+            tf = NET_FLOP_PER_EVAL * evals / step_s / 1e12 / (world if args.workload == "selfplay" else 1)  # per GPU
             roof = {"bound": "tensor", "achieved": round(tf, 2), "peak": sustained, "unit": "TFLOP/s", "frac": round(tf / sustained, 4),
                     "traffic": None, "peak_source": tsrc + " (sustained figure: the kernel runs inside a long step)",
                     "kernel": "conv3x3_tc_kernel (tcgen05, 38 of the 42 launches of one forward)",

@@ -72,7 +72,7 @@ struct ConvLayer {
     float *wf32 = nullptr;       // fp32 mode: [9][c_in][c_out] (BatchNorm folded)
     int c_in = 0, c_out = 0;
     float *bias = nullptr;       // [c_out_pad]
-    CUtensorMap wmap, wmap3, wmap3_n64;
+    CUtensorMap wmap, wmap3, wmap3_n64, wmap3_n32;
     CUtensorMap wmap_n64, wmap_n32;  // the same weights through 64- and 32-row boxes: small batches run smaller CTA tiles
     int c_out_pad = 0, K = 0, ntaps = 9, chunks = 4, bn = 128;
 };
@@ -184,6 +184,7 @@ static int32_t build_conv(diee_ctx *ctx, ConvLayer &L, const float *w, const flo
     if (rc != DIEE_OK) return rc;
     if (!make_w_map(&L.wmap3, L.w3, c_out_pad, 3 * K, bn)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (split weights) failed");
     if (c_out_pad >= 64 && !make_w_map(&L.wmap3_n64, L.w3, c_out_pad, 3 * K, 64)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (split weights) failed");
+    if (c_out_pad >= 32 && !make_w_map(&L.wmap3_n32, L.w3, c_out_pad, 3 * K, 32)) return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (split weights) failed");
     return upload_f32(ctx, L, wf, c_in, c_out);
 }
 
@@ -342,6 +343,25 @@ int32_t diee_net_destroy(diee_ctx *ctx, diee_net *net) {
     return DIEE_OK;
 }
 
+// The CTA tile of the tower: nb boards x bn output channels.  A CTA's time is set by its K loop (a K-block costs ~0.2 us plus
+// its MMAs) whatever the batch, so the smallest tile that still fits the whole layer in one wave of CTAs wins: 16 x 128 at
+// 1,024 boards, 8 x 64 at 256, 4 x 32 at 64 -- the long tail of a self-play batch.  DIEE_CONV_TILE="nb,bn" forces one.
+static void pick_conv_tile(diee_ctx *ctx, int n, int F, int &nb, int &bn) {
+    nb = 16; bn = 128;
+    static int sms = 0;
+    if (sms == 0) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device); if (sms <= 0) sms = 148; }
+    const int cand[5][2] = {{4, 32}, {8, 32}, {8, 64}, {8, 128}, {16, 128}};  // ascending bytes per K-block
+    for (int c = 0; c < 5; ++c) {
+        const int cnb = cand[c][0], cbn = cand[c][1];
+        if (F % cbn != 0) continue;
+        if ((long long)((n + cnb - 1) / cnb) * (F / cbn) <= sms) { nb = cnb; bn = cbn; break; }
+    }
+    if (const char *force_tile = getenv("DIEE_CONV_TILE")) {  // "nb,bn" (experiments, tests)
+        int a = 0, b = 0;
+        if (sscanf(force_tile, "%d,%d", &a, &b) == 2 && F % b == 0) { nb = a; bn = b; }
+    }
+}
+
 // DIEE_CONV_2CTA=n: run the tower's 16-board x 128-channel tile on CTA pairs (cta_group::2, net_kernels.cu) from n boards on.
 // OFF by default: bit-identical to the single-CTA form (tests/test_gpu_net.py) but measured SLOWER on B200 -- one
 // alpha_mcts_parallel of 1,024 games: bf16 152.8 -> 160.1 ms, split3 827.6 -> 860.7 ms -- so the shared-memory port is not
@@ -404,8 +424,11 @@ int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *
             CU(cudaMemsetAsync(net->board_max.p, 0, net->board_max.cap, ctx->stream));  // (split_planes_kernel leaves it zeroed)
         }
         RESERVE(net->row_scale, (size_t)n * 4);
-        CUtensorMap m_in, mP;
-        if (!make_act_map(&m_in, net->in0.p, n, 64) || !make_act_map(&mP, net->planes.p, n, 3 * F))
+        int nb, bn;
+        pick_conv_tile(ctx, n, F, nb, bn);  // the tower's tile (the first layer and the heads keep 16-board tiles)
+        CUtensorMap m_in, mP, mPt;
+        if (!make_act_map(&m_in, net->in0.p, n, 64) || !make_act_map(&mP, net->planes.p, n, 3 * F) ||
+            !make_act_map(&mPt, net->planes.p, n, 3 * F, nb))
             return fail(ctx, DIEE_ERR_CUDA, "cuTensorMapEncodeTiled (activations) failed");
         cudaStream_t st = ctx->stream;
         float *small = (float *)net->small.p, *rscale = (float *)net->row_scale.p;
@@ -414,9 +437,14 @@ int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *
         const bool pairs2 = use_cta_pairs(n);
         auto conv = [&](const CUtensorMap &mx, const ConvLayer &L, bool first, const float *residual, float *out, int c_out, bool want_max) -> int32_t {
             SplitEpilogue sp{small, first ? nullptr : rscale, L.wscale, residual, want_max ? bmax : nullptr};
-            if (pairs2 && !first && L.bn == 128) {  // tower layers on CTA pairs
+            const bool tower = !first && L.bn == 128;
+            if (pairs2 && tower && nb == 16 && bn == 128) {  // tower layers on CTA pairs
                 CU(launch_conv_pair(st, mx, L.wmap3_n64, n, L.ntaps, L.chunks, nullptr, nullptr, small, 1, c_out, 0, 5, PAIRS_SMALL5, F, L.K));
                 CU(launch_conv_pair(st, mx, L.wmap3_n64, n, L.ntaps, L.chunks, L.bias, nullptr, out, 2, c_out, 1, 1, PAIRS_BIG, F, L.K, &sp));
+            } else if (tower && !(nb == 16 && bn == 128)) {  // small batches: smaller tiles over all SMs (same bits)
+                const CUtensorMap &wm = bn == 128 ? L.wmap3 : bn == 64 ? L.wmap3_n64 : L.wmap3_n32;
+                CU(launch_conv_tile(st, bn, nb, mPt, wm, n, L.ntaps, L.chunks, nullptr, nullptr, small, 1, c_out, 0, 5, PAIRS_SMALL5, F, L.K));
+                CU(launch_conv_tile(st, bn, nb, mPt, wm, n, L.ntaps, L.chunks, L.bias, nullptr, out, 2, c_out, 1, 1, PAIRS_BIG, F, L.K, &sp));
             } else {
                 CU(launch_conv(st, L.bn, mx, L.wmap3, n, L.ntaps, L.chunks, nullptr, nullptr, small, 1, c_out, 0, first ? 2 : 5,
                                first ? PAIRS_SMALL2 : PAIRS_SMALL5, first ? 0 : F, L.K));
@@ -456,22 +484,8 @@ int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *
     RESERVE(net->actC, rows * F * 2);
     RESERVE(net->pfeat, rows * 32 * 2);
     RESERVE(net->vfeat, rows * 16 * 4);
-    // The CTA tile of the tower: nb boards x bn output channels.  A CTA's time is set by the bytes it pulls through its
-    // own SM's L2 port (nb * 3 KB + bn * 128 B per K-block), so the smallest tile that still fits the whole layer in one
-    // wave of CTAs wins: 16 x 128 at 1,024 boards, 8 x 64 at 256, 4 x 32 at 64 -- the long tail of a self-play batch.
-    const char *force_tile = getenv("DIEE_CONV_TILE");  // "nb,bn" (experiments, tests)
-    int nb = 16, bn = 128;
-    {
-        static int sms = 0;
-        if (sms == 0) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device); if (sms <= 0) sms = 148; }
-        const int cand[5][2] = {{4, 32}, {8, 32}, {8, 64}, {8, 128}, {16, 128}};  // ascending bytes per K-block
-        for (int c = 0; c < 5; ++c) {
-            const int cnb = cand[c][0], cbn = cand[c][1];
-            if (F % cbn != 0) continue;
-            if ((long long)((n + cnb - 1) / cnb) * (F / cbn) <= sms) { nb = cnb; bn = cbn; break; }
-        }
-        if (force_tile) { int a = 0, b = 0; if (sscanf(force_tile, "%d,%d", &a, &b) == 2 && F % b == 0) { nb = a; bn = b; } }
-    }
+    int nb, bn;
+    pick_conv_tile(ctx, n, F, nb, bn);
     CUtensorMap m_in, mA, mB, mC, m_head;
     if (!make_act_map(&m_in, net->in0.p, n, 64, nb) || !make_act_map(&mA, net->actA.p, n, F, nb) || !make_act_map(&mB, net->actB.p, n, F, nb) ||
         !make_act_map(&mC, net->actC.p, n, F, nb))

@@ -279,6 +279,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, the bias tile --
+    // constants of the net) may run while the previous layer's grid is still draining; its OUTPUT (this layer's
+    // activations, residual, scratch) is only touched after this wait.  Dependents may be scheduled as soon as this CTA is here.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -733,6 +738,12 @@ fc_f32_kernel(const float *__restrict__ feat, const float *__restrict__ wT, cons
 }
 
 // ---------------------------------------------------------------- launchers
+// DIEE_CONV_PDL=0 launches the convolutions without programmatic dependent launch (experiments)
+static bool pdl_enabled() {
+    static const bool on = !(getenv("DIEE_CONV_PDL") && atoi(getenv("DIEE_CONV_PDL")) == 0);
+    return on;
+}
+
 template <int BN, int NB, int KC>
 static cudaError_t launch_conv_bn(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,
                                   int chunks, const float *bias, const __nv_bfloat16 *residual, void *out, int out_mode,
@@ -743,11 +754,18 @@ static cudaError_t launch_conv_bn(cudaStream_t st, const CUtensorMap &ta, const 
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid((n_boards + NB - 1) / NB, c_out_total / BN);
-    conv3x3_tc_kernel<BN, NB, KC><<<grid, CONV_THREADS, ConvCfg<BN, NB, KC>::SMEM_BYTES, st>>>(ta, tb, n_boards, ntaps, chunks, bias, residual,
-                                                                                              out, out_mode, c_out_total, relu, npairs, pairs,
-                                                                                              a_plane, b_plane, epi);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((n_boards + NB - 1) / NB), (unsigned)(c_out_total / BN));
+    cfg.blockDim = dim3(CONV_THREADS);
+    cfg.dynamicSmemBytes = ConvCfg<BN, NB, KC>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol.wait in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, NB, KC>, ta, tb, n_boards, ntaps, chunks, bias, residual, out, out_mode,
+                              c_out_total, relu, npairs, pairs, a_plane, b_plane, epi);
 }
 
 // the CTA-pair form of the 16-board x 128-channel tile: `tb` encoded with a box of 64 rows (each CTA stages half of the tile)

@@ -133,17 +133,18 @@ def test_every_cta_tile_shape_gives_the_same_bits(ctx, oracle, monkeypatch):
     from die_e_b200 import _ffi, nnet
     tens = nnet.synthetic_tensors(seed=11, filters=256, blocks=2, bn_stats="random")
     net = _ffi.Net(ctx, tens)
-    net.set_precision(_ffi.NET_BF16)
     states, _ = _inputs(oracle, 43, seed=5)
-    monkeypatch.setenv("DIEE_CONV_TILE", "16,128")
-    p_ref, v_ref = net.forward(states)
-    for tile in ("8,128", "8,64", "8,32", "4,32"):
-        monkeypatch.setenv("DIEE_CONV_TILE", tile)
-        p, v = net.forward(states)
-        assert (p == p_ref).all() and (v == v_ref).all(), tile
-    monkeypatch.delenv("DIEE_CONV_TILE")
-    p, v = net.forward(states)   # the automatic choice
-    assert (p == p_ref).all() and (v == v_ref).all()
+    for mode in (_ffi.NET_BF16, _ffi.NET_SPLIT3):      # both tensor-core modes pick their tile the same way
+        net.set_precision(mode)
+        monkeypatch.setenv("DIEE_CONV_TILE", "16,128")
+        p_ref, v_ref = net.forward(states)
+        for tile in ("8,128", "8,64", "8,32", "4,32"):
+            monkeypatch.setenv("DIEE_CONV_TILE", tile)
+            p, v = net.forward(states)
+            assert (p == p_ref).all() and (v == v_ref).all(), (mode, tile)
+        monkeypatch.delenv("DIEE_CONV_TILE")
+        p, v = net.forward(states)   # the automatic choice
+        assert (p == p_ref).all() and (v == v_ref).all(), mode
     net.close()
 
 

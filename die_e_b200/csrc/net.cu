@@ -436,15 +436,30 @@ int32_t diee_net_forward_dev(diee_ctx *ctx, diee_net *net, const diee_bg_state *
         // one convolution: x planes (map mx) * w planes -> fp32 `out` [rows][c_out]; first = the im2col layer (one exact plane, unit 1)
         const bool pairs2 = use_cta_pairs(n);
         auto conv = [&](const CUtensorMap &mx, const ConvLayer &L, bool first, const float *residual, float *out, int c_out, bool want_max) -> int32_t {
-            SplitEpilogue sp{small, first ? nullptr : rscale, L.wscale, residual, want_max ? bmax : nullptr};
+            SplitEpilogue sp{small, first ? nullptr : rscale, L.wscale, residual, want_max ? bmax : nullptr, 0};
             const bool tower = !first && L.bn == 128;
             if (pairs2 && tower && nb == 16 && bn == 128) {  // tower layers on CTA pairs
                 CU(launch_conv_pair(st, mx, L.wmap3_n64, n, L.ntaps, L.chunks, nullptr, nullptr, small, 1, c_out, 0, 5, PAIRS_SMALL5, F, L.K));
                 CU(launch_conv_pair(st, mx, L.wmap3_n64, n, L.ntaps, L.chunks, L.bias, nullptr, out, 2, c_out, 1, 1, PAIRS_BIG, F, L.K, &sp));
-            } else if (tower && !(nb == 16 && bn == 128)) {  // small batches: smaller tiles over all SMs (same bits)
+            } else if (tower && !(nb == 16 && bn == 128)) {
+                // small batches: smaller tiles over all SMs, and ONE launch per layer -- the tile's two accumulators fit TMEM
+                // (2 x MT x BN <= 512 columns), so the five small pairs and the exact pair run back to back in one K loop
+                // and the epilogue adds them in registers: same bits, no scratch round trip, one pipeline ramp instead of two
                 const CUtensorMap &wm = bn == 128 ? L.wmap3 : bn == 64 ? L.wmap3_n64 : L.wmap3_n32;
-                CU(launch_conv_tile(st, bn, nb, mPt, wm, n, L.ntaps, L.chunks, nullptr, nullptr, small, 1, c_out, 0, 5, PAIRS_SMALL5, F, L.K));
-                CU(launch_conv_tile(st, bn, nb, mPt, wm, n, L.ntaps, L.chunks, L.bias, nullptr, out, 2, c_out, 1, 1, PAIRS_BIG, F, L.K, &sp));
+                static const bool no_fuse = getenv("DIEE_SPLIT_FUSE") && atoi(getenv("DIEE_SPLIT_FUSE")) == 0;
+                if (!no_fuse) {
+                    sp.addend = nullptr; sp.fused = 1;
+                    CU(launch_conv_tile(st, bn, nb, mPt, wm, n, L.ntaps, L.chunks, L.bias, nullptr, out, 2, c_out, 1, 6, PAIRS_SMALL5, F, L.K, &sp));
+                    ctx->launches -= 1;
+                } else {
+                    CU(launch_conv_tile(st, bn, nb, mPt, wm, n, L.ntaps, L.chunks, nullptr, nullptr, small, 1, c_out, 0, 5, PAIRS_SMALL5, F, L.K));
+                    CU(launch_conv_tile(st, bn, nb, mPt, wm, n, L.ntaps, L.chunks, L.bias, nullptr, out, 2, c_out, 1, 1, PAIRS_BIG, F, L.K, &sp));
+                }
+            } else if (!first && L.bn < 128 && !(getenv("DIEE_SPLIT_FUSE") && atoi(getenv("DIEE_SPLIT_FUSE")) == 0)) {
+                // the two head convolutions (32 / 16 output channels): their accumulators are narrow, one fused launch each
+                sp.addend = nullptr; sp.fused = 1;
+                CU(launch_conv(st, L.bn, mx, L.wmap3, n, L.ntaps, L.chunks, L.bias, nullptr, out, 2, c_out, 1, 6, PAIRS_SMALL5, F, L.K, &sp));
+                ctx->launches -= 1;
             } else {
                 CU(launch_conv(st, L.bn, mx, L.wmap3, n, L.ntaps, L.chunks, nullptr, nullptr, small, 1, c_out, 0, first ? 2 : 5,
                                first ? PAIRS_SMALL2 : PAIRS_SMALL5, first ? 0 : F, L.K));

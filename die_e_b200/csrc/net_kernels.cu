@@ -209,7 +209,9 @@ struct ConvCfg {
 #endif
     static constexpr int STAGES = STAGES_RAW > DIEE_CONV_MAX_STAGES ? DIEE_CONV_MAX_STAGES : STAGES_RAW;
     static constexpr int SLACK = (ROWS % 128) ? 16 * 1024 : 0;  // a padded M-tile reads past its tile: keep that inside the allocation
-    static constexpr int TMEM_COLS = (MT * BN <= 32) ? 32 : (MT * BN <= 64) ? 64 : (MT * BN <= 128) ? 128 : (MT * BN <= 256) ? 256 : 512;
+    static constexpr bool CAN_FUSE = 2 * MT * BN <= 512;  // room for the split-precision mode's two accumulators
+    static constexpr int ACC_COLS = CAN_FUSE ? 2 * MT * BN : MT * BN;
+    static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/ + SLACK;
     static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned (128B swizzle atoms)");
     static_assert(STAGES >= 2, "pipeline depth");
@@ -240,6 +242,9 @@ struct ConvEpi {
     const float *col_scale;     // [c_out_total]: units of the weight planes per output channel (nullable = 1)
     const float *residual_f32;  // fp32 [rows][c_out_total] (nullable)
     unsigned int *board_max;    // [board]: max of the (post-ReLU, >= 0) outputs as float bits, atomicMax (nullable)
+    int fused;                  // 1: ONE launch runs all six pairs -- the five small ones into a first accumulator, the exact pair
+                                // (the last one) into a second -- and the epilogue adds the two in registers instead of reading
+                                // `addend`: no second launch, no scratch round trip.  Needs 2 x MT x BN TMEM columns (small tiles).
 };
 template <int BN, int NB, int KC, bool TWO = false>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
@@ -324,6 +329,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             if (lane == 0) {
                 const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
                 const uint32_t sb = sa + KC * Cfg::A_BYTES;
+                // fused split precision: the last pair (the exact integer one) accumulates in its own TMEM region
+                const int kb_big = (npairs - 1) * per_pair / KC;
+                const bool big = epi.fused && kb >= kb_big;
+                const uint32_t acc0 = tmem_base + (big ? (uint32_t)(Cfg::MT * BN) : 0u);
+                const bool fresh = kb == 0 || (epi.fused && kb == kb_big);  // first K-block of an accumulator
 #pragma unroll
                 for (int h = 0; h < KC; ++h) {
 #pragma unroll
@@ -332,8 +342,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzled row
                             const uint64_t ad = umma_desc_sw128(sa + h * Cfg::A_BYTES + mt * (128 * 128) + kk * 32);
                             const uint64_t bd = umma_desc_sw128(sb + h * Cfg::B_BYTES + kk * 32);
-                            if (TWO) umma_bf16_2sm(tmem_base + (uint32_t)(mt * BN), ad, bd, idesc, (kb | h | kk) != 0 ? 1u : 0u);
-                            else umma_bf16(tmem_base + (uint32_t)(mt * BN), ad, bd, idesc, (kb | h | kk) != 0 ? 1u : 0u);
+                            const uint32_t accumulate = (fresh && h == 0 && kk == 0) ? 0u : 1u;
+                            if (TWO) umma_bf16_2sm(acc0 + (uint32_t)(mt * BN), ad, bd, idesc, accumulate);
+                            else umma_bf16(acc0 + (uint32_t)(mt * BN), ad, bd, idesc, accumulate);
                         }
                     }
                 }
@@ -363,8 +374,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN + c0);
                 const int ncol = (BN - c0) >= 32 ? 32 : 16;
-                if (ncol == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-                tmem_ld_wait();
+                if (epi.fused) {  // v = exact pair's accumulator + the small pairs' (fp32 add, as the two-launch form does from its scratch)
+                    uint32_t sm[32];
+                    if (ncol == 32) { tmem_ld32(taddr, sm); tmem_ld32(taddr + (uint32_t)(Cfg::MT * BN), v); }
+                    else { tmem_ld16(taddr, sm); tmem_ld16(taddr + (uint32_t)(Cfg::MT * BN), v); }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(sm[j]));
+                } else {
+                    if (ncol == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+                    tmem_ld_wait();
+                }
                 if (valid && out_mode == 2) {
                     // split-precision epilogue: (acc + small pairs) * 2^(e_board + e_channel) + bias (+ residual), ReLU, fp32
                     const size_t off = (size_t)grow * c_out_total + n0 + c0;
@@ -775,7 +795,7 @@ cudaError_t launch_conv_pair(cudaStream_t st, const CUtensorMap &ta, const CUten
     using Cfg = ConvCfg<128, 16, 1, true>;
     const __nv_bfloat16 *residual = static_cast<const __nv_bfloat16 *>(residual_v);
     ConvEpi epi{};
-    if (sp) epi = ConvEpi{sp->addend, sp->row_scale, sp->col_scale, sp->residual_f32, sp->board_max};
+    if (sp) epi = ConvEpi{sp->addend, sp->row_scale, sp->col_scale, sp->residual_f32, sp->board_max, sp->fused};
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<128, 16, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -803,7 +823,7 @@ cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap 
                              int npairs, uint32_t pairs, int a_plane, int b_plane, const SplitEpilogue *sp) {
     const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(residual);
     ConvEpi epi{};
-    if (sp) epi = ConvEpi{sp->addend, sp->row_scale, sp->col_scale, sp->residual_f32, sp->board_max};
+    if (sp) epi = ConvEpi{sp->addend, sp->row_scale, sp->col_scale, sp->residual_f32, sp->board_max, sp->fused};
 
     // several chunks per pipeline stage where the tile is small enough for >= 3 such stages and the layer's chunk count
     // divides (DIEE_CONV_KC=n caps it; 1 keeps one chunk per stage everywhere)

@@ -11,6 +11,7 @@ namespace diee {
 struct SplitEpilogue {
     const float *addend, *row_scale, *col_scale, *residual_f32;
     unsigned int *board_max;
+    int fused;  // all six pairs in one launch, two TMEM accumulators (tiles with 2 x MT x BN <= 512 columns only)
 };
 // one convolution with an explicit CTA tile: nb boards x bn output channels (ta encoded with a box of nb boards, tb with bn rows)
 cudaError_t launch_conv_tile(cudaStream_t st, int bn, int nb, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,

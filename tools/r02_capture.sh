@@ -22,6 +22,7 @@ ncu --set full --clock-control none --import-source on -k regex:mcts_search_kern
 ncu -i gpurun_out/r02_prof_tree_$TAG.ncu-rep --page raw --csv > gpurun_out/r02_prof_tree_${TAG}_raw.csv 2>/dev/null
 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc_kernel -s 40 -c 2 -o gpurun_out/r02_prof_conv_split3_$TAG -f python bench.py --workload alpha --precision split3 --steps 1 --warmup 0 --no-cpu-baseline --no-parity-check > gpurun_out/ncu_f3.log 2>&1
 ncu -i gpurun_out/r02_prof_conv_split3_$TAG.ncu-rep --page raw --csv > gpurun_out/r02_prof_conv_split3_${TAG}_raw.csv 2>/dev/null
-ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc_kernel -s 40 -c 1 -o gpurun_out/r02_prof_conv_bf16_$TAG -f python bench.py --workload alpha --precision bf16 --steps 1 --warmup 0 --no-cpu-baseline --no-parity-check > gpurun_out/ncu_f4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc_kernel -s 45 -c 1 -o gpurun_out/r02_prof_conv_bf16_$TAG -f python bench.py --workload alpha --precision bf16 --steps 1 --warmup 0 --no-cpu-baseline --no-parity-check > gpurun_out/ncu_f4.log 2>&1
 ncu -i gpurun_out/r02_prof_conv_bf16_$TAG.ncu-rep --page raw --csv > gpurun_out/r02_prof_conv_bf16_${TAG}_raw.csv 2>/dev/null
 ls -la gpurun_out | tail -25
+python tools/net_lat.py > gpurun_out/r02_net_latency_$TAG.txt 2>&1; cat gpurun_out/r02_net_latency_$TAG.txt

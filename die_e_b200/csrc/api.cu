@@ -116,6 +116,9 @@ int32_t diee_ctx_create(int32_t device, diee_ctx **out) {
         }
         ctx->pb_index.cap = index.size() * 4;
         ctx->pb_plays.cap = plays.size() * 2;
+        // a cudaMemcpy from pageable memory may return before its DMA has landed, and ctx->stream / the side streams are
+        // non-blocking: without this a search issued right after the create could read a half-written table
+        if (cudaDeviceSynchronize() != cudaSuccess) { delete ctx; return DIEE_ERR_CUDA; }
     }
     *out = ctx;
     return DIEE_OK;

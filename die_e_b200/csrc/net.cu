@@ -236,6 +236,9 @@ int32_t diee_net_create(diee_ctx *ctx, int32_t game_kind, const float *const *t,
         ctx->err = why;
         return rc_build;
     }
+    // The uploads above are cudaMemcpy calls from pageable host memory: such a copy may return once the data is staged, before
+    // the DMA has landed, and the engine's streams are non-blocking (they do not order themselves behind the null stream).
+    CU(cudaDeviceSynchronize());
     *out = net;
     return DIEE_OK;
 }

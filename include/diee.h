@@ -184,7 +184,9 @@ int32_t diee_bg_encode_states_dev(diee_ctx *ctx, const diee_bg_state *states, in
  * best_moves_out: diee_move[n] (backgammon) or uint8[n] (tictactoe; 10 = EMPTY_MOVE).
  * status_out[i]: DIEE_OK / DIEE_ERR_NO_MOVES_PANIC / DIEE_ERR_OVERFLOW per game.
  * Optional pool read-back (all nullable): nodes_out[n*(iterations+1)], node_states_out (same
- * count, state type by game_kind), n_nodes_out[n]; stats_out[n] = work counters;
+ * count, state type by game_kind), n_nodes_out[n] (game i's live entries are the first n_nodes_out[i]
+ * of its iterations+1; the rest are unspecified -- 0 live entries for a root that is already won);
+ * stats_out[n] = work counters;
  * rollout_finals_out[n*iterations] = the state each simulation's rollout ended in (all-zero where
  * the iteration ran no rollout), which makes the rollouts themselves checkable against the oracle.
  * With reference-exact rollouts (no DIEE_MODE_ROLLOUT_CHECK_CURRENT) a rollout cannot influence the

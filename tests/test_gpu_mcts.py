@@ -122,6 +122,24 @@ def test_mct_search_host_api(ctx, oracle):
     assert mv in bg.get_valid_moves()
 
 
+def _same_search(ref, got, tag, oracle_finals=None):
+    names = ("best", "status", "stats", "nodes", "node_states", "n_nodes", "finals")
+    assert np.asarray(ref[5]).tobytes() == np.asarray(got[5]).tobytes(), f"{tag}: n_nodes differ"
+    live = np.arange(np.asarray(ref[3]).shape[1])[None, :] < np.asarray(ref[5])[:, None]   # pool entries >= n_nodes are unspecified
+    for name, a, b in zip(names, ref, got):
+        if name in ("nodes", "node_states"):
+            a, b = np.asarray(a)[live], np.asarray(b)[live]
+        a8 = np.frombuffer(np.asarray(a).tobytes(), dtype=np.uint8)
+        b8 = np.frombuffer(np.asarray(b).tobytes(), dtype=np.uint8)
+        if a8.tobytes() != b8.tobytes():
+            where = np.nonzero(a8 != b8)[0]
+            extra = ""
+            if name == "finals" and oracle_finals is not None:
+                o8 = np.frombuffer(oracle_finals, dtype=np.uint8)
+                extra = f"; reference run == oracle: {bool((a8 == o8).all())}, this run == oracle: {bool((b8 == o8).all())}"
+            raise AssertionError(f"{tag}: {name} differs at bytes {where[:6].tolist()} ({len(where)} in all){extra}")
+
+
 def test_sliced_search_is_the_same_search(ctx, oracle, monkeypatch):
     """DIEE_SEARCH_SLICES: the search cut into slices of iterations (tree kernel of slice s+1 beside the rollouts of
     slice s on a side stream) must give exactly the unsliced result -- nodes, best moves, rollout end states."""
@@ -130,18 +148,19 @@ def test_sliced_search_is_the_same_search(ctx, oracle, monkeypatch):
     players = states["player"].copy()
     cfg = oracle.mcts_cfg(iterations=30, c=2.0, limit=60, mode=_ffi.MODE_PASS_CHILD)
     ref = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
+    ofin = b"".join(oracle.mcts_search_bg(states[i:i + 1], int(players[i]), cfg, 5, 100 + i, 3, want_finals=True)[4].tobytes()
+                    for i in range(len(states)))
+    assert np.asarray(ref[6]).tobytes() == ofin
     for slices in ("2", "4"):
         monkeypatch.setenv("DIEE_SEARCH_SLICES", slices)
-        got = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
-        for a, b in zip(ref, got):
-            assert np.asarray(a).tobytes() == np.asarray(b).tobytes()
-    # the same slices on an SM partition (green contexts: tree slices on 64 SMs, rollouts on the rest) and with the
-    # rollouts' items in game-minor order; a fresh context, because the partition is set up once per context
+        _same_search(ref, ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True), f"{slices} slices", ofin)
+    # the same slices on an SM partition (green contexts: tree slices on 64 SMs, rollouts on the rest); a fresh context,
+    # because the partition is set up once per context
     monkeypatch.setenv("DIEE_TREE_SMS", "64")
     ctx2 = _ffi.Context(0)
-    got = ctx2.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
-    for a, b in zip(ref, got):
-        assert np.asarray(a).tobytes() == np.asarray(b).tobytes()
+    for rep in range(3):
+        _same_search(ref, ctx2.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True),
+                     f"4 slices on an SM partition, run {rep}", ofin)
     ctx2.close()
     monkeypatch.delenv("DIEE_TREE_SMS")
     monkeypatch.delenv("DIEE_SEARCH_SLICES")
@@ -162,8 +181,7 @@ def test_lockstep_check_current_groups_and_fused_form_agree(ctx, oracle, monkeyp
         monkeypatch.setenv(env, val)
         got = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
         monkeypatch.delenv(env) if env != "DIEE_CC_FUSED" else monkeypatch.setenv("DIEE_CC_FUSED", "0")
-        for k, (a, b) in enumerate(zip(ref, got)):
-            assert np.asarray(a).tobytes() == np.asarray(b).tobytes(), (env, val, k)
+        _same_search(ref, got, f"{env}={val}")
     # and against the oracle, game by game, with the full rollout cap
     _cmp_trees(oracle, _ffi, ctx, _ffi.GAME_BACKGAMMON, states[:24], players[:24], cfg, 5, 100, 3)
     monkeypatch.delenv("DIEE_CC_FUSED")

@@ -685,8 +685,34 @@ def sub_mcts(ctx, ffi, torch, dev, stream, rank, world, G2, cfg, reduce_max, rep
     ms2 = reduce_max(e0.elapsed_time(e1))
     assert int(d2_status.abs().sum().item()) == 0
     its = int(cfg["iterations"][0])
-    return {"games_per_gpu": G2, "value": round(reps * G2 * world * its / (ms2 / 1e3), 1), "unit": "simulations/s",
-            "ms_per_search": round(ms2 / reps, 4)}
+    out = {"games_per_gpu": G2, "value": round(reps * G2 * world * its / (ms2 / 1e3), 1), "unit": "simulations/s",
+           "ms_per_search": round(ms2 / reps, 4)}
+    if not (int(cfg["mode_flags"][0]) & ffi.MODE_ROLLOUT_CHECK_CURRENT):
+        # which rollout kernel ran (lane_kernels.cu: jobs of >= 1,024 rollouts per SM go to the packed kernel), its share of
+        # the search, and that the other kernel finds the same moves on this very batch
+        try:
+            tree_ms, roll_ms = ctx.search_timing()
+            plies = ctx.search_work()
+            packed = os.environ.get("DIEE_LANE_PACK", "1") != "0" and G2 * its >= 148 * 1024
+            best_timed = d2_best.cpu().numpy().tobytes()
+            old_env = os.environ.get("DIEE_LANE_PACK")
+            os.environ["DIEE_LANE_PACK"] = "0" if packed else "2"
+            go(reps)
+            torch.cuda.synchronize()
+            same = d2_best.cpu().numpy().tobytes() == best_timed
+            if old_env is None:
+                del os.environ["DIEE_LANE_PACK"]
+            else:
+                os.environ["DIEE_LANE_PACK"] = old_env
+            out.update({"rollout_kernel": "lane_pack_kernel" if packed else "lane_run_kernel", "tree_ms": round(tree_ms, 4),
+                        "rollout_ms": round(roll_ms, 4), "rollout_plies_played": plies,
+                        "rollout_gplies_per_s": round(plies / roll_ms / 1e6, 2),
+                        "same_best_moves_with_the_other_rollout_kernel": bool(same)})
+            if not same:
+                raise SystemExit("bench: the packed and the lane-resident rollout kernels disagree at %d games" % G2)
+        except ffi.DieeError:
+            pass
+    return out
 
 
 def exchange_step(ctx, ffi, dist, dev, rank, world, recs, barrier):

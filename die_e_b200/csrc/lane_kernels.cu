@@ -285,6 +285,277 @@ __global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32
     stats_out[gm].rollout_plies += c;
 }
 
+// ---------------- the packed form: games queue up by the code their next ply needs ----------------
+// lane_run_kernel keeps a game in the lane that took it, so a warp is as full as its vote: 11-16 of 32 lanes take part in a
+// step and 6.8 are active per instruction.  For jobs much larger than the machine (the queue refills every lane anyway, the
+// longest dependent chain does not matter) the games live in SHARED memory instead -- bit planes, ply counter and stream
+// coordinates, 13 words per game, [word][slot] -- and wait in one of six queues: two dice | doubles | bar entries | bear-off
+// table | bear-off walk | turnover (write the result, take the next item of the job).  A warp takes 32 games off the
+// longest queue, plays ONE ply of each -- 32 lanes in the same code -- and appends every game to the queue of its next ply.
+// There is no block barrier: the queues are rings of slot numbers with a reserved-then-written protocol (the producer adds
+// to `tail`, writes the game, then the ring entry; a consumer moves `head` by compare-and-swap and waits for each entry to
+// leave its EMPTY value).  512 resident games per 8 warps guarantee a full queue somewhere while the job lasts (256 in
+// flight leaves 256 waiting in six queues); when nothing is full for a few polls -- the tail of the job -- a warp takes
+// what there is (1 / 2 / 4 / 16 polls: 3.70 / 3.70 / 3.70 / 3.92 ms for the rollouts of 8,192 games).  The first form of this kernel sorted the whole CTA between two barriers every ply: 35 instead of 66 warp
+// instructions per ply at 19.3 lanes per instruction, but 8 of 12 stalled warps sat at the barrier behind the slowest
+// kind and the kernel was only 7 % faster; hence the queues.
+// The plies themselves are the same device functions as above, and a game's dice and choices are keyed by (game id, ply),
+// so who plays a ply changes nothing in what is played.
+#ifndef DIEE_PK_S
+#define DIEE_PK_S 512
+#endif
+#ifndef DIEE_PK_PATIENCE
+#define DIEE_PK_PATIENCE 4
+#endif
+constexpr int PK_T = 256;        // threads per CTA
+constexpr int PK_S = DIEE_PK_S;  // resident games per CTA
+constexpr int PK_RING = PK_S <= 512 ? 512 : 1024;  // ring size per queue (a power of two >= PK_S: a game is in one queue at most)
+constexpr int PK_AREAS = 3;      // warps that may run the bear-off walk at a time (one scratch area each)
+constexpr int PK_PATIENCE = DIEE_PK_PATIENCE;  // polls without a full queue before a warp takes a partial one
+constexpr int PK_WORDS = 13;
+enum { PC_TWO = 0, PC_DBL, PC_BAR, PC_TABLE, PC_WALK, PC_TURN, PC_LISTS, PC_DEAD = PC_LISTS };
+constexpr uint32_t PK_HAS_GAME = 1u << 24;
+constexpr unsigned PK_EMPTY = 0xFFFFu;
+
+struct PackSmem {
+    uint32_t st[PK_WORDS][PK_S];        // own[4], opp[4], misc, ply, item, game id, counter word 3
+    uint32_t scr[PK_AREAS][L_SCRATCH][32];
+    uint16_t ring[PC_LISTS][PK_RING];
+    unsigned head[8], tail[8];
+    int area_lock[4];
+    int n_dead;
+};
+
+__device__ __forceinline__ int pack_class(const LaneBoard &g) {
+    if (lane_path(g) == PATH_WALK) return PC_WALK;
+    if (g.bar_own > 0) return PC_BAR;
+    const uint32_t own1 = g.own[0] | g.own[1] | g.own[2] | g.own[3];
+    if (own1 != 0 && (own1 & ~0x3Fu) == 0) return PC_TABLE;  // (lane_path: every checker home, no opposing checker there)
+    return g.roll0 == g.roll1 ? PC_DBL : PC_TWO;
+}
+__device__ __forceinline__ uint32_t pack_misc(const LaneBoard &g) {
+    return (uint32_t)g.bar_own | ((uint32_t)g.bar_opp << 4) | ((uint32_t)g.off_own << 8) | ((uint32_t)g.off_opp << 12) |
+           ((uint32_t)g.roll0 << 16) | ((uint32_t)g.roll1 << 19) | ((uint32_t)g.second << 22) | ((g.player > 0 ? 1u : 0u) << 23) | PK_HAS_GAME;
+}
+__device__ __forceinline__ void unpack_misc(LaneBoard &g, uint32_t m) {
+    g.bar_own = (int)(m & 15u); g.bar_opp = (int)((m >> 4) & 15u); g.off_own = (int)((m >> 8) & 15u); g.off_opp = (int)((m >> 12) & 15u);
+    g.roll0 = (int)((m >> 16) & 7u); g.roll1 = (int)((m >> 19) & 7u); g.second = (int)((m >> 22) & 1u); g.player = (m >> 23) & 1u ? 1 : -1;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PK_T, 3)
+lane_pack_kernel(LaneJob job) {
+    static_assert(MODE == LANE_PLAYOUT || MODE == LANE_ROLLOUT, "the lock-step rollouts are one wave: lane_run_kernel");
+    constexpr bool ROLLOUT = MODE == LANE_ROLLOUT;
+    extern __shared__ __align__(16) unsigned char pack_smem_raw[];
+    PackSmem &sm = *reinterpret_cast<PackSmem *>(pack_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t stream = ROLLOUT ? DIEE_STREAM_ROLLOUT : DIEE_STREAM_GAME;
+    // every slot starts in the turnover queue without a game: "take one"
+    for (int s = tid; s < PK_S; s += PK_T) sm.st[8][s] = 0;
+    for (int i = tid; i < PC_LISTS * PK_RING; i += PK_T) (&sm.ring[0][0])[i] = (uint16_t)PK_EMPTY;
+    __syncthreads();
+    for (int s = tid; s < PK_S; s += PK_T) sm.ring[PC_TURN][s] = (uint16_t)s;
+    if (tid < 8) { sm.head[tid] = 0; sm.tail[tid] = tid == PC_TURN ? PK_S : 0; }
+    if (tid < 4) sm.area_lock[tid] = 0;
+    if (tid == 0) sm.n_dead = 0;
+    __syncthreads();
+    volatile unsigned *vhead = sm.head, *vtail = sm.tail;
+    volatile int *vlock = sm.area_lock;
+    volatile int *vdead = &sm.n_dead;
+#ifdef DIEE_LANE_STATS
+    unsigned long long st_batches = 0, st_lanes = 0, st_polls = 0, st_kind[PC_LISTS] = {0, 0, 0, 0, 0, 0};
+#endif
+    int polls = 0;
+    for (;;) {
+        if (*vdead >= PK_S) break;
+        // ---- the longest queue ----
+        unsigned cnt = 0;
+        if (lane < PC_LISTS) {
+            const unsigned h0 = vhead[lane];  // head before tail: head only grows and never passes tail
+            cnt = vtail[lane] - h0;
+            if (lane == PC_WALK && cnt && vlock[0] && vlock[1] && vlock[2]) cnt = 0;  // no scratch area free
+            if (cnt > 1023u) cnt = 1023u;
+        }
+        const unsigned best = __reduce_max_sync(0xFFFFFFFFu, (cnt << 3) | (unsigned)(lane & 7));
+        const int c = (int)(best & 7u);
+        const int avail = (int)(best >> 3);
+        const int take = avail >= 32 ? 32 : (polls >= PK_PATIENCE ? avail : 0);
+        if (take == 0) {
+            ++polls;
+#ifdef DIEE_LANE_STATS
+            ++st_polls;
+#endif
+            __nanosleep(polls <= PK_PATIENCE ? 100u : 400u);  // (nothing at all to take: the other warps need the issue slots)
+            continue;
+        }
+        int ok = 0, area = -1;
+        unsigned h = 0;
+        if (lane == 0) {
+            if (c == PC_WALK)
+                for (int a = 0; a < PK_AREAS && area < 0; ++a)
+                    if (atomicCAS(&sm.area_lock[a], 0, 1) == 0) area = a;
+            if (c != PC_WALK || area >= 0) {
+                h = vhead[c];
+                const unsigned t = vtail[c];
+                if ((int)(t - h) >= take) ok = atomicCAS(&sm.head[c], h, h + (unsigned)take) == h;
+                if (!ok && area >= 0) { atomicExch(&sm.area_lock[area], 0); area = -1; }
+            }
+        }
+        ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+        if (!ok) continue;  // somebody else was faster: look again
+        h = __shfl_sync(0xFFFFFFFFu, h, 0);
+        area = __shfl_sync(0xFFFFFFFFu, area, 0);
+        polls = 0;
+        const bool act = lane < take;
+        int slot = 0;
+        if (act) {
+            volatile uint16_t *e = &sm.ring[c][(h + (unsigned)lane) & (PK_RING - 1)];
+            unsigned v;
+            while ((v = *e) == PK_EMPTY) {}  // reserved, not written yet
+            *e = (uint16_t)PK_EMPTY;
+            slot = (int)v;
+        }
+        __threadfence_block();
+        __syncwarp();
+#ifdef DIEE_LANE_STATS
+        ++st_batches; st_lanes += take; st_kind[c] += take;
+#endif
+        const uint32_t act_mask = __ballot_sync(0xFFFFFFFFu, act);
+        int newc = -1;
+        if (act) {
+            LaneBoard g;
+            uint32_t k, item, gid, c3;
+            const uint32_t misc = sm.st[8][slot];
+            bool keep = true;  // a game goes back into the slot
+            if (c == PC_TURN) {
+                k = sm.st[9][slot]; item = sm.st[10][slot]; gid = sm.st[11][slot]; c3 = sm.st[12][slot];
+                const bool has = misc & PK_HAS_GAME;
+                {   // plies this job actually played (the closed-form tail below is not work)
+                    const uint32_t sum = __reduce_add_sync(act_mask, has ? k : 0u);
+                    if (lane == 0 && sum) atomicAdd(job.next_item + 1, (unsigned long long)sum);
+                }
+                if (has) {
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) { g.own[w] = sm.st[w][slot]; g.opp[w] = sm.st[4 + w][slot]; }
+                    unpack_misc(g, misc);
+                    if (ROLLOUT) {
+                        if (k < job.limit) {  // both sides have collected everything: the rest are skip_turns (see lane_run_kernel)
+                            uint32_t o[4];
+                            l_philox((uint32_t)job.seed, (uint32_t)(job.seed >> 32), job.limit - 1u, gid, stream, c3, o);
+                            if ((job.limit - k) & 1u) l_pass_turn(g, 0, 0);
+                            g.second = 0; g.roll0 = l_die(o[0]); g.roll1 = l_die(o[1]);
+                        }
+                        lane_store_state(g, job.finals + item);
+                    } else {
+                        job.winners[item] = (int8_t)l_winner(g);
+                        job.plies[item] = (int32_t)k;
+                        if (job.finals) lane_store_state(g, job.finals + item);
+                    }
+                }
+                // the next items of the job
+                long long first = 0;
+                if (lane == 0) first = (long long)atomicAdd(job.next_item, (unsigned long long)take);
+                first = __shfl_sync(act_mask, first, 0);
+                const long long it_l = first + lane;
+                keep = false;
+                newc = PC_TURN;
+                k = 0;
+                if (it_l >= job.n_items) {
+                    newc = PC_DEAD;
+                } else if (ROLLOUT) {
+                    uint32_t gm, it;
+                    if (job.game_minor) {
+                        const uint32_t q = (uint32_t)(it_l / job.n_games);
+                        gm = (uint32_t)(it_l - (long long)q * job.n_games);
+                        it = job.it_begin + q;
+                    } else {
+                        gm = (uint32_t)(it_l / job.it_count);
+                        it = job.it_begin + (uint32_t)(it_l - (long long)gm * job.it_count);
+                    }
+                    item = gm * job.iterations + it;  // the (game, iteration) pair
+                    const int node = job.sim_node[item];
+                    if (node >= 0 && job.limit > 0) {  // node < 0: the iteration ended on a terminal leaf, no rollout
+                        lane_load_state(g, job.states + (size_t)gm * (job.iterations + 1) + node);
+                        gid = job.first_game_id + gm; c3 = (job.epoch << 16) | (it & 0xFFFFu);
+                        keep = true;
+                        newc = (g.off_own == 15 && g.off_opp == 15) ? PC_TURN : pack_class(g);
+                    }
+                } else {
+                    item = (uint32_t)it_l;
+                    lane_load_state(g, job.states + item);
+                    gid = job.first_game_id + item; c3 = 0;
+                    keep = true;
+                    newc = (l_winner(g) != 0 || job.limit == 0) ? PC_TURN : pack_class(g);
+                }
+                if (keep) { sm.st[10][slot] = item; sm.st[11][slot] = gid; sm.st[12][slot] = c3; }
+                else sm.st[8][slot] = 0;
+            } else {
+                // ---- one ply ----
+#pragma unroll
+                for (int w = 0; w < 4; ++w) { g.own[w] = sm.st[w][slot]; g.opp[w] = sm.st[4 + w][slot]; }
+                unpack_misc(g, misc);
+                k = sm.st[9][slot]; gid = sm.st[11][slot]; c3 = sm.st[12][slot];
+                uint32_t o[4];
+                l_philox((uint32_t)job.seed, (uint32_t)(job.seed >> 32), k, gid, stream, c3, o);
+                LanePlay pl;
+                pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
+                if (c != PC_WALK) {
+                    const int hi = max(g.roll0, g.roll1), lo = min(g.roll0, g.roll1);
+                    LaneMasks m;
+                    l_closed_applies(g, m, lo, hi);
+                    if (g.bar_own == 0 && m.own1 != 0 && (m.own1 & ~0x3Fu) == 0) {
+                        const uint32_t e = __ldg(job.pb.index + l_pb_key(g));
+                        const uint32_t U = e & 255u;
+                        if (U > 0) pl = l_pb_unpack(__ldg(job.pb.plays + (e >> 8) + l_index(o[2], U)));
+                    } else {
+                        if (m.own1 != 0 || g.bar_own > 0) l_contact_select(g, m, lo, hi, -2, o[2], pl);
+                    }
+                } else {
+                    LaneGen gen;
+                    uint32_t *scr = &sm.scr[area][0][lane];
+                    l_movegen_walk_t<true>(g, gen, scr, 32);
+                    if (gen.U > 0) pl = l_pick_walk(gen, scr, 32, (int)l_index(o[2], (uint32_t)gen.U));
+                }
+                l_step(g, pl, l_die(o[0]), l_die(o[1]));
+                ++k;
+                const bool over = ROLLOUT ? (k == job.limit || (g.off_own == 15 && g.off_opp == 15)) : (k == job.limit || l_winner(g) != 0);
+                newc = over ? PC_TURN : pack_class(g);
+            }
+            if (keep) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) { sm.st[w][slot] = g.own[w]; sm.st[4 + w][slot] = g.opp[w]; }
+                sm.st[8][slot] = pack_misc(g);
+                sm.st[9][slot] = k;
+            }
+        }
+        __threadfence_block();  // the games before their ring entries
+        __syncwarp();
+        if (area >= 0 && lane == 0) atomicExch(&sm.area_lock[area], 0);
+        {   // ---- append every game to the queue of its next ply (one shared atomic per kind present) ----
+            const uint32_t same = __match_any_sync(0xFFFFFFFFu, newc);
+            const int leader = __ffs(same) - 1;
+            unsigned base = 0;
+            if (lane == leader) {
+                if (newc >= 0 && newc < PC_LISTS) base = atomicAdd(&sm.tail[newc], (unsigned)__popc(same));
+                else if (newc == PC_DEAD) atomicAdd(&sm.n_dead, __popc(same));
+            }
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (newc >= 0 && newc < PC_LISTS) {
+                volatile uint16_t *e = &sm.ring[newc][(base + (unsigned)__popc(same & ((1u << lane) - 1u))) & (PK_RING - 1)];
+                *e = (uint16_t)slot;
+            }
+        }
+    }
+#ifdef DIEE_LANE_STATS
+    // [0] batches, [1] games in them, [2] polls without a batch, [8 + kind] games played per kind
+    if (lane == 0) {
+        atomicAdd(&g_lane_stats[0], st_batches); atomicAdd(&g_lane_stats[1], st_lanes); atomicAdd(&g_lane_stats[2], st_polls);
+        for (int q = 0; q < PC_LISTS; ++q) atomicAdd(&g_lane_stats[8 + q], st_kind[q]);
+    }
+#endif
+}
+
 template <int MODE>
 static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) {
     // tuning knobs, read once: waiting-time weight of the vote and resident CTAs (x 2 warps) per SM.  Measured on B200 with
@@ -316,6 +587,28 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
     // (the head only: next_item[1], the played-plies counter, is zeroed once per search / playout call by the caller)
     cudaError_t e = cudaMemsetAsync(job.next_item, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
+    if constexpr (MODE != LANE_ROLLOUT_CC) {
+        // jobs of about a machine-full of resident games and more: the packed form.  Measured on B200, rollouts of a
+        // 100-iteration search, lane-resident / packed: 1,024 games 1.24 / 1.59 ms (one wave, bound by its longest chains: it
+        // stays lane-resident), 2,048 games 1.98 / 1.85, 4,096 3.39 / 2.29, 8,192 6.08 / 3.72, 32,768 22.6 / 12.3, 65,536
+        // 44.7 / 24.0 ms.  DIEE_LANE_PACK=0 keeps the lane-resident kernel, =2 forces the packed one for every job size
+        // (which is how the tests reach it with small batches).
+        const int pack_env = getenv("DIEE_LANE_PACK") ? atoi(getenv("DIEE_LANE_PACK")) : 1;
+        const int pack_bps = getenv("DIEE_PACK_BPS") ? atoi(getenv("DIEE_PACK_BPS")) : 3;
+        const bool fits = job.n_items < (1ll << 31) && (MODE == LANE_PLAYOUT || (long long)job.n_games * job.iterations < (1ll << 31));
+        if (fits && (pack_env == 2 || (pack_env == 1 && job.n_items >= (long long)sms * 1024))) {
+            long long pb = (job.n_items + PK_S - 1) / PK_S;
+            if (pb > (long long)sms * pack_bps) pb = (long long)sms * pack_bps;
+            static bool attr_set = false;  // (per kernel instance: this is a template)
+            if (!attr_set) {
+                if ((e = cudaFuncSetAttribute(lane_pack_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem))) != cudaSuccess) return e;
+                attr_set = true;
+            }
+            lane_pack_kernel<MODE><<<(unsigned)pb, PK_T, sizeof(PackSmem), st>>>(job);
+            if (launches) *launches += 1;
+            return cudaGetLastError();
+        }
+    }
     lane_run_kernel<MODE><<<(unsigned)blocks, LANE_CTA, 0, st>>>(job);
     if (launches) *launches += 1;
     return cudaGetLastError();

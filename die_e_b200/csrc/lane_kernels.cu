@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "bg_lane.cuh"
+#include "lane_pack.cuh"
 #include "launchers.h"
 
 namespace diee {
@@ -25,19 +26,6 @@ namespace diee {
 using namespace lane;
 
 constexpr int LANE_CTA = 64;
-
-__device__ __forceinline__ void lane_load_state(LaneBoard &g, const diee_bg_state *s) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(s));
-    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(s) + 1);
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    l_load(g, w);
-}
-__device__ __forceinline__ void lane_store_state(const LaneBoard &g, diee_bg_state *s) {
-    uint32_t w[8];
-    l_store(g, w);
-    reinterpret_cast<uint4 *>(s)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    reinterpret_cast<uint4 *>(s)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-}
 
 #ifdef DIEE_LANE_STATS
 __device__ unsigned long long g_lane_stats[16];  // [p] = steps executed on path p, [8+p] = lanes advanced
@@ -70,27 +58,8 @@ struct LaneJob {
     const int8_t *players;         // the player each game's search counts the value for
     float *results;                // [game]: Node::simulate's return value (node.rs:182-185,195)
     diee_search_stats *stats;      // [game]: rollout_plies += plies played (nullable)
+    int pack_slots;                // lane_pack_kernel: resident games per CTA (<= PK_S; fewer when the job is smaller than the machine)
 };
-
-// The code path the next ply of a game needs.  A warp runs ONE path per step, for all its lanes that
-// wait for that path (see lane_run_kernel).
-// PATH_CLOSED: the distinct plays are counted in closed form (contact play, entering from the bar, or
-// nothing to move); PATH_WALK: the side can bear off within the play, counted root by root.
-// PATH_STORE: the game is over (or the rollout has nothing left to play): write its result, once, in one place.
-enum { PATH_DONE = 0, PATH_CLOSED, PATH_WALK, PATH_STORE, PATH_COUNT };
-
-__device__ __forceinline__ int lane_path(const LaneBoard &g) {
-    const uint32_t o123 = g.own[1] | g.own[2] | g.own[3];
-    const uint32_t own1 = g.own[0] | o123;
-    if (g.bar_own > 0 || own1 == 0) return PATH_CLOSED;
-    const uint32_t outside = own1 & ~0x3Fu;
-    if ((outside & (outside - 1u)) == 0 && (outside & ~(g.own[0] & ~o123)) == 0) {
-        // bearing off.  Every checker home and no opposing checker there: the play comes out of the table (cheap, so it
-        // rides with the closed path); one checker still outside, or contact inside the home board: the walk.
-        return (outside == 0 && ((g.opp[0] | g.opp[1] | g.opp[2] | g.opp[3]) & 0x3Fu) == 0) ? PATH_CLOSED : PATH_WALK;
-    }
-    return PATH_CLOSED;
-}
 
 // One lane per item (a game, or one rollout of a search), whole job in one launch.
 //
@@ -301,47 +270,6 @@ __global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32
 // kind and the kernel was only 7 % faster; hence the queues.
 // The plies themselves are the same device functions as above, and a game's dice and choices are keyed by (game id, ply),
 // so who plays a ply changes nothing in what is played.
-#ifndef DIEE_PK_S
-#define DIEE_PK_S 512
-#endif
-#ifndef DIEE_PK_PATIENCE
-#define DIEE_PK_PATIENCE 4
-#endif
-constexpr int PK_T = 256;        // threads per CTA
-constexpr int PK_S = DIEE_PK_S;  // resident games per CTA
-constexpr int PK_RING = PK_S <= 512 ? 512 : 1024;  // ring size per queue (a power of two >= PK_S: a game is in one queue at most)
-constexpr int PK_AREAS = 3;      // warps that may run the bear-off walk at a time (one scratch area each)
-constexpr int PK_PATIENCE = DIEE_PK_PATIENCE;  // polls without a full queue before a warp takes a partial one
-constexpr int PK_WORDS = 13;
-enum { PC_TWO = 0, PC_DBL, PC_BAR, PC_TABLE, PC_WALK, PC_TURN, PC_LISTS, PC_DEAD = PC_LISTS };
-constexpr uint32_t PK_HAS_GAME = 1u << 24;
-constexpr unsigned PK_EMPTY = 0xFFFFu;
-
-struct PackSmem {
-    uint32_t st[PK_WORDS][PK_S];        // own[4], opp[4], misc, ply, item, game id, counter word 3
-    uint32_t scr[PK_AREAS][L_SCRATCH][32];
-    uint16_t ring[PC_LISTS][PK_RING];
-    unsigned head[8], tail[8];
-    int area_lock[4];
-    int n_dead;
-};
-
-__device__ __forceinline__ int pack_class(const LaneBoard &g) {
-    if (lane_path(g) == PATH_WALK) return PC_WALK;
-    if (g.bar_own > 0) return PC_BAR;
-    const uint32_t own1 = g.own[0] | g.own[1] | g.own[2] | g.own[3];
-    if (own1 != 0 && (own1 & ~0x3Fu) == 0) return PC_TABLE;  // (lane_path: every checker home, no opposing checker there)
-    return g.roll0 == g.roll1 ? PC_DBL : PC_TWO;
-}
-__device__ __forceinline__ uint32_t pack_misc(const LaneBoard &g) {
-    return (uint32_t)g.bar_own | ((uint32_t)g.bar_opp << 4) | ((uint32_t)g.off_own << 8) | ((uint32_t)g.off_opp << 12) |
-           ((uint32_t)g.roll0 << 16) | ((uint32_t)g.roll1 << 19) | ((uint32_t)g.second << 22) | ((g.player > 0 ? 1u : 0u) << 23) | PK_HAS_GAME;
-}
-__device__ __forceinline__ void unpack_misc(LaneBoard &g, uint32_t m) {
-    g.bar_own = (int)(m & 15u); g.bar_opp = (int)((m >> 4) & 15u); g.off_own = (int)((m >> 8) & 15u); g.off_opp = (int)((m >> 12) & 15u);
-    g.roll0 = (int)((m >> 16) & 7u); g.roll1 = (int)((m >> 19) & 7u); g.second = (int)((m >> 22) & 1u); g.player = (m >> 23) & 1u ? 1 : -1;
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(PK_T, 3)
 lane_pack_kernel(LaneJob job) {
@@ -355,20 +283,30 @@ lane_pack_kernel(LaneJob job) {
     for (int s = tid; s < PK_S; s += PK_T) sm.st[8][s] = 0;
     for (int i = tid; i < PC_LISTS * PK_RING; i += PK_T) (&sm.ring[0][0])[i] = (uint16_t)PK_EMPTY;
     __syncthreads();
-    for (int s = tid; s < PK_S; s += PK_T) sm.ring[PC_TURN][s] = (uint16_t)s;
-    if (tid < 8) { sm.head[tid] = 0; sm.tail[tid] = tid == PC_TURN ? PK_S : 0; }
+    const int my_slots = job.pack_slots;  // (the others stay dead: a job smaller than the machine is spread over all CTAs)
+    for (int s = tid; s < my_slots; s += PK_T) sm.ring[PC_TURN][s] = (uint16_t)s;
+    if (tid < 8) { sm.head[tid] = 0; sm.tail[tid] = tid == PC_TURN ? (unsigned)my_slots : 0u; }
     if (tid < 4) sm.area_lock[tid] = 0;
-    if (tid == 0) sm.n_dead = 0;
+    if (tid == 0) {
+        sm.n_dead = PK_S - my_slots;
+        sm.n_avail = my_slots;
+        sm.drain = (long long)gridDim.x * my_slots >= job.n_items ? 1 : 0;  // one wave: every item is resident from the start
+    }
     __syncthreads();
     volatile unsigned *vhead = sm.head, *vtail = sm.tail;
     volatile int *vlock = sm.area_lock;
-    volatile int *vdead = &sm.n_dead;
+    volatile int *vdead = &sm.n_dead, *vavail = &sm.n_avail, *vdrain = &sm.drain;
 #ifdef DIEE_LANE_STATS
     unsigned long long st_batches = 0, st_lanes = 0, st_polls = 0, st_kind[PC_LISTS] = {0, 0, 0, 0, 0, 0};
 #endif
     int polls = 0;
     for (;;) {
         if (*vdead >= PK_S) break;
+        if (*vavail <= 0) {  // nothing waits anywhere: a cheap poll (idle warps share the issue slots with the busy ones)
+            ++polls;
+            __nanosleep(*vdrain ? 40u : 200u);
+            continue;
+        }
         // ---- the longest queue ----
         unsigned cnt = 0;
         if (lane < PC_LISTS) {
@@ -380,7 +318,7 @@ lane_pack_kernel(LaneJob job) {
         const unsigned best = __reduce_max_sync(0xFFFFFFFFu, (cnt << 3) | (unsigned)(lane & 7));
         const int c = (int)(best & 7u);
         const int avail = (int)(best >> 3);
-        const int take = avail >= 32 ? 32 : (polls >= PK_PATIENCE ? avail : 0);
+        const int take = avail >= 32 ? 32 : ((polls >= PK_PATIENCE || *vdrain) ? avail : 0);
         if (take == 0) {
             ++polls;
 #ifdef DIEE_LANE_STATS
@@ -399,6 +337,7 @@ lane_pack_kernel(LaneJob job) {
                 h = vhead[c];
                 const unsigned t = vtail[c];
                 if ((int)(t - h) >= take) ok = atomicCAS(&sm.head[c], h, h + (unsigned)take) == h;
+                if (ok) atomicSub(&sm.n_avail, take);
                 if (!ok && area >= 0) { atomicExch(&sm.area_lock[area], 0); area = -1; }
             }
         }
@@ -463,6 +402,7 @@ lane_pack_kernel(LaneJob job) {
                 k = 0;
                 if (it_l >= job.n_items) {
                     newc = PC_DEAD;
+                    sm.drain = 1;
                 } else if (ROLLOUT) {
                     uint32_t gm, it;
                     if (job.game_minor) {
@@ -537,7 +477,7 @@ lane_pack_kernel(LaneJob job) {
             const int leader = __ffs(same) - 1;
             unsigned base = 0;
             if (lane == leader) {
-                if (newc >= 0 && newc < PC_LISTS) base = atomicAdd(&sm.tail[newc], (unsigned)__popc(same));
+                if (newc >= 0 && newc < PC_LISTS) { base = atomicAdd(&sm.tail[newc], (unsigned)__popc(same)); atomicAdd(&sm.n_avail, __popc(same)); }
                 else if (newc == PC_DEAD) atomicAdd(&sm.n_dead, __popc(same));
             }
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
@@ -597,8 +537,10 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
         const int pack_bps = getenv("DIEE_PACK_BPS") ? atoi(getenv("DIEE_PACK_BPS")) : 3;
         const bool fits = job.n_items < (1ll << 31) && (MODE == LANE_PLAYOUT || (long long)job.n_games * job.iterations < (1ll << 31));
         if (fits && (pack_env == 2 || (pack_env == 1 && job.n_items >= (long long)sms * 1024))) {
-            long long pb = (job.n_items + PK_S - 1) / PK_S;
+            long long pb = (job.n_items + 31) / 32;
             if (pb > (long long)sms * pack_bps) pb = (long long)sms * pack_bps;
+            long long per_cta = ((job.n_items + pb - 1) / pb + 31) / 32 * 32;
+            job.pack_slots = (int)(per_cta < PK_S ? per_cta : PK_S);
             static bool attr_set = false;  // (per kernel instance: this is a template)
             if (!attr_set) {
                 if ((e = cudaFuncSetAttribute(lane_pack_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem))) != cudaSuccess) return e;

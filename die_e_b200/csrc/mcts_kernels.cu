@@ -17,6 +17,7 @@
 
 #include "bg_device.cuh"
 #include "bg_lane.cuh"
+#include "lane_pack.cuh"
 #include "launchers.h"
 
 namespace diee {
@@ -229,43 +230,23 @@ __device__ __forceinline__ float rollout_plies(G &game, WarpSlab &slab, int lane
     return 0.f;
 }
 
-// SPLIT = reference-exact rollouts only: Node::simulate tests the winner of the START state
-// (node.rs:181, quirk Q5), so a rollout from a non-terminal node returns 0 whatever it plays and the
-// tree never depends on it.  The tree kernel then only records which node each simulation rolls
-// out from, and rollout_kernel runs all games x iterations rollouts concurrently (same stream
-// coordinates, so every rollout plays the same plies as in the fused form).
-//
-// LOCK = lock-step search (DIEE_MODE_ROLLOUT_CHECK_CURRENT on the lane engine): the rollout DOES feed the tree, so the
-// search runs as one launch per iteration for all games -- this kernel does back-propagation of the previous
-// iteration's rollout result (pool.roll_result, written by lane_run_kernel<LANE_ROLLOUT_CC>), select and expand, and
-// defers the new rollout to the lane kernel that follows it on the stream; a last launch with it_begin == it_end ==
-// iterations back-propagates the last result and picks the move.  The pool stays in HBM / L2 between launches.
-// MINB = resident CTAs per SM the register allocation must allow.  The kernel is latency-bound, so a batch of many
-// waves gains from 5 CTAs per SM (102 registers, a few spilled words: 8,192 games 1.25 -> 1.13 ms, 32,768 games 4.08 ->
-// 3.62 ms), while the one-wave BASELINE batch is a little faster with the full 126 (0.466 vs 0.478 ms).
-template <class G, bool SPLIT, bool LOCK = false, int MINB = 1>
-__global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32, MINB)
-mcts_search_kernel(const typename G::State *__restrict__ roots, int g0, int n, const int8_t *__restrict__ players,
-                   diee_mcts_cfg cfg, uint32_t it_begin, uint32_t it_end, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
-                   Pool pool, const float *__restrict__ ln_table, uint32_t *__restrict__ best_out,
-                   int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out, bool slab_in_smem,
-                   bool fill_counts) {
-    __shared__ WarpSlab slabs[MCTS_WARPS_PER_CTA];
-    // the root's plays, generated once, 32 per call (every lane asks for a different one): Node::expand pops them one
-    // by one over the first iterations of the search, and each pop would otherwise regenerate the root's move set
-    __shared__ uint32_t root_plays_all[MCTS_WARPS_PER_CTA][ROOT_PLAYS];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int gidx = g0 + blockIdx.x * MCTS_WARPS_PER_CTA + wib;  // this launch covers games [g0, n)
-    if (gidx >= n) return;
-    WarpSlab &slab = slabs[wib];
-    uint32_t *root_plays = root_plays_all[wib];
+// One game's share of a launch: iterations [it_begin, it_end) of its search (see the kernel below for the forms).  `mine` is
+// the game's node slab in shared memory, or null when the search works on the pool in HBM / L2 directly.  A device function
+// so that the persistent check-current search (cc_search_kernel) can run tree steps from inside its own loop.
+template <class G, bool SPLIT, bool LOCK>
+__device__ __forceinline__ void mcts_game_body(const int gidx, const int lane, WarpSlab &slab, uint32_t *root_plays, unsigned char *mine,
+                                               const typename G::State *__restrict__ roots, const int8_t *__restrict__ players,
+                                               const diee_mcts_cfg &cfg, uint32_t it_begin, uint32_t it_end, uint64_t seed,
+                                               uint32_t first_game_id, uint32_t epoch, const Pool &pool, const float *__restrict__ ln_table,
+                                               uint32_t *__restrict__ best_out, int32_t *__restrict__ status_out,
+                                               diee_search_stats *__restrict__ stats_out, bool fill_counts) {
+    const bool slab_in_smem = mine != nullptr;
     const int cap = (int)cfg.iterations + 1;
     const size_t base = (size_t)gidx * cap;
     // The game's node slab.  While the kernel runs it lives in SHARED memory when it fits (the search is a
     // chain of dependent reads of parent / visits / value / move counts / states -- a few dozen cycles each
     // from shared memory, several hundred from L2) and is written back to the HBM pool, coalesced, at the
     // end; otherwise the kernel works on the pool directly.
-    extern __shared__ __align__(16) unsigned char slab_mem[];
     typename G::State *gst = reinterpret_cast<typename G::State *>(pool.states) + base;
     int32_t *gparent = pool.parent + base;
     float *gvisits = pool.visits + base, *gvalue = pool.value + base;
@@ -284,7 +265,6 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int g0, int n, c
     // a handful of times, and each time would otherwise regenerate its move set to pop one play
     uint32_t *nplays = nullptr;
     if (slab_in_smem) {
-        unsigned char *mine = slab_mem + (size_t)wib * cap * (sizeof(typename G::State) + 24 + 4 * NODE_PLAYS);
         st = reinterpret_cast<typename G::State *>(mine);
         parent = reinterpret_cast<int32_t *>(mine + (size_t)cap * sizeof(typename G::State));
         visits = reinterpret_cast<float *>(parent + cap);
@@ -573,6 +553,254 @@ mcts_search_kernel(const typename G::State *__restrict__ roots, int g0, int n, c
     }
 }
 
+// SPLIT = reference-exact rollouts only: Node::simulate tests the winner of the START state
+// (node.rs:181, quirk Q5), so a rollout from a non-terminal node returns 0 whatever it plays and the
+// tree never depends on it.  The tree kernel then only records which node each simulation rolls
+// out from, and rollout_kernel runs all games x iterations rollouts concurrently (same stream
+// coordinates, so every rollout plays the same plies as in the fused form).
+//
+// LOCK = lock-step search (DIEE_MODE_ROLLOUT_CHECK_CURRENT on the lane engine): the rollout DOES feed the tree, so the
+// search runs as one launch per iteration for all games -- this kernel does back-propagation of the previous
+// iteration's rollout result (pool.roll_result, written by lane_run_kernel<LANE_ROLLOUT_CC>), select and expand, and
+// defers the new rollout to the lane kernel that follows it on the stream; a last launch with it_begin == it_end ==
+// iterations back-propagates the last result and picks the move.  The pool stays in HBM / L2 between launches.
+// MINB = resident CTAs per SM the register allocation must allow.  The kernel is latency-bound, so a batch of many
+// waves gains from 5 CTAs per SM (102 registers, a few spilled words: 8,192 games 1.25 -> 1.13 ms, 32,768 games 4.08 ->
+// 3.62 ms), while the one-wave BASELINE batch is a little faster with the full 126 (0.466 vs 0.478 ms).
+template <class G, bool SPLIT, bool LOCK = false, int MINB = 1>
+__global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32, MINB)
+mcts_search_kernel(const typename G::State *__restrict__ roots, int g0, int n, const int8_t *__restrict__ players,
+                   diee_mcts_cfg cfg, uint32_t it_begin, uint32_t it_end, uint64_t seed, uint32_t first_game_id, uint32_t epoch,
+                   Pool pool, const float *__restrict__ ln_table, uint32_t *__restrict__ best_out,
+                   int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out, bool slab_in_smem,
+                   bool fill_counts) {
+    __shared__ WarpSlab slabs[MCTS_WARPS_PER_CTA];
+    // the root's plays, generated once, 32 per call (every lane asks for a different one): Node::expand pops them one
+    // by one over the first iterations of the search, and each pop would otherwise regenerate the root's move set
+    __shared__ uint32_t root_plays_all[MCTS_WARPS_PER_CTA][ROOT_PLAYS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gidx = g0 + blockIdx.x * MCTS_WARPS_PER_CTA + wib;  // this launch covers games [g0, n)
+    if (gidx >= n) return;
+    WarpSlab &slab = slabs[wib];
+    uint32_t *root_plays = root_plays_all[wib];
+    extern __shared__ __align__(16) unsigned char slab_mem[];
+    unsigned char *mine = slab_in_smem ? slab_mem + (size_t)wib * ((size_t)cfg.iterations + 1) * (sizeof(typename G::State) + 24 + 4 * NODE_PLAYS) : nullptr;
+    mcts_game_body<G, SPLIT, LOCK>(gidx, lane, slab, root_plays, mine, roots, players, cfg, it_begin, it_end, seed, first_game_id, epoch, pool,
+                                   ln_table, best_out, status_out, stats_out, fill_counts);
+}
+
+// ---------------- check-current search, persistent form ----------------
+// With DIEE_MODE_ROLLOUT_CHECK_CURRENT a rollout's result feeds the tree, so iteration i+1 of a game waits for its rollout
+// i -- but only for ITS rollout.  The lock-step form (one tree launch + one rollout launch per iteration) makes every game
+// wait for the slowest rollout of its group, iteration after iteration.  Here every game runs at its own pace inside ONE
+// launch: the games of a CTA are resident in shared memory exactly as in lane_pack_kernel (lane_kernels.cu) and queue up
+// by the code their next step needs -- the five kinds of ply, or "tree step".  A warp that takes tree steps off the queue
+// runs them one game after the other with the warp-per-game code of the tree kernel (mcts_game_body, LOCK form: back-
+// propagate the rollout that just ended, select, expand), then each of its lanes loads the new leaf and the game goes
+// back into the ply queues.  Same pool, same stream coordinates, same float operations in the same order per game as
+// the lock-step form, so the results are bit-identical.  A game is bound to one slot of one CTA for the whole search.
+struct CcSmem {
+    PackSmem pk;
+    WarpSlab slabs[PK_T / 32];
+    uint32_t root_plays[PK_T / 32][32];  // (the LOCK form writes the root's first plays here and never reads them)
+};
+
+__device__ __forceinline__ void cc_load_state(LaneBoard &g, const diee_bg_state *s) {
+    // written earlier in this launch by another warp of the CTA: L2, not the read-only path
+    const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(s));
+    const uint4 b = __ldcg(reinterpret_cast<const uint4 *>(s) + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    l_load(g, w);
+}
+
+__global__ void __launch_bounds__(PK_T, 2)
+cc_search_kernel(const diee_bg_state *__restrict__ roots, int n, const int8_t *__restrict__ players, diee_mcts_cfg cfg, uint64_t seed,
+                 uint32_t first_game_id, uint32_t epoch, Pool pool, const float *__restrict__ ln_table, uint32_t *__restrict__ best_out,
+                 int32_t *__restrict__ status_out, diee_search_stats *__restrict__ stats_out, bool fill_counts, int my_slots,
+                 unsigned long long *__restrict__ work) {
+    extern __shared__ __align__(16) unsigned char cc_smem_raw[];
+    CcSmem &cs = *reinterpret_cast<CcSmem *>(cc_smem_raw);
+    PackSmem &sm = cs.pk;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    // slot s of this CTA holds game s * gridDim.x + blockIdx.x for the whole search
+    int n_mine = (n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    n_mine = n_mine < 0 ? 0 : (n_mine > my_slots ? my_slots : n_mine);
+    for (int s = tid; s < PK_S; s += PK_T) { sm.st[8][s] = 0; sm.st[10][s] = 0; sm.st[11][s] = (uint32_t)(s * (int)gridDim.x + (int)blockIdx.x); }
+    for (int i = tid; i < PC_LISTS * PK_RING; i += PK_T) (&sm.ring[0][0])[i] = (uint16_t)PK_EMPTY;
+    __syncthreads();
+    for (int s = tid; s < n_mine; s += PK_T) sm.ring[PC_TURN][s] = (uint16_t)s;  // every game starts with a tree step
+    if (tid < 8) { sm.head[tid] = 0; sm.tail[tid] = tid == PC_TURN ? (unsigned)n_mine : 0u; }
+    if (tid < 4) sm.area_lock[tid] = 0;
+    if (tid == 0) { sm.n_dead = PK_S - n_mine; sm.n_avail = n_mine; sm.drain = 1; }
+    __syncthreads();
+    volatile unsigned *vhead = sm.head, *vtail = sm.tail;
+    volatile int *vlock = sm.area_lock;
+    volatile int *vdead = &sm.n_dead, *vavail = &sm.n_avail;
+    const size_t cap = (size_t)cfg.iterations + 1;
+    for (;;) {
+        if (*vdead >= PK_S) break;
+        if (*vavail <= 0) { __nanosleep(40u); continue; }
+        // ---- the longest queue; whatever it holds is taken at once (every game of the search is resident: nothing to wait for)
+        unsigned cnt = 0;
+        if (lane < PC_LISTS) {
+            const unsigned h0 = vhead[lane];
+            cnt = vtail[lane] - h0;
+            if (lane == PC_WALK && cnt && vlock[0] && vlock[1] && vlock[2]) cnt = 0;
+            if (cnt > 1023u) cnt = 1023u;
+        }
+        const unsigned best = __reduce_max_sync(FULL, (cnt << 3) | (unsigned)(lane & 7));
+        const int c = (int)(best & 7u);
+        const int avail = (int)(best >> 3);
+        const int take = avail >= 32 ? 32 : avail;
+        if (take == 0) { __nanosleep(40u); continue; }
+        int ok = 0, area = -1;
+        unsigned h = 0;
+        if (lane == 0) {
+            if (c == PC_WALK)
+                for (int a = 0; a < PK_AREAS && area < 0; ++a)
+                    if (atomicCAS(&sm.area_lock[a], 0, 1) == 0) area = a;
+            if (c != PC_WALK || area >= 0) {
+                h = vhead[c];
+                const unsigned t = vtail[c];
+                if ((int)(t - h) >= take) ok = atomicCAS(&sm.head[c], h, h + (unsigned)take) == h;
+                if (ok) atomicSub(&sm.n_avail, take);
+                if (!ok && area >= 0) { atomicExch(&sm.area_lock[area], 0); area = -1; }
+            }
+        }
+        ok = __shfl_sync(FULL, ok, 0);
+        if (!ok) continue;
+        h = __shfl_sync(FULL, h, 0);
+        area = __shfl_sync(FULL, area, 0);
+        const bool act = lane < take;
+        int slot = 0;
+        if (act) {
+            volatile uint16_t *e = &sm.ring[c][(h + (unsigned)lane) & (PK_RING - 1)];
+            unsigned v;
+            while ((v = *e) == PK_EMPTY) {}
+            *e = (uint16_t)PK_EMPTY;
+            slot = (int)v;
+        }
+        __threadfence_block();
+        __syncwarp();
+        const uint32_t act_mask = __ballot_sync(FULL, act);
+        int newc = -1;
+        LaneBoard g;
+        uint32_t k = 0, it = 0, gm = 0;
+        bool keep = false;
+        if (c == PC_TURN) {
+            // ---- tree steps ----
+            uint32_t misc = 0;
+            if (act) {
+                misc = sm.st[8][slot]; k = sm.st[9][slot]; it = sm.st[10][slot]; gm = sm.st[11][slot];
+                if (misc & PK_HAS_GAME) {  // a rollout has ended: node.rs:181-185 on the rolled-out state (see lane_run_kernel)
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) { g.own[w] = sm.st[w][slot]; g.opp[w] = sm.st[4 + w][slot]; }
+                    unpack_misc(g, misc);
+                    const int w = k < cfg.simulate_round_limit ? l_winner(g) : 0, pl = players[gm];
+                    pool.roll_result[gm] = w == 0 ? 0.f : (w == pl ? 1.f : (w == -pl ? -1.f : 0.f));
+                    if (stats_out) stats_out[gm].rollout_plies += k;
+                    lane_store_state(g, reinterpret_cast<diee_bg_state *>(pool.finals) + (size_t)gm * cfg.iterations + it);
+                    it += 1;  // the game's next iteration (== iterations: only the last back-propagation and the move are left)
+                }
+            }
+            {
+                const uint32_t sum = __reduce_add_sync(FULL, (act && (misc & PK_HAS_GAME)) ? k : 0u);
+                if (lane == 0 && sum) atomicAdd(work + 1, (unsigned long long)sum);
+            }
+            __syncwarp();
+            int my_node = -1;
+            bool my_over = false;
+            for (uint32_t todo = act_mask; todo; todo &= todo - 1u) {
+                const int j = __ffs(todo) - 1;
+                const int gj = (int)__shfl_sync(FULL, gm, j);
+                uint32_t itj = __shfl_sync(FULL, it, j);
+                int node = -1;
+                bool over = false;
+                for (;;) {  // tree steps until one defers a rollout, or the game's search is over
+                    mcts_game_body<BgGame, false, true>(gj, lane, cs.slabs[wib], cs.root_plays[wib], nullptr, roots, players, cfg, itj,
+                                                        itj < cfg.iterations ? itj + 1u : itj, seed, first_game_id, epoch, pool, ln_table,
+                                                        best_out, status_out, stats_out, fill_counts);
+                    __syncwarp();
+                    if (itj >= cfg.iterations) { over = true; break; }
+                    int v = 0;
+                    if (lane == 0) v = __ldcg(pool.sim_node + (size_t)gj * cfg.iterations + itj);
+                    v = __shfl_sync(FULL, v, 0);
+                    if (v >= 0) { node = v; break; }
+                    ++itj;
+                }
+                if (lane == j) { it = itj; my_node = node; my_over = over; }
+            }
+            __syncwarp();
+            if (act) {
+                if (my_over) {
+                    newc = PC_DEAD;
+                } else {
+                    cc_load_state(g, reinterpret_cast<const diee_bg_state *>(pool.states) + (size_t)gm * cap + my_node);
+                    k = 0;
+                    keep = true;
+                    newc = l_winner(g) != 0 ? PC_TURN : pack_class(g);
+                    sm.st[10][slot] = it;
+                }
+            }
+        } else if (act) {
+            // ---- one ply ----
+            const uint32_t misc = sm.st[8][slot];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { g.own[w] = sm.st[w][slot]; g.opp[w] = sm.st[4 + w][slot]; }
+            unpack_misc(g, misc);
+            k = sm.st[9][slot]; it = sm.st[10][slot]; gm = sm.st[11][slot];
+            uint32_t o[4];
+            l_philox((uint32_t)seed, (uint32_t)(seed >> 32), k, first_game_id + gm, DIEE_STREAM_ROLLOUT, (epoch << 16) | (it & 0xFFFFu), o);
+            LanePlay pl;
+            pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
+            if (c != PC_WALK) {
+                const int hi = max(g.roll0, g.roll1), lo = min(g.roll0, g.roll1);
+                LaneMasks m;
+                l_closed_applies(g, m, lo, hi);
+                if (g.bar_own == 0 && m.own1 != 0 && (m.own1 & ~0x3Fu) == 0) {
+                    const uint32_t e = __ldg(pool.pb.index + l_pb_key(g));
+                    const uint32_t U = e & 255u;
+                    if (U > 0) pl = l_pb_unpack(__ldg(pool.pb.plays + (e >> 8) + l_index(o[2], U)));
+                } else {
+                    if (m.own1 != 0 || g.bar_own > 0) l_contact_select(g, m, lo, hi, -2, o[2], pl);
+                }
+            } else {
+                LaneGen gen;
+                uint32_t *scr = &sm.scr[area][0][lane];
+                l_movegen_walk_t<true>(g, gen, scr, 32);
+                if (gen.U > 0) pl = l_pick_walk(gen, scr, 32, (int)l_index(o[2], (uint32_t)gen.U));
+            }
+            l_step(g, pl, l_die(o[0]), l_die(o[1]));
+            ++k;
+            keep = true;
+            newc = (k == cfg.simulate_round_limit || l_winner(g) != 0) ? PC_TURN : pack_class(g);
+        }
+        if (keep) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { sm.st[w][slot] = g.own[w]; sm.st[4 + w][slot] = g.opp[w]; }
+            sm.st[8][slot] = pack_misc(g);
+            sm.st[9][slot] = k;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (area >= 0 && lane == 0) atomicExch(&sm.area_lock[area], 0);
+        {
+            const uint32_t same = __match_any_sync(FULL, newc);
+            const int leader = __ffs(same) - 1;
+            unsigned base = 0;
+            if (lane == leader) {
+                if (newc >= 0 && newc < PC_LISTS) { base = atomicAdd(&sm.tail[newc], (unsigned)__popc(same)); atomicAdd(&sm.n_avail, __popc(same)); }
+                else if (newc == PC_DEAD) atomicAdd(&sm.n_dead, __popc(same));
+            }
+            base = __shfl_sync(FULL, base, leader);
+            if (newc >= 0 && newc < PC_LISTS) {
+                volatile uint16_t *e = &sm.ring[newc][(base + (unsigned)__popc(same & ((1u << lane) - 1u))) & (PK_RING - 1)];
+                *e = (uint16_t)slot;
+            }
+        }
+    }
+}
+
 // all deferred rollouts of a split search: one warp per (game, iteration)
 template <class G>
 __global__ void __launch_bounds__(MCTS_WARPS_PER_CTA * 32)
@@ -654,6 +882,34 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         // iterations: 1,024 games 18.8 ms fused / 60 ms lock-step; 16,384 games 110 / 70.6 ms; 65,536 games: 125 ms lock-step.
         const char *fenv = getenv("DIEE_CC_FUSED");
         const bool fused = fenv ? atoi(fenv) != 0 : n < 12288;
+        // DIEE_CC_PERSISTENT=1: the persistent form (cc_search_kernel: every game at its own pace inside one launch), for
+        // batches whose games all fit the machine's resident slots.  EXPERIMENT, off by default: bit-identical, but measured on
+        // B200 (100 iterations) 1,024 games 39.5 ms (fused 18.4), 16,384 games 88.0 ms (lock-step 71.2), 65,536 games 132.9 ms
+        // (lock-step 126.1) -- a game no longer waits for the slowest rollout of its group, but its own plies cost ~3 us each
+        // through the queues (one thread's dependent chain per ply, as in the lane kernel), and a tree step on the pool in
+        // L2 holds a warp for tens of microseconds while the SM's issue slots are busy with plies.
+        if (!split && cfg.simulate_round_limit > 0) {
+            const char *penv = getenv("DIEE_CC_PERSISTENT");
+            int sms = 148;
+            { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+            long long grid = ((long long)n + 31) / 32;
+            if (grid > 2ll * sms) grid = 2ll * sms;
+            const long long per_cta = (((long long)n + grid - 1) / grid + 31) / 32 * 32;
+            const bool persistent = penv ? atoi(penv) != 0 : false;
+            if (persistent && per_cta <= PK_S && cfg.iterations < 65536u) {
+                static bool attr_set = false;
+                if (!attr_set) {
+                    if ((e = cudaFuncSetAttribute(cc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcSmem))) != cudaSuccess) return e;
+                    attr_set = true;
+                }
+                *pipe.timed = false;
+                cc_search_kernel<<<(unsigned)grid, PK_T, sizeof(CcSmem), st>>>(
+                    reinterpret_cast<const diee_bg_state *>(r), n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out,
+                    status_out, stats_out, dump, (int)per_cta, pipe.queue_heads);
+                *launches += 1;
+                return cudaGetLastError();
+            }
+        }
         if (!split && !fused && cfg.simulate_round_limit > 0) {
             int groups = n >= 8192 ? 4 : (n >= 2048 ? 2 : 1);
             if (const char *ev = getenv("DIEE_CC_GROUPS")) groups = atoi(ev);

@@ -167,21 +167,52 @@ def test_sliced_search_is_the_same_search(ctx, oracle, monkeypatch):
 
 
 def test_lockstep_check_current_groups_and_fused_form_agree(ctx, oracle, monkeypatch):
-    """DIEE_MODE_ROLLOUT_CHECK_CURRENT runs lock-step on the lane engine (one tree launch + one rollout launch per
-    iteration, games cut into groups on side streams).  Any number of groups, and the round-1 fused form
-    (DIEE_CC_FUSED=1: one launch, warp-per-game rollouts), must give the same pool, moves and rollout end states."""
+    """DIEE_MODE_ROLLOUT_CHECK_CURRENT has three forms: lock-step on the lane engine (one tree launch + one rollout launch
+    per iteration, games cut into groups on side streams), the round-1 fused form (DIEE_CC_FUSED=1: one launch, warp-per-game
+    rollouts) and the persistent form (DIEE_CC_PERSISTENT=1, cc_search_kernel: one launch, every game at its own pace,
+    games queued by the code of their next step).  All must give the same pool, moves and rollout end states."""
     from die_e_b200 import _ffi
     states = positions.midgame_positions(seed=29, n=70, max_adv=110)
     players = states["player"].copy()
     cfg = oracle.mcts_cfg(iterations=25, c=2.0, limit=400, mode=_ffi.MODE_PASS_CHILD | _ffi.MODE_ROLLOUT_CHECK_CURRENT)
     monkeypatch.setenv("DIEE_CC_FUSED", "0")   # (small batches default to the fused form)
+    monkeypatch.setenv("DIEE_CC_PERSISTENT", "0")
     ref = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
     assert (ref[1] == 0).all() and int(ref[2]["rollout_plies"].sum()) > 0
-    for env, val in (("DIEE_CC_GROUPS", "3"), ("DIEE_CC_GROUPS", "4"), ("DIEE_CC_FUSED", "1")):
+    for env, val in (("DIEE_CC_GROUPS", "3"), ("DIEE_CC_GROUPS", "4"), ("DIEE_CC_FUSED", "1"), ("DIEE_CC_PERSISTENT", "1")):
         monkeypatch.setenv(env, val)
         got = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 5, 100, 3, dump=True)
-        monkeypatch.delenv(env) if env != "DIEE_CC_FUSED" else monkeypatch.setenv("DIEE_CC_FUSED", "0")
+        if env == "DIEE_CC_GROUPS":
+            monkeypatch.delenv(env)
+        else:
+            monkeypatch.setenv(env, "0")
         _same_search(ref, got, f"{env}={val}")
-    # and against the oracle, game by game, with the full rollout cap
+    # and against the oracle, game by game, with the full rollout cap -- the lock-step form, then the persistent one
     _cmp_trees(oracle, _ffi, ctx, _ffi.GAME_BACKGAMMON, states[:24], players[:24], cfg, 5, 100, 3)
+    monkeypatch.setenv("DIEE_CC_PERSISTENT", "1")
+    _cmp_trees(oracle, _ffi, ctx, _ffi.GAME_BACKGAMMON, states[:24], players[:24], cfg, 5, 100, 3)
+    for mode in (1, 3):   # without PASS_CHILD some games hit the reference's panic: the persistent form reports the same
+        cfg2 = oracle.mcts_cfg(iterations=40, c=2.0, limit=60, mode=mode)
+        _cmp_trees(oracle, _ffi, ctx, _ffi.GAME_BACKGAMMON, states[:32], players[:32], cfg2, 9, 7, 1)
     monkeypatch.delenv("DIEE_CC_FUSED")
+    monkeypatch.delenv("DIEE_CC_PERSISTENT")
+
+
+def test_persistent_check_current_at_a_few_thousand_games(ctx, oracle, monkeypatch):
+    """3,000 games (ten resident games per CTA and more): the same search as the lock-step form, game for game"""
+    from die_e_b200 import _ffi
+    rng = np.random.default_rng(5)
+    base = positions.midgame_positions(seed=31, n=500, max_adv=130)
+    states = base[rng.integers(0, len(base), size=3000)]
+    players = states["player"].copy()
+    cfg = oracle.mcts_cfg(iterations=16, c=2.0, limit=400, mode=_ffi.MODE_PASS_CHILD | _ffi.MODE_ROLLOUT_CHECK_CURRENT)
+    monkeypatch.setenv("DIEE_CC_FUSED", "0")
+    monkeypatch.setenv("DIEE_CC_PERSISTENT", "0")
+    ref = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 11, 0, 2, dump=True)
+    work_ref = ctx.search_work()
+    monkeypatch.setenv("DIEE_CC_PERSISTENT", "1")
+    got = ctx.mcts_search(_ffi.GAME_BACKGAMMON, states, players, cfg, 11, 0, 2, dump=True)
+    _same_search(ref, got, "persistent form, 3,000 games")
+    assert ctx.search_work() == work_ref == int(ref[2]["rollout_plies"].sum())
+    monkeypatch.delenv("DIEE_CC_FUSED")
+    monkeypatch.delenv("DIEE_CC_PERSISTENT")

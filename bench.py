@@ -708,6 +708,8 @@ def sub_mcts(ctx, ffi, torch, dev, stream, rank, world, G2, cfg, reduce_max, rep
                         "rollout_ms": round(roll_ms, 4), "rollout_plies_played": plies,
                         "rollout_gplies_per_s": round(plies / roll_ms / 1e6, 2),
                         "same_best_moves_with_the_other_rollout_kernel": bool(same)})
+            if packed and G2 == 8192:  # the committed ncu export of this very job (tools/pack_stats.py 8192, tools/ncu_issue.py)
+                out["issue"] = issue_record("r02_lane_pack_rollouts_issue.json")
             if not same:
                 raise SystemExit("bench: the packed and the lane-resident rollout kernels disagree at %d games" % G2)
         except ffi.DieeError:

@@ -28,7 +28,8 @@ using namespace lane;
 constexpr int LANE_CTA = 64;
 
 #ifdef DIEE_LANE_STATS
-__device__ unsigned long long g_lane_stats[16];  // [p] = steps executed on path p, [8+p] = lanes advanced
+__device__ unsigned long long g_lane_stats[16];
+__device__ unsigned long long g_lane_stats2[16];  // [p] = steps executed on path p, [8+p] = lanes advanced
 #endif
 
 enum { LANE_PLAYOUT = 0, LANE_ROLLOUT = 1, LANE_ROLLOUT_CC = 2 };
@@ -298,6 +299,8 @@ lane_pack_kernel(LaneJob job) {
     volatile int *vdead = &sm.n_dead, *vavail = &sm.n_avail, *vdrain = &sm.drain;
 #ifdef DIEE_LANE_STATS
     unsigned long long st_batches = 0, st_lanes = 0, st_polls = 0, st_kind[PC_LISTS] = {0, 0, 0, 0, 0, 0};
+    unsigned long long st_cyc[PC_LISTS] = {0, 0, 0, 0, 0, 0}, st_nb[PC_LISTS] = {0, 0, 0, 0, 0, 0};
+    unsigned st_kmax = 0;
 #endif
     int polls = 0;
     for (;;) {
@@ -359,6 +362,7 @@ lane_pack_kernel(LaneJob job) {
         __syncwarp();
 #ifdef DIEE_LANE_STATS
         ++st_batches; st_lanes += take; st_kind[c] += take;
+        const long long t_batch = clock64();
 #endif
         const uint32_t act_mask = __ballot_sync(0xFFFFFFFFu, act);
         int newc = -1;
@@ -370,6 +374,9 @@ lane_pack_kernel(LaneJob job) {
             if (c == PC_TURN) {
                 k = sm.st[9][slot]; item = sm.st[10][slot]; gid = sm.st[11][slot]; c3 = sm.st[12][slot];
                 const bool has = misc & PK_HAS_GAME;
+#ifdef DIEE_LANE_STATS
+                if (has && k > st_kmax) st_kmax = k;
+#endif
                 {   // plies this job actually played (the closed-form tail below is not work)
                     const uint32_t sum = __reduce_add_sync(act_mask, has ? k : 0u);
                     if (lane == 0 && sum) atomicAdd(job.next_item + 1, (unsigned long long)sum);
@@ -436,31 +443,38 @@ lane_pack_kernel(LaneJob job) {
                 for (int w = 0; w < 4; ++w) { g.own[w] = sm.st[w][slot]; g.opp[w] = sm.st[4 + w][slot]; }
                 unpack_misc(g, misc);
                 k = sm.st[9][slot]; gid = sm.st[11][slot]; c3 = sm.st[12][slot];
-                uint32_t o[4];
-                l_philox((uint32_t)job.seed, (uint32_t)(job.seed >> 32), k, gid, stream, c3, o);
-                LanePlay pl;
-                pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
-                if (c != PC_WALK) {
-                    const int hi = max(g.roll0, g.roll1), lo = min(g.roll0, g.roll1);
-                    LaneMasks m;
-                    l_closed_applies(g, m, lo, hi);
-                    if (g.bar_own == 0 && m.own1 != 0 && (m.own1 & ~0x3Fu) == 0) {
-                        const uint32_t e = __ldg(job.pb.index + l_pb_key(g));
-                        const uint32_t U = e & 255u;
-                        if (U > 0) pl = l_pb_unpack(__ldg(job.pb.plays + (e >> 8) + l_index(o[2], U)));
+                // While the job drains (no new games will come; what is left are the long ones) latency counts, not how full
+                // the warps are: a game stays with its lane while its next ply runs the same code -- any closed-form kind after
+                // a closed-form kind, a walk after a walk -- up to job.reps plies per visit, as in lane_run_kernel.
+                int reps = *vdrain ? job.reps : 1;
+                for (;;) {
+                    uint32_t o[4];
+                    l_philox((uint32_t)job.seed, (uint32_t)(job.seed >> 32), k, gid, stream, c3, o);
+                    LanePlay pl;
+                    pl.n = 0; pl.x1 = pl.t1 = pl.x2 = pl.t2 = 0;
+                    if (c != PC_WALK) {
+                        const int hi = max(g.roll0, g.roll1), lo = min(g.roll0, g.roll1);
+                        LaneMasks m;
+                        l_closed_applies(g, m, lo, hi);
+                        if (g.bar_own == 0 && m.own1 != 0 && (m.own1 & ~0x3Fu) == 0) {
+                            const uint32_t e = __ldg(job.pb.index + l_pb_key(g));
+                            const uint32_t U = e & 255u;
+                            if (U > 0) pl = l_pb_unpack(__ldg(job.pb.plays + (e >> 8) + l_index(o[2], U)));
+                        } else {
+                            if (m.own1 != 0 || g.bar_own > 0) l_contact_select(g, m, lo, hi, -2, o[2], pl);
+                        }
                     } else {
-                        if (m.own1 != 0 || g.bar_own > 0) l_contact_select(g, m, lo, hi, -2, o[2], pl);
+                        LaneGen gen;
+                        uint32_t *scr = &sm.scr[area][0][lane];
+                        l_movegen_walk_t<true>(g, gen, scr, 32);
+                        if (gen.U > 0) pl = l_pick_walk(gen, scr, 32, (int)l_index(o[2], (uint32_t)gen.U));
                     }
-                } else {
-                    LaneGen gen;
-                    uint32_t *scr = &sm.scr[area][0][lane];
-                    l_movegen_walk_t<true>(g, gen, scr, 32);
-                    if (gen.U > 0) pl = l_pick_walk(gen, scr, 32, (int)l_index(o[2], (uint32_t)gen.U));
+                    l_step(g, pl, l_die(o[0]), l_die(o[1]));
+                    ++k;
+                    const bool over = ROLLOUT ? (k == job.limit || (g.off_own == 15 && g.off_opp == 15)) : (k == job.limit || l_winner(g) != 0);
+                    newc = over ? PC_TURN : pack_class(g);
+                    if (--reps <= 0 || (c == PC_WALK ? newc != PC_WALK : newc >= PC_WALK)) break;
                 }
-                l_step(g, pl, l_die(o[0]), l_die(o[1]));
-                ++k;
-                const bool over = ROLLOUT ? (k == job.limit || (g.off_own == 15 && g.off_opp == 15)) : (k == job.limit || l_winner(g) != 0);
-                newc = over ? PC_TURN : pack_class(g);
             }
             if (keep) {
 #pragma unroll
@@ -471,6 +485,9 @@ lane_pack_kernel(LaneJob job) {
         }
         __threadfence_block();  // the games before their ring entries
         __syncwarp();
+#ifdef DIEE_LANE_STATS
+        st_cyc[c] += (unsigned long long)(clock64() - t_batch); ++st_nb[c];
+#endif
         if (area >= 0 && lane == 0) atomicExch(&sm.area_lock[area], 0);
         {   // ---- append every game to the queue of its next ply (one shared atomic per kind present) ----
             const uint32_t same = __match_any_sync(0xFFFFFFFFu, newc);
@@ -493,6 +510,10 @@ lane_pack_kernel(LaneJob job) {
         atomicAdd(&g_lane_stats[0], st_batches); atomicAdd(&g_lane_stats[1], st_lanes); atomicAdd(&g_lane_stats[2], st_polls);
         for (int q = 0; q < PC_LISTS; ++q) atomicAdd(&g_lane_stats[8 + q], st_kind[q]);
     }
+    // (second block, read with diee_debug_lane_stats2: cycles and batches per kind, warp 0 lane 0 of every CTA)
+    if (tid == 0)
+        for (int q = 0; q < PC_LISTS; ++q) { atomicAdd(&g_lane_stats2[q], st_cyc[q]); atomicAdd(&g_lane_stats2[8 + q], st_nb[q]); }
+    atomicMax(&g_lane_stats[15], (unsigned long long)st_kmax);
 #endif
 }
 
@@ -614,6 +635,11 @@ cudaError_t launch_bg_rollout_count(cudaStream_t st, int n_games, const diee_mct
 
 }  // namespace diee
 #ifdef DIEE_LANE_STATS
+extern "C" int diee_debug_lane_stats2(unsigned long long *out16, int reset) {
+    cudaMemcpyFromSymbol(out16, diee::g_lane_stats2, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(diee::g_lane_stats2, z, sizeof z); }
+    return 0;
+}
 extern "C" int diee_debug_lane_stats(unsigned long long *out16, int reset) {
     cudaMemcpyFromSymbol(out16, diee::g_lane_stats, sizeof(unsigned long long) * 16);
     if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(diee::g_lane_stats, z, sizeof z); }

@@ -37,6 +37,7 @@ static void print_state(const orc_bg_state &s) {
 static long long n_checked = 0, n_moves_checked = 0, n_boregime = 0, n_bo_opp_home = 0, n_doubles = 0, n_bar = 0;
 static int max_moves = 0;
 static long long n_closed = 0, n_pb = 0;
+static long long n_bo_outside = 0, n_bo_outside3 = 0;
 static std::vector<uint32_t> pb_index;
 static std::vector<uint16_t> pb_plays;
 
@@ -73,6 +74,13 @@ static bool check_position(const orc_bg_state &s) {
                 memcpy(&o, &mv[k], 4);
                 if (l_play_to_seq(pl, g.player) != o) { fprintf(stderr, "bear-off walk play %d differs\n", k); print_state(s); return false; }
             }
+        }
+        if (bo && n > 0 && outside) {   // one lone checker outside the home board: how many outside sources a play can have
+            ++n_bo_outside;
+            const int hi2 = g.roll0 > g.roll1 ? g.roll0 : g.roll1, lo2 = g.roll0 > g.roll1 ? g.roll1 : g.roll0;
+            int p = 0;
+            while (!((outside >> p) & 1u)) ++p;
+            if (p - hi2 >= 6 && lo2 != hi2) ++n_bo_outside3;
         }
         if (bo && n > 0) {
             ++n_boregime;
@@ -290,7 +298,7 @@ int main(int argc, char **argv) {
         if (!check_position(s)) return 1;
     }
     printf("lane engine == oracle on %lld positions, %lld plays (bear-off regime %lld, of which opposing checkers in the home board %lld; "
-           "doubles %lld; from the bar %lld; counted in closed form %lld; pure bear-off form %lld; most plays in one position %d)\n",
-           n_checked, n_moves_checked, n_boregime, n_bo_opp_home, n_doubles, n_bar, n_closed, n_pb, max_moves);
+           "a lone checker outside %lld, with three outside sources %lld; doubles %lld; from the bar %lld; counted in closed form %lld; pure bear-off form %lld; most plays in one position %d)\n",
+           n_checked, n_moves_checked, n_boregime, n_bo_opp_home, n_bo_outside, n_bo_outside3, n_doubles, n_bar, n_closed, n_pb, max_moves);
     return 0;
 }

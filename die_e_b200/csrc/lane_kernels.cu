@@ -354,7 +354,9 @@ lane_pack_kernel(LaneJob job) {
         if (act) {
             volatile uint16_t *e = &sm.ring[c][(h + (unsigned)lane) & (PK_RING - 1)];
             unsigned v;
-            while ((v = *e) == PK_EMPTY) {}  // reserved, not written yet
+            unsigned spins = 0;
+            while ((v = *e) == PK_EMPTY)  // reserved, not written yet (a handful of cycles; a lost entry must not hang the device)
+                if (++spins > (1u << 28)) __trap();
             *e = (uint16_t)PK_EMPTY;
             slot = (int)v;
         }
@@ -562,11 +564,8 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
             if (pb > (long long)sms * pack_bps) pb = (long long)sms * pack_bps;
             long long per_cta = ((job.n_items + pb - 1) / pb + 31) / 32 * 32;
             job.pack_slots = (int)(per_cta < PK_S ? per_cta : PK_S);
-            static bool attr_set = false;  // (per kernel instance: this is a template)
-            if (!attr_set) {
-                if ((e = cudaFuncSetAttribute(lane_pack_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem))) != cudaSuccess) return e;
-                attr_set = true;
-            }
+            // (every launch: the attribute is per device, and a process may hold contexts on several)
+            if ((e = cudaFuncSetAttribute(lane_pack_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem))) != cudaSuccess) return e;
             lane_pack_kernel<MODE><<<(unsigned)pb, PK_T, sizeof(PackSmem), st>>>(job);
             if (launches) *launches += 1;
             return cudaGetLastError();

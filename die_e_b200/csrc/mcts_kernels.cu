@@ -676,7 +676,9 @@ cc_search_kernel(const diee_bg_state *__restrict__ roots, int n, const int8_t *_
         if (act) {
             volatile uint16_t *e = &sm.ring[c][(h + (unsigned)lane) & (PK_RING - 1)];
             unsigned v;
-            while ((v = *e) == PK_EMPTY) {}
+            unsigned spins = 0;
+            while ((v = *e) == PK_EMPTY)
+                if (++spins > (1u << 28)) __trap();
             *e = (uint16_t)PK_EMPTY;
             slot = (int)v;
         }
@@ -897,11 +899,7 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
             const long long per_cta = (((long long)n + grid - 1) / grid + 31) / 32 * 32;
             const bool persistent = penv ? atoi(penv) != 0 : false;
             if (persistent && per_cta <= PK_S && cfg.iterations < 65536u) {
-                static bool attr_set = false;
-                if (!attr_set) {
-                    if ((e = cudaFuncSetAttribute(cc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcSmem))) != cudaSuccess) return e;
-                    attr_set = true;
-                }
+                if ((e = cudaFuncSetAttribute(cc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcSmem))) != cudaSuccess) return e;
                 *pipe.timed = false;
                 cc_search_kernel<<<(unsigned)grid, PK_T, sizeof(CcSmem), st>>>(
                     reinterpret_cast<const diee_bg_state *>(r), n, players, cfg, seed, first_game_id, epoch, pool, ln_table, best_out,

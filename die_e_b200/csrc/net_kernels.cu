@@ -764,16 +764,24 @@ static bool pdl_enabled() {
     return on;
 }
 
+// cudaFuncSetAttribute is per DEVICE (a process may hold contexts on several): once per device and kernel
+template <class F>
+static cudaError_t smem_opt_in(F *fn, int bytes, unsigned long long &done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && ((done >> dev) & 1ull)) return cudaSuccess;
+    if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if (dev < 64) done |= 1ull << dev;
+    return cudaSuccess;
+}
+
 template <int BN, int NB, int KC>
 static cudaError_t launch_conv_bn(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int n_boards, int ntaps,
                                   int chunks, const float *bias, const __nv_bfloat16 *residual, void *out, int out_mode,
                                   int c_out_total, int relu, int npairs, uint32_t pairs, int a_plane, int b_plane, const ConvEpi &epi) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<BN, NB, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, NB, KC>::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static unsigned long long opted = 0;
+    if (cudaError_t e = smem_opt_in(conv3x3_tc_kernel<BN, NB, KC>, ConvCfg<BN, NB, KC>::SMEM_BYTES, opted); e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)((n_boards + NB - 1) / NB), (unsigned)(c_out_total / BN));
     cfg.blockDim = dim3(CONV_THREADS);
@@ -796,12 +804,8 @@ cudaError_t launch_conv_pair(cudaStream_t st, const CUtensorMap &ta, const CUten
     const __nv_bfloat16 *residual = static_cast<const __nv_bfloat16 *>(residual_v);
     ConvEpi epi{};
     if (sp) epi = ConvEpi{sp->addend, sp->row_scale, sp->col_scale, sp->residual_f32, sp->board_max, sp->fused};
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<128, 16, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static unsigned long long opted = 0;
+    if (cudaError_t e = smem_opt_in(conv3x3_tc_kernel<128, 16, 1, true>, Cfg::SMEM_BYTES, opted); e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     const unsigned tiles = (unsigned)((n_boards + 15) / 16);
     cfg.gridDim = dim3((tiles + 1u) & ~1u, (unsigned)(c_out_total / 128));  // a tile past the batch loads zeros and stores nothing
@@ -868,12 +872,8 @@ cudaError_t launch_encode_im2col(cudaStream_t st, const diee_bg_state *states, i
 cudaError_t launch_heads(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, const float *bp, const float *vfeat,
                          const float *wv, float bv, int n, float *policy_out, float *value_out) {
     if (n <= 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static unsigned long long opted = 0;
+    if (cudaError_t e0 = smem_opt_in(fc_tc_kernel, FC_SMEM_BYTES, opted); e0 != cudaSuccess) return e0;
     dim3 grid((n + 127) / 128, FC_N_PAD / 128);
     fc_tc_kernel<<<grid, CONV_THREADS, FC_SMEM_BYTES, st>>>(ta, tb, n, bp, policy_out);
     cudaError_t e = cudaGetLastError();

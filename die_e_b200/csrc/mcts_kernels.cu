@@ -24,6 +24,9 @@ namespace diee {
 
 constexpr int MCTS_WARPS_PER_CTA = 4;
 constexpr int NO_WINNER = 2;
+#ifndef DIEE_TREE_MINB
+#define DIEE_TREE_MINB 5  // resident CTAs per SM the many-wave instance of the tree kernel is compiled for (see mcts_search_kernel)
+#endif
 constexpr int NODE_PLAYS = 4;                 // plays kept per node from the call that counted them (the ones expand pops first)
 constexpr int ROOT_PLAYS = 128;               // cached plays of the root (a backgammon position has at most ~130)
 constexpr uint32_t NM_UNKNOWN = 0xFFFFFFFFu;  // a node whose legal moves have not been counted yet
@@ -969,8 +972,8 @@ static cudaError_t launch_typed(cudaStream_t st, const void *roots, int n, const
         if (slices == 1) {  // everything on the caller's stream, with timing marks around the two kernels
             if ((e = cudaEventRecord(pipe.t_begin, st)) != cudaSuccess) return e;
             if (n >= 4096 && in_smem) {
-                if ((e = cudaFuncSetAttribute(mcts_search_kernel<G, true, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
-                mcts_search_kernel<G, true, false, 5><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
+                if ((e = cudaFuncSetAttribute(mcts_search_kernel<G, true, false, DIEE_TREE_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess) return e;
+                mcts_search_kernel<G, true, false, DIEE_TREE_MINB><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(
                     r, 0, n, players, cfg, 0u, cfg.iterations, seed, first_game_id, epoch, pool, ln_table, best_out, status_out, stats_out, in_smem, dump);
             } else
             mcts_search_kernel<G, true><<<mcts_grid(n), MCTS_WARPS_PER_CTA * 32, slab_bytes, st>>>(

@@ -301,6 +301,7 @@ lane_pack_kernel(LaneJob job) {
     unsigned long long st_batches = 0, st_lanes = 0, st_polls = 0, st_kind[PC_LISTS] = {0, 0, 0, 0, 0, 0};
     unsigned long long st_cyc[PC_LISTS] = {0, 0, 0, 0, 0, 0}, st_nb[PC_LISTS] = {0, 0, 0, 0, 0, 0};
     unsigned st_kmax = 0;
+    unsigned long long st_same = 0, st_fam = 0;  // plies whose next ply is of the same kind / of another closed-form kind
 #endif
     int polls = 0;
     for (;;) {
@@ -475,6 +476,9 @@ lane_pack_kernel(LaneJob job) {
                     ++k;
                     const bool over = ROLLOUT ? (k == job.limit || (g.off_own == 15 && g.off_opp == 15)) : (k == job.limit || l_winner(g) != 0);
                     newc = over ? PC_TURN : pack_class(g);
+#ifdef DIEE_LANE_STATS
+                    if (newc == c) ++st_same; else if (c != PC_WALK && newc < PC_WALK) ++st_fam;
+#endif
                     if (--reps <= 0 || (c == PC_WALK ? newc != PC_WALK : newc >= PC_WALK)) break;
                 }
             }
@@ -516,6 +520,7 @@ lane_pack_kernel(LaneJob job) {
     if (tid == 0)
         for (int q = 0; q < PC_LISTS; ++q) { atomicAdd(&g_lane_stats2[q], st_cyc[q]); atomicAdd(&g_lane_stats2[8 + q], st_nb[q]); }
     atomicMax(&g_lane_stats[15], (unsigned long long)st_kmax);
+    atomicAdd(&g_lane_stats2[6], st_same); atomicAdd(&g_lane_stats2[7], st_fam);
 #endif
 }
 

@@ -28,3 +28,4 @@ if HAVE and out[0]:
     lib.diee_debug_lane_stats2(out2, 1)
     print("cycles per visit (warp 0 of every CTA): " + ", ".join(f"{k} {out2[i] / max(out2[8 + i], 1):.0f} ({out2[8 + i]})" for i, k in enumerate(kinds)))
     print("longest rollout: %d plies played" % out[15])
+    print(f"next ply of the same kind: {out2[6] / max(out[1], 1):.3f} of the plies; of another closed-form kind: {out2[7] / max(out[1], 1):.3f}")

@@ -293,6 +293,7 @@ lane_pack_kernel(LaneJob job) {
         sm.n_avail = my_slots;
         sm.drain = (long long)gridDim.x * my_slots >= job.n_items ? 1 : 0;  // one wave: every item is resident from the start
     }
+    const bool one_wave = (long long)gridDim.x * my_slots >= job.n_items;
     __syncthreads();
     volatile unsigned *vhead = sm.head, *vtail = sm.tail;
     volatile int *vlock = sm.area_lock;
@@ -446,10 +447,12 @@ lane_pack_kernel(LaneJob job) {
                 for (int w = 0; w < 4; ++w) { g.own[w] = sm.st[w][slot]; g.opp[w] = sm.st[4 + w][slot]; }
                 unpack_misc(g, misc);
                 k = sm.st[9][slot]; gid = sm.st[11][slot]; c3 = sm.st[12][slot];
-                // While the job drains (no new games will come; what is left are the long ones) latency counts, not how full
-                // the warps are: a game stays with its lane while its next ply runs the same code -- any closed-form kind after
-                // a closed-form kind, a walk after a walk -- up to job.reps plies per visit, as in lane_run_kernel.
-                int reps = *vdrain ? job.reps : 1;
+                // A job that is resident from the start (one wave: nothing to refill with, its time is its longest games) is
+                // about latency, not about how full the warps are: there a game stays with its lane while its next ply runs the
+                // same code -- any closed-form kind after a closed-form kind, a walk after a walk -- up to job.reps plies per
+                // visit, as in lane_run_kernel (forced packed run of the 1,024-game rollouts: 1.34 -> 1.18 ms).  In the tail of
+                // a many-wave job it costs lanes (16.4 instead of 17.8 per instruction) and 1-2 % of the time: one ply per visit.
+                int reps = one_wave ? job.reps : 1;
                 for (;;) {
                     uint32_t o[4];
                     l_philox((uint32_t)job.seed, (uint32_t)(job.seed >> 32), k, gid, stream, c3, o);

@@ -71,15 +71,17 @@ def test_packed_rollouts_give_the_same_search(ctx, oracle, monkeypatch, mode):
 
 
 def test_packed_kernel_is_what_a_large_job_runs(ctx, monkeypatch):
-    """65,536 playouts (BASELINE configs[1]): the default picks the packed kernel; same results as the lane-resident one,
-    and the played-plies counter agrees"""
-    n = 65536
+    """160,000 playouts (more than 1,024 items per SM): the default picks the packed kernel; same results as the
+    lane-resident one, and the played-plies counter agrees"""
+    n = 160000
     starts = _opening(n, seed=3)
     monkeypatch.setenv("DIEE_LANE_PACK", "0")
     w0, p0, f0 = ctx.bg_playout(starts, seed=0xD1EE, round_limit=100000, want_finals=True)
     work0 = ctx.search_work()
+    launches0 = ctx.launch_count()
     monkeypatch.delenv("DIEE_LANE_PACK")
     w1, p1, f1 = ctx.bg_playout(starts, seed=0xD1EE, round_limit=100000, want_finals=True)
     work1 = ctx.search_work()
     assert w1.tobytes() == w0.tobytes() and p1.tobytes() == p0.tobytes() and f1.tobytes() == f0.tobytes()
     assert (w1 != 0).all() and work0 == work1 == int(p1.sum())
+    assert ctx.launch_count() - launches0 == 1   # one launch for the whole job

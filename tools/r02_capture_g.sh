@@ -1,5 +1,5 @@
 # round-2 final evidence run (on the GPU box) -> gpurun_out/*_g.*   usage: bash tools/r02_capture_g.sh
-TAG=g
+TAG=${1:-g}
 mkdir -p gpurun_out
 nvidia-smi -L
 python -m pytest tests -q -m gpu > gpurun_out/r02_pytest_gpu_$TAG.txt 2>&1; tail -2 gpurun_out/r02_pytest_gpu_$TAG.txt
@@ -7,8 +7,8 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke_$TAG.t
 ( time python bench.py > gpurun_out/r02_bench_mcts_$TAG.json 2> gpurun_out/r02_bench_mcts_$TAG.err ) 2>&1 | grep real
 python bench.py --impl reference > gpurun_out/r02_bench_ref_$TAG.json 2> gpurun_out/r02_bench_ref_$TAG.err
 python bench.py --workload playout > gpurun_out/r02_bench_playout_$TAG.json 2> gpurun_out/r02_bench_playout_$TAG.err
-python bench.py --workload alpha --precision split3 --no-cpu-baseline > gpurun_out/r02_bench_alpha_split3_$TAG.json 2> gpurun_out/r02_bench_alpha_$TAG.err
-python bench.py --workload alpha --precision bf16 --no-cpu-baseline > gpurun_out/r02_bench_alpha_bf16_$TAG.json 2>> gpurun_out/r02_bench_alpha_$TAG.err
+
+
 # launch lists: the headline step, and the default line with its sub-records (the large batches run lane_pack_kernel)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_mcts_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-subrecords --no-parity-check > gpurun_out/ncu_l1.log 2>&1
 # full captures: the packed rollout kernel on 8,192 games, the lane-resident one and the tree kernel on the headline batch

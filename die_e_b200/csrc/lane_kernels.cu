@@ -271,7 +271,7 @@ __global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32
 // kind and the kernel was only 7 % faster; hence the queues.
 // The plies themselves are the same device functions as above, and a game's dice and choices are keyed by (game id, ply),
 // so who plays a ply changes nothing in what is played.
-template <int MODE>
+template <int MODE, bool ONE_WAVE>
 __global__ void __launch_bounds__(PK_T, 3)
 lane_pack_kernel(LaneJob job) {
     static_assert(MODE == LANE_PLAYOUT || MODE == LANE_ROLLOUT, "the lock-step rollouts are one wave: lane_run_kernel");
@@ -293,7 +293,6 @@ lane_pack_kernel(LaneJob job) {
         sm.n_avail = my_slots;
         sm.drain = (long long)gridDim.x * my_slots >= job.n_items ? 1 : 0;  // one wave: every item is resident from the start
     }
-    const bool one_wave = (long long)gridDim.x * my_slots >= job.n_items;
     __syncthreads();
     volatile unsigned *vhead = sm.head, *vtail = sm.tail;
     volatile int *vlock = sm.area_lock;
@@ -452,7 +451,7 @@ lane_pack_kernel(LaneJob job) {
                 // same code -- any closed-form kind after a closed-form kind, a walk after a walk -- up to job.reps plies per
                 // visit, as in lane_run_kernel (forced packed run of the 1,024-game rollouts: 1.34 -> 1.18 ms).  In the tail of
                 // a many-wave job it costs lanes (16.4 instead of 17.8 per instruction) and 1-2 % of the time: one ply per visit.
-                int reps = one_wave ? job.reps : 1;
+                int reps = ONE_WAVE ? job.reps : 1;
                 for (;;) {
                     uint32_t o[4];
                     l_philox((uint32_t)job.seed, (uint32_t)(job.seed >> 32), k, gid, stream, c3, o);
@@ -482,7 +481,7 @@ lane_pack_kernel(LaneJob job) {
 #ifdef DIEE_LANE_STATS
                     if (newc == c) ++st_same; else if (c != PC_WALK && newc < PC_WALK) ++st_fam;
 #endif
-                    if (--reps <= 0 || (c == PC_WALK ? newc != PC_WALK : newc >= PC_WALK)) break;
+                    if (!ONE_WAVE || --reps <= 0 || (c == PC_WALK ? newc != PC_WALK : newc >= PC_WALK)) break;
                 }
             }
             if (keep) {
@@ -573,8 +572,13 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
             long long per_cta = ((job.n_items + pb - 1) / pb + 31) / 32 * 32;
             job.pack_slots = (int)(per_cta < PK_S ? per_cta : PK_S);
             // (every launch: the attribute is per device, and a process may hold contexts on several)
-            if ((e = cudaFuncSetAttribute(lane_pack_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem))) != cudaSuccess) return e;
-            lane_pack_kernel<MODE><<<(unsigned)pb, PK_T, sizeof(PackSmem), st>>>(job);
+            if (pb * job.pack_slots >= job.n_items) {  // resident from the start (the kernel's ONE_WAVE form: several plies per visit)
+                if ((e = cudaFuncSetAttribute(lane_pack_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem))) != cudaSuccess) return e;
+                lane_pack_kernel<MODE, true><<<(unsigned)pb, PK_T, sizeof(PackSmem), st>>>(job);
+            } else {
+                if ((e = cudaFuncSetAttribute(lane_pack_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem))) != cudaSuccess) return e;
+                lane_pack_kernel<MODE, false><<<(unsigned)pb, PK_T, sizeof(PackSmem), st>>>(job);
+            }
             if (launches) *launches += 1;
             return cudaGetLastError();
         }

@@ -420,6 +420,15 @@ def run_ours(args, rank, world):
     for i in range(args.warmup):
         step_dev(i)
         torch.cuda.synchronize()
+    # W short steps are a few milliseconds -- less than the SM clocks take to come up from idle, and under torchrun the
+    # ranks do not start together: keep stepping (untimed) until 60 ms have passed, so that every rank times steady state
+    extra_warm = 0
+    if args.workload in ("mcts", "playout"):
+        t_w = time.perf_counter()
+        while time.perf_counter() - t_w < 0.06 and extra_warm < 256:
+            step_dev(args.warmup + args.steps + 1000 + extra_warm)
+            torch.cuda.synchronize()
+            extra_warm += 1
 
     # ---- timed: device-resident (`value`) ----
     launches0 = ctx.launch_count()
@@ -633,7 +642,9 @@ def run_ours(args, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": workload_config(args),
             "detail": {"timing": "CUDA events per step on the launch stream, max over ranks; L2 flushed (256 MiB fill) between "
-                                 "timed steps", "wall_s": round(t_wall, 3),
+                                 "timed steps; after the W warm-up steps the loop keeps stepping untimed until 60 ms have "
+                                 "passed (clock ramp, rank start skew)", "extra_warmup_steps": extra_warm,
+                       "wall_s": round(t_wall, 3),
                        "parallelism": f"games sharded over {world} GPU(s) by global game id, no data-path collective; "
                                       "the one exchange step (trajectory all-gather, C ABI over NCCL) is timed under "
                                       "detail.alphazero.exchange", **detail},

@@ -193,6 +193,18 @@ def first_existing(*names):
     return names[-1]
 
 
+def rollout_kernel_name(n_items, playout=False):
+    """which lane kernel the library picks for a job (lane_kernels.cu launch_lane_job): the packed one from 640 rollouts
+    (400 playouts) per SM on, as ONE wave on two CTAs per SM up to 1,024 items per SM"""
+    env = os.environ.get("DIEE_LANE_PACK", "1")
+    sms = 148
+    packed = env == "2" or (env != "0" and n_items >= sms * (400 if playout else 640))
+    if not packed:
+        return "lane_run_kernel (one lane per %s, warp-vote scheduling)" % ("game" if playout else "rollout")
+    one_wave = n_items <= 2 * sms * 512
+    return "lane_pack_kernel (games queued by the code of their next ply; %s)" % ("one wave, two CTAs per SM" if one_wave else "512 resident games per CTA, refilled")
+
+
 def issue_record(name):
     """the issue-side reading of the dominant kernel: profiles/<name> is written by tools/ncu_issue.py from a committed
     ncu --set full export (never measured live: ncu replays kernels), or None"""
@@ -592,7 +604,7 @@ def run_ours(args, rank, world):
                 nominal = 64.0 * plies_per_sim * G * args.iterations
                 roof_extra = {"achieved_counting_closed_form_plies": round(nominal / (roll_ms / 1e3) / 1e9, 2),
                               "frac_counting_closed_form_plies": round(nominal / (roll_ms / 1e3) / 1e9 / hbm_peak, 4)}
-                dominant = ("lane_run_kernel<true> (all rollouts of one search, one lane each)", roll_ms)
+                dominant = (rollout_kernel_name(G * args.iterations) + ": all rollouts of one search", roll_ms)
             else:
                 alg_bytes = b_sim * G * args.iterations  # per launch
         elif args.workload == "playout":
@@ -603,11 +615,19 @@ def run_ours(args, rank, world):
             alg_bytes = 0.0
         traffic, issue = None, None
         if args.workload == "mcts" and dominant and G == 1024 and args.iterations == 100 and args.round_limit == 400:
-            traffic = ncu_traffic(first_existing("r02_lane_run_rollouts_ncu_full_summary.txt", "r01_lane_run_rollouts_v8_ncu_full_summary.txt"))
-            issue = issue_record("r02_lane_run_rollouts_issue.json")
+            if rollout_kernel_name(G * args.iterations).startswith("lane_pack"):
+                traffic = ncu_traffic(first_existing("r02_lane_pack_headline_ncu_full_summary.txt"))
+                issue = issue_record("r02_lane_pack_headline_issue.json")
+            else:
+                traffic = ncu_traffic(first_existing("r02_lane_run_rollouts_ncu_full_summary.txt", "r01_lane_run_rollouts_v8_ncu_full_summary.txt"))
+                issue = issue_record("r02_lane_run_rollouts_issue.json")
         if args.workload == "playout" and G == 65536 and args.round_limit == 400:
-            traffic = ncu_traffic(first_existing("r02_lane_run_playouts_ncu_full_summary.txt", "r01_lane_run_playouts_v8_ncu_full_summary.txt"))
-            issue = issue_record("r02_lane_run_playouts_issue.json")
+            if rollout_kernel_name(G, playout=True).startswith("lane_pack"):
+                traffic = ncu_traffic(first_existing("r02_lane_pack_playouts_ncu_full_summary.txt"))
+                issue = issue_record("r02_lane_pack_playouts_issue.json")
+            else:
+                traffic = ncu_traffic(first_existing("r02_lane_run_playouts_ncu_full_summary.txt", "r01_lane_run_playouts_v8_ncu_full_summary.txt"))
+                issue = issue_record("r02_lane_run_playouts_issue.json")
         avg_launch_ms = float(np.mean(kern_ms))
         achieved = alg_bytes / ((dominant[1] if dominant else avg_launch_ms) / 1e3) / 1e9
         roof = None
@@ -651,13 +671,13 @@ def run_ours(args, rank, world):
             "roofline": roof or {"bound": "hbm", "achieved": round(achieved, 4), "peak": hbm_peak, "unit": "GB/s",
                          "frac": round(achieved / hbm_peak, 8), "traffic": traffic, "peak_source": peak_src,
                          "kernel": (dominant[0] if dominant else "mcts_search_kernel<BgGame> (fused rollouts)") if args.workload == "mcts"
-                         else "lane_run_kernel<false> (whole games, one lane each)",
+                         else rollout_kernel_name(G, playout=True) + ": whole games",
                          **roof_extra, "issue": issue,
                          "note": "achieved = 64 B per ply (32 B state in + 32 B out, SURVEY 8d(1)) x the plies the launch EXECUTES / that "
                                  "kernel's CUDA-event time (plies of a reference-exact rollout after both sides have collected "
                                  "everything are forced passes resolved in closed form: not executed, not counted).  The path is "
-                                 "integer-issue bound, not HBM bound: a game lives in one lane's registers from its first ply to "
-                                 "its last, so the real traffic is 64 B per GAME (`traffic`, ncu); `issue` (from the committed ncu "
+                                 "integer-issue bound, not HBM bound: a game lives on the chip (a lane's registers, or shared memory) from its "
+                                 "first ply to its last, so the real traffic is 64 B per GAME (`traffic`, ncu); `issue` (from the committed ncu "
                                  "export, tools/ncu_issue.py) is the reading that tracks kernel quality"},
             "e2e": {"value": round(e2e_units / e2e_s, 1), "unit": unit, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world},
@@ -704,7 +724,7 @@ def sub_mcts(ctx, ffi, torch, dev, stream, rank, world, G2, cfg, reduce_max, rep
         try:
             tree_ms, roll_ms = ctx.search_timing()
             plies = ctx.search_work()
-            packed = os.environ.get("DIEE_LANE_PACK", "1") != "0" and G2 * its >= 148 * 1024
+            packed = rollout_kernel_name(G2 * its).startswith("lane_pack")
             best_timed = d2_best.cpu().numpy().tobytes()
             old_env = os.environ.get("DIEE_LANE_PACK")
             os.environ["DIEE_LANE_PACK"] = "0" if packed else "2"

@@ -272,7 +272,7 @@ __global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32
 // The plies themselves are the same device functions as above, and a game's dice and choices are keyed by (game id, ply),
 // so who plays a ply changes nothing in what is played.
 template <int MODE, bool ONE_WAVE>
-__global__ void __launch_bounds__(PK_T, 3)
+__global__ void __launch_bounds__(PK_T, ONE_WAVE ? 2 : DIEE_PK_MINB)  // (the one-wave form runs two CTAs per SM, see launch_lane_job)
 lane_pack_kernel(LaneJob job) {
     static_assert(MODE == LANE_PLAYOUT || MODE == LANE_ROLLOUT, "the lock-step rollouts are one wave: lane_run_kernel");
     constexpr bool ROLLOUT = MODE == LANE_ROLLOUT;
@@ -558,17 +558,22 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
     cudaError_t e = cudaMemsetAsync(job.next_item, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     if constexpr (MODE != LANE_ROLLOUT_CC) {
-        // jobs of about a machine-full of resident games and more: the packed form.  Measured on B200, rollouts of a
-        // 100-iteration search, lane-resident / packed: 1,024 games 1.24 / 1.59 ms (one wave, bound by its longest chains: it
-        // stays lane-resident), 2,048 games 1.98 / 1.85, 4,096 3.39 / 2.29, 8,192 6.08 / 3.72, 32,768 22.6 / 12.3, 65,536
-        // 44.7 / 24.0 ms.  DIEE_LANE_PACK=0 keeps the lane-resident kernel, =2 forces the packed one for every job size
-        // (which is how the tests reach it with small batches).
+        // The packed form, for jobs from ~640 items per SM on.  Measured on B200, rollouts of a 100-iteration search,
+        // lane-resident / packed: 512 games 0.93 / 0.91 ms (stays lane-resident), 1,024 games 1.19 / 1.05, 2,048 games
+        // 1.98 / 1.59, 4,096 3.39 / 2.29, 8,192 6.08 / 3.70, 32,768 22.6 / 12.4, 65,536 44.7 / 24.0 ms.
+        // A job that fits two CTAs per SM (up to 1,024 items per SM) runs as ONE wave on two CTAs per SM -- fewer, fuller
+        // CTAs (346 games each for the 1,024-game headline: 1.05 ms against 1.20 ms on three CTAs per SM of 231 games); bigger
+        // jobs take three CTAs per SM with 512 resident games each and refill from the job queue.
+        // DIEE_LANE_PACK=0 keeps the lane-resident kernel, =2 forces the packed one for every job size (which is how the
+        // tests reach it with small batches); DIEE_PACK_MIN = items per SM from which the default picks it.
         const int pack_env = getenv("DIEE_LANE_PACK") ? atoi(getenv("DIEE_LANE_PACK")) : 1;
-        const int pack_bps = getenv("DIEE_PACK_BPS") ? atoi(getenv("DIEE_PACK_BPS")) : 3;
+        const int pack_bps = getenv("DIEE_PACK_BPS") ? atoi(getenv("DIEE_PACK_BPS")) : 0;  // 0 = by job size
+        const int pack_min = getenv("DIEE_PACK_MIN") ? atoi(getenv("DIEE_PACK_MIN")) : (MODE == LANE_PLAYOUT ? 400 : 640);  // (65,536 playouts: 0.936 ms lane-resident, 0.895 ms packed)
         const bool fits = job.n_items < (1ll << 31) && (MODE == LANE_PLAYOUT || (long long)job.n_games * job.iterations < (1ll << 31));
-        if (fits && (pack_env == 2 || (pack_env == 1 && job.n_items >= (long long)sms * 1024))) {
+        if (fits && (pack_env == 2 || (pack_env == 1 && job.n_items >= (long long)sms * pack_min))) {
+            const int bps = pack_bps > 0 ? pack_bps : (job.n_items <= 2ll * sms * PK_S ? 2 : 3);
             long long pb = (job.n_items + 31) / 32;
-            if (pb > (long long)sms * pack_bps) pb = (long long)sms * pack_bps;
+            if (pb > (long long)sms * bps) pb = (long long)sms * bps;
             long long per_cta = ((job.n_items + pb - 1) / pb + 31) / 32 * 32;
             job.pack_slots = (int)(per_cta < PK_S ? per_cta : PK_S);
             // (every launch: the attribute is per device, and a process may hold contexts on several)

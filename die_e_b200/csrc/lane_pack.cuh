@@ -47,7 +47,13 @@ __device__ __forceinline__ int lane_path(const LaneBoard &g) {
 #ifndef DIEE_PK_PATIENCE
 #define DIEE_PK_PATIENCE 4
 #endif
-constexpr int PK_T = 256;        // threads per CTA
+#ifndef DIEE_PK_T
+#define DIEE_PK_T 256
+#endif
+#ifndef DIEE_PK_MINB
+#define DIEE_PK_MINB 3
+#endif
+constexpr int PK_T = DIEE_PK_T;  // threads per CTA
 constexpr int PK_S = DIEE_PK_S;  // resident games per CTA
 constexpr int PK_RING = PK_S <= 512 ? 512 : 1024;  // ring size per queue (a power of two >= PK_S: a game is in one queue at most)
 constexpr int PK_AREAS = 3;      // warps that may run the bear-off walk at a time (one scratch area each)

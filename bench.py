@@ -719,7 +719,7 @@ def sub_mcts(ctx, ffi, torch, dev, stream, rank, world, G2, cfg, reduce_max, rep
     out = {"games_per_gpu": G2, "value": round(reps * G2 * world * its / (ms2 / 1e3), 1), "unit": "simulations/s",
            "ms_per_search": round(ms2 / reps, 4)}
     if not (int(cfg["mode_flags"][0]) & ffi.MODE_ROLLOUT_CHECK_CURRENT):
-        # which rollout kernel ran (lane_kernels.cu: jobs of >= 1,024 rollouts per SM go to the packed kernel), its share of
+        # which rollout kernel ran (lane_kernels.cu: jobs of >= 640 rollouts per SM go to the packed kernel), its share of
         # the search, and that the other kernel finds the same moves on this very batch
         try:
             tree_ms, roll_ms = ctx.search_timing()

@@ -202,7 +202,7 @@ def rollout_kernel_name(n_items, playout=False):
     if not packed:
         return "lane_run_kernel (one lane per %s, warp-vote scheduling)" % ("game" if playout else "rollout")
     one_wave = n_items <= 2 * sms * 512
-    return "lane_pack_kernel (games queued by the code of their next ply; %s)" % ("one wave, two CTAs per SM" if one_wave else "512 resident games per CTA, refilled")
+    return "lane_pack_kernel (games queued by the code of their next ply; %s)" % ("one wave, two CTAs per SM" if one_wave else "three CTAs per SM, up to 512 resident games each, refilled from the job queue")
 
 
 def issue_record(name):

@@ -577,7 +577,9 @@ static cudaError_t launch_lane_job(cudaStream_t st, LaneJob job, int *launches) 
             long long per_cta = ((job.n_items + pb - 1) / pb + 31) / 32 * 32;
             job.pack_slots = (int)(per_cta < PK_S ? per_cta : PK_S);
             // (every launch: the attribute is per device, and a process may hold contexts on several)
-            if (pb * job.pack_slots >= job.n_items) {  // resident from the start (the kernel's ONE_WAVE form: several plies per visit)
+            // resident from the start AND on two CTAs per SM: the kernel's ONE_WAVE form (several plies per visit; compiled for
+            // two CTAs per SM).  A one-wave job on three CTAs per SM (1,024-1,536 items per SM) runs the other instance.
+            if (bps == 2 && pb * job.pack_slots >= job.n_items) {
                 if ((e = cudaFuncSetAttribute(lane_pack_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem))) != cudaSuccess) return e;
                 lane_pack_kernel<MODE, true><<<(unsigned)pb, PK_T, sizeof(PackSmem), st>>>(job);
             } else {

@@ -262,9 +262,9 @@ __global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32
 // coordinates, 13 words per game, [word][slot] -- and wait in one of six queues: two dice | doubles | bar entries | bear-off
 // table | bear-off walk | turnover (write the result, take the next item of the job).  A warp takes 32 games off the
 // longest queue, plays ONE ply of each -- 32 lanes in the same code -- and appends every game to the queue of its next ply.
-// There is no block barrier: the queues are rings of slot numbers with a reserved-then-written protocol (the producer adds
-// to `tail`, writes the game, then the ring entry; a consumer moves `head` by compare-and-swap and waits for each entry to
-// leave its EMPTY value).  512 resident games per 8 warps guarantee a full queue somewhere while the job lasts (256 in
+// There is no block barrier: the queues are rings of slot numbers whose cells are one-entry mailboxes (the producer adds
+// to `tail`, writes the game, then puts the slot number into its cell; a consumer moves `head` by compare-and-swap and takes
+// its cells, waiting where nothing has been put yet -- lane_pack.cuh ring_put / ring_take).  512 resident games per 8 warps guarantee a full queue somewhere while the job lasts (256 in
 // flight leaves 256 waiting in six queues); when nothing is full for a few polls -- the tail of the job -- a warp takes
 // what there is (1 / 2 / 4 / 16 polls: 3.70 / 3.70 / 3.70 / 3.92 ms for the rollouts of 8,192 games).  The first form of this kernel sorted the whole CTA between two barriers every ply: 35 instead of 66 warp
 // instructions per ply at 19.3 lanes per instruction, but 8 of 12 stalled warps sat at the barrier behind the slowest
@@ -282,10 +282,10 @@ lane_pack_kernel(LaneJob job) {
     const uint32_t stream = ROLLOUT ? DIEE_STREAM_ROLLOUT : DIEE_STREAM_GAME;
     // every slot starts in the turnover queue without a game: "take one"
     for (int s = tid; s < PK_S; s += PK_T) sm.st[8][s] = 0;
-    for (int i = tid; i < PC_LISTS * PK_RING; i += PK_T) (&sm.ring[0][0])[i] = (uint16_t)PK_EMPTY;
+    for (int i = tid; i < PC_LISTS * PK_RING; i += PK_T) (&sm.ring[0][0])[i] = PK_EMPTY;
     __syncthreads();
     const int my_slots = job.pack_slots;  // (the others stay dead: a job smaller than the machine is spread over all CTAs)
-    for (int s = tid; s < my_slots; s += PK_T) sm.ring[PC_TURN][s] = (uint16_t)s;
+    for (int s = tid; s < my_slots; s += PK_T) sm.ring[PC_TURN][s] = (unsigned)s;
     if (tid < 8) { sm.head[tid] = 0; sm.tail[tid] = tid == PC_TURN ? (unsigned)my_slots : 0u; }
     if (tid < 4) sm.area_lock[tid] = 0;
     if (tid == 0) {
@@ -353,13 +353,7 @@ lane_pack_kernel(LaneJob job) {
         const bool act = lane < take;
         int slot = 0;
         if (act) {
-            volatile uint16_t *e = &sm.ring[c][(h + (unsigned)lane) & (PK_RING - 1)];
-            unsigned v;
-            unsigned spins = 0;
-            while ((v = *e) == PK_EMPTY)  // reserved, not written yet (a handful of cycles; a lost entry must not hang the device)
-                if (++spins > (1u << 28)) __trap();
-            *e = (uint16_t)PK_EMPTY;
-            slot = (int)v;
+            slot = (int)ring_take(&sm.ring[c][(h + (unsigned)lane) & (PK_RING - 1)]);
         }
         __threadfence_block();
         __syncwarp();
@@ -507,8 +501,7 @@ lane_pack_kernel(LaneJob job) {
             }
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (newc >= 0 && newc < PC_LISTS) {
-                volatile uint16_t *e = &sm.ring[newc][(base + (unsigned)__popc(same & ((1u << lane) - 1u))) & (PK_RING - 1)];
-                *e = (uint16_t)slot;
+                ring_put(&sm.ring[newc][(base + (unsigned)__popc(same & ((1u << lane) - 1u))) & (PK_RING - 1)], (unsigned)slot);
             }
         }
     }

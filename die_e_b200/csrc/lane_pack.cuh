@@ -61,18 +61,37 @@ constexpr int PK_PATIENCE = DIEE_PK_PATIENCE;  // polls without a full queue bef
 constexpr int PK_WORDS = 13;
 enum { PC_TWO = 0, PC_DBL, PC_BAR, PC_TABLE, PC_WALK, PC_TURN, PC_LISTS, PC_DEAD = PC_LISTS };
 constexpr uint32_t PK_HAS_GAME = 1u << 24;
-constexpr unsigned PK_EMPTY = 0xFFFFu;
+constexpr unsigned PK_EMPTY = 0xFFFFFFFFu;
 
 struct PackSmem {
     uint32_t st[PK_WORDS][PK_S];        // own[4], opp[4], misc, ply, item, game id, counter word 3
     uint32_t scr[PK_AREAS][L_SCRATCH][32];
-    uint16_t ring[PC_LISTS][PK_RING];
+    unsigned ring[PC_LISTS][PK_RING];     // slot numbers, or PK_EMPTY; every cell is a one-entry mailbox (ring_put / ring_take)
     unsigned head[8], tail[8];
     int area_lock[4];
     int n_dead;
     int n_avail;  // games waiting in the queues (what an idle warp polls)
     int drain;    // the job has no more items: take what there is, at once
 };
+
+// A ring cell is a mailbox: a producer puts a slot number into an EMPTY cell (compare-and-swap), a consumer takes whatever
+// is there and leaves EMPTY behind (exchange).  Positions are handed out by `tail` (atomic add) and `head` (compare-and-swap
+// over what `tail` shows), so a cell's consumer may arrive before its producer has written (it waits), and -- when a
+// consumer is slow to read what it claimed while the other warps recycle games through the same ring -- the producer of
+// position p + PK_RING may arrive before the consumer of position p has taken its entry (it waits, too).  Entries of one
+// ring are interchangeable (slots whose next ply is of that kind), so which of two waiting consumers gets which entry does
+// not matter; every entry put is taken exactly once (tests/ring_model.cpp runs the same protocol with host threads).
+__device__ __forceinline__ void ring_put(unsigned *cell, unsigned slot) {
+    unsigned spins = 0;
+    while (atomicCAS(cell, PK_EMPTY, slot) != PK_EMPTY)
+        if (++spins > (1u << 28)) __trap();
+}
+__device__ __forceinline__ unsigned ring_take(unsigned *cell) {
+    unsigned v, spins = 0;
+    while ((v = atomicExch(cell, PK_EMPTY)) == PK_EMPTY)  // reserved, not written yet (a lost entry must not hang the device)
+        if (++spins > (1u << 28)) __trap();
+    return v;
+}
 
 __device__ __forceinline__ int pack_class(const LaneBoard &g) {
     if (lane_path(g) == PATH_WALK) return PC_WALK;

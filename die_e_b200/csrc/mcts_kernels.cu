@@ -629,9 +629,9 @@ cc_search_kernel(const diee_bg_state *__restrict__ roots, int n, const int8_t *_
     int n_mine = (n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     n_mine = n_mine < 0 ? 0 : (n_mine > my_slots ? my_slots : n_mine);
     for (int s = tid; s < PK_S; s += PK_T) { sm.st[8][s] = 0; sm.st[10][s] = 0; sm.st[11][s] = (uint32_t)(s * (int)gridDim.x + (int)blockIdx.x); }
-    for (int i = tid; i < PC_LISTS * PK_RING; i += PK_T) (&sm.ring[0][0])[i] = (uint16_t)PK_EMPTY;
+    for (int i = tid; i < PC_LISTS * PK_RING; i += PK_T) (&sm.ring[0][0])[i] = PK_EMPTY;
     __syncthreads();
-    for (int s = tid; s < n_mine; s += PK_T) sm.ring[PC_TURN][s] = (uint16_t)s;  // every game starts with a tree step
+    for (int s = tid; s < n_mine; s += PK_T) sm.ring[PC_TURN][s] = (unsigned)s;  // every game starts with a tree step
     if (tid < 8) { sm.head[tid] = 0; sm.tail[tid] = tid == PC_TURN ? (unsigned)n_mine : 0u; }
     if (tid < 4) sm.area_lock[tid] = 0;
     if (tid == 0) { sm.n_dead = PK_S - n_mine; sm.n_avail = n_mine; sm.drain = 1; }
@@ -677,13 +677,7 @@ cc_search_kernel(const diee_bg_state *__restrict__ roots, int n, const int8_t *_
         const bool act = lane < take;
         int slot = 0;
         if (act) {
-            volatile uint16_t *e = &sm.ring[c][(h + (unsigned)lane) & (PK_RING - 1)];
-            unsigned v;
-            unsigned spins = 0;
-            while ((v = *e) == PK_EMPTY)
-                if (++spins > (1u << 28)) __trap();
-            *e = (uint16_t)PK_EMPTY;
-            slot = (int)v;
+            slot = (int)ring_take(&sm.ring[c][(h + (unsigned)lane) & (PK_RING - 1)]);
         }
         __threadfence_block();
         __syncwarp();
@@ -799,8 +793,7 @@ cc_search_kernel(const diee_bg_state *__restrict__ roots, int n, const int8_t *_
             }
             base = __shfl_sync(FULL, base, leader);
             if (newc >= 0 && newc < PC_LISTS) {
-                volatile uint16_t *e = &sm.ring[newc][(base + (unsigned)__popc(same & ((1u << lane) - 1u))) & (PK_RING - 1)];
-                *e = (uint16_t)slot;
+                ring_put(&sm.ring[newc][(base + (unsigned)__popc(same & ((1u << lane) - 1u))) & (PK_RING - 1)], (unsigned)slot);
             }
         }
     }

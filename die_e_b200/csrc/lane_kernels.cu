@@ -263,11 +263,13 @@ __global__ void bg_rollout_count_kernel(int n_games, uint32_t iterations, uint32
 // table | bear-off walk | turnover (write the result, take the next item of the job).  A warp takes 32 games off the
 // longest queue, plays ONE ply of each -- 32 lanes in the same code -- and appends every game to the queue of its next ply.
 // There is no block barrier: the queues are rings of slot numbers whose cells are one-entry mailboxes (the producer adds
-// to `tail`, writes the game, then puts the slot number into its cell; a consumer moves `head` by compare-and-swap and takes
-// its cells, waiting where nothing has been put yet -- lane_pack.cuh ring_put / ring_take).  512 resident games per 8 warps guarantee a full queue somewhere while the job lasts (256 in
-// flight leaves 256 waiting in six queues); when nothing is full for a few polls -- the tail of the job -- a warp takes
-// what there is (1 / 2 / 4 / 16 polls: 3.70 / 3.70 / 3.70 / 3.92 ms for the rollouts of 8,192 games).  The first form of this kernel sorted the whole CTA between two barriers every ply: 35 instead of 66 warp
-// instructions per ply at 19.3 lanes per instruction, but 8 of 12 stalled warps sat at the barrier behind the slowest
+// to `tail`, writes the game, then puts the slot number into its cell; a consumer moves `head` by compare-and-swap and
+// takes its cells, waiting where nothing has been put yet -- lane_pack.cuh ring_put / ring_take).  512 resident games
+// per 8 warps guarantee a full queue somewhere while the job lasts (256 in flight leaves 256 waiting in six queues);
+// when nothing is full for a few polls -- the tail of the job -- a warp takes what there is (1 / 2 / 4 / 16 polls:
+// 3.70 / 3.70 / 3.70 / 3.92 ms for the rollouts of 8,192 games).  The first form of this kernel sorted the whole CTA
+// between two barriers every ply: 35 instead of 66 warp instructions per ply at 19.3 lanes per instruction, but 8 of 12
+// stalled warps sat at the barrier behind the slowest
 // kind and the kernel was only 7 % faster; hence the queues.
 // The plies themselves are the same device functions as above, and a game's dice and choices are keyed by (game id, ply),
 // so who plays a ply changes nothing in what is played.

@@ -35,3 +35,29 @@ def test_reference_arm_line_mcts():
 def test_reference_arm_line_playout():
     d = _run("--workload", "playout")
     assert d["impl"] == "reference" and d["metric"] == "playout_plies_per_sec" and d["unit"] == "plies/s" and d["value"] > 0
+
+
+def test_bench_names_the_rollout_kernel_the_library_picks():
+    """bench.rollout_kernel_name mirrors launch_lane_job (lane_kernels.cu): the thresholds there must be the ones here"""
+    import re
+    sys.path.insert(0, ROOT)
+    import bench
+    src = open(os.path.join(ROOT, "die_e_b200", "csrc", "lane_kernels.cu")).read()
+    m = re.search(r"MODE == LANE_PLAYOUT \? (\d+) : (\d+)\);", src)
+    assert m and (int(m.group(1)), int(m.group(2))) == (400, 640)
+    assert "job.n_items <= 2ll * sms * PK_S ? 2 : 3" in src
+    hdr = open(os.path.join(ROOT, "die_e_b200", "csrc", "lane_pack.cuh")).read()
+    assert re.search(r"#define DIEE_PK_S 512", hdr)
+    old = os.environ.pop("DIEE_LANE_PACK", None)
+    try:
+        assert bench.rollout_kernel_name(512 * 100).startswith("lane_run_kernel")            # 51,200 < 148 * 640
+        assert "one wave" in bench.rollout_kernel_name(1024 * 100)                           # the headline batch
+        assert "refilled" in bench.rollout_kernel_name(8192 * 100)
+        assert bench.rollout_kernel_name(32768, playout=True).startswith("lane_run_kernel")  # < 148 * 400
+        assert "one wave" in bench.rollout_kernel_name(65536, playout=True)
+        os.environ["DIEE_LANE_PACK"] = "0"
+        assert bench.rollout_kernel_name(8192 * 100).startswith("lane_run_kernel")
+    finally:
+        os.environ.pop("DIEE_LANE_PACK", None)
+        if old is not None:
+            os.environ["DIEE_LANE_PACK"] = old

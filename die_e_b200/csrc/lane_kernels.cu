@@ -307,10 +307,15 @@ lane_pack_kernel(LaneJob job) {
 #endif
     int polls = 0;
     for (;;) {
-        if (*vdead >= PK_S) break;
-        if (*vavail <= 0) {  // nothing waits anywhere: a cheap poll (idle warps share the issue slots with the busy ones)
+        // one lane reads the CTA's counters and the warp agrees on them: what follows must be decided warp-uniformly
+        unsigned ctl = 0;
+        if (lane == 0) ctl = (unsigned)*vdead | ((*vavail > 0 ? 1u : 0u) << 16) | ((*vdrain ? 1u : 0u) << 17);
+        ctl = __shfl_sync(0xFFFFFFFFu, ctl, 0);
+        const bool draining = (ctl >> 17) & 1u;
+        if ((ctl & 0xFFFFu) >= (unsigned)PK_S) break;
+        if (!((ctl >> 16) & 1u)) {  // nothing waits anywhere: a cheap poll (idle warps share the issue slots with the busy ones)
             ++polls;
-            __nanosleep(*vdrain ? 40u : 200u);
+            __nanosleep(draining ? 40u : 200u);
             continue;
         }
         // ---- the longest queue ----
@@ -324,7 +329,7 @@ lane_pack_kernel(LaneJob job) {
         const unsigned best = __reduce_max_sync(0xFFFFFFFFu, (cnt << 3) | (unsigned)(lane & 7));
         const int c = (int)(best & 7u);
         const int avail = (int)(best >> 3);
-        const int take = avail >= 32 ? 32 : ((polls >= PK_PATIENCE || *vdrain) ? avail : 0);
+        const int take = avail >= 32 ? 32 : ((polls >= PK_PATIENCE || draining) ? avail : 0);
         if (take == 0) {
             ++polls;
 #ifdef DIEE_LANE_STATS

@@ -641,8 +641,11 @@ cc_search_kernel(const diee_bg_state *__restrict__ roots, int n, const int8_t *_
     volatile int *vdead = &sm.n_dead, *vavail = &sm.n_avail;
     const size_t cap = (size_t)cfg.iterations + 1;
     for (;;) {
-        if (*vdead >= PK_S) break;
-        if (*vavail <= 0) { __nanosleep(40u); continue; }
+        unsigned ctl = 0;  // (one lane reads the CTA's counters, the warp agrees on them)
+        if (lane == 0) ctl = (unsigned)*vdead | ((*vavail > 0 ? 1u : 0u) << 16);
+        ctl = __shfl_sync(FULL, ctl, 0);
+        if ((ctl & 0xFFFFu) >= (unsigned)PK_S) break;
+        if (!((ctl >> 16) & 1u)) { __nanosleep(40u); continue; }
         // ---- the longest queue; whatever it holds is taken at once (every game of the search is resident: nothing to wait for)
         unsigned cnt = 0;
         if (lane < PC_LISTS) {
